@@ -1,0 +1,230 @@
+"""cognn_b200 -- B200-native share-local engine for CoGNN's secret-shared GCN path.
+
+The product is libcognn_b200.so (hand-written sm_100a CUDA behind the C ABI of include/cognn_b200.h) plus the C++
+host engine in cognn_b200/host.  This Python package is plumbing for tests and bench.py: it binds the C ABI with
+ctypes and lets torch own device buffers / streams / process groups.  u64 shares are stored in torch.int64 tensors
+(same bits).
+"""
+import ctypes as C
+
+from . import _lib
+from ._lib import CgbError, LIB_PATH, SIGNATURES, load  # noqa: F401
+
+SCALER_BITS = 16
+NO_ROW = 0xFFFFFFFF
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Csr:
+    def __init__(self, ctx, handle, n_rows, n_edges, n_src_rows):
+        self.ctx, self.handle = ctx, handle
+        self.n_rows, self.n_edges, self.n_src_rows = n_rows, n_edges, n_src_rows
+
+    def destroy(self):
+        if self.handle is not None:
+            self.ctx.lib.cgb_csr_destroy(self.ctx.handle, self.handle)
+            self.handle = None
+
+
+class Context:
+    """One cgb_ctx bound to a CUDA device and (by default) torch's current stream."""
+
+    def __init__(self, device=0, own_stream=False):
+        import torch
+
+        self.torch = torch
+        self.lib = load()
+        self.device = int(device)
+        h = C.c_void_p()
+        if own_stream:
+            rc = self.lib.cgb_ctx_create(self.device, C.byref(h))
+        else:
+            with torch.cuda.device(self.device):
+                stream = torch.cuda.current_stream().cuda_stream
+            rc = self.lib.cgb_ctx_create_on_stream(self.device, C.c_void_p(stream), C.byref(h))
+        if rc != 0:
+            raise CgbError(f"cgb_ctx_create failed ({rc}): {self.lib.cgb_last_error(None).decode()}")
+        self.handle = h
+
+    # -- helpers ---------------------------------------------------------------------------------------------
+    def check(self, rc):
+        if rc != 0:
+            raise CgbError(f"cgb error {rc}: {self.lib.cgb_last_error(self.handle).decode()}")
+
+    def close(self):
+        if self.handle is not None:
+            self.lib.cgb_ctx_destroy(self.handle)
+            self.handle = None
+
+    def sync(self):
+        self.check(self.lib.cgb_ctx_sync(self.handle))
+
+    @property
+    def launches(self):
+        return int(self.lib.cgb_ctx_launch_count(self.handle))
+
+    def _dev(self):
+        return self.torch.device("cuda", self.device)
+
+    def empty(self, *shape):
+        return self.torch.empty(*shape, dtype=self.torch.int64, device=self._dev())
+
+    def _u64(self, t):
+        assert t.dtype == self.torch.int64 and t.is_cuda and t.is_contiguous(), "expect contiguous cuda int64"
+        return t
+
+    # -- (1) gather --------------------------------------------------------------------------------------------
+    def csr_create(self, rowptr, col, n_src_rows):
+        """rowptr/col: int32 torch tensors (cuda -> device path, cpu -> host path)."""
+        t = self.torch
+        n_rows = rowptr.numel() - 1
+        n_edges = col.numel()
+        h = C.c_void_p()
+        assert rowptr.dtype == t.int32 and col.dtype == t.int32
+        rowptr, col = rowptr.contiguous(), col.contiguous()
+        fn = self.lib.cgb_csr_create_device if rowptr.is_cuda else self.lib.cgb_csr_create
+        self.check(fn(self.handle, _ptr(rowptr), _ptr(col), n_rows, n_edges, n_src_rows, C.byref(h)))
+        return Csr(self, h, n_rows, n_edges, n_src_rows)
+
+    def gather_sum(self, csr, x, delta=None, out=None):
+        D = x.shape[1]
+        assert x.shape[0] == csr.n_src_rows
+        if out is None:
+            out = self.empty(csr.n_rows, D)
+        self.check(self.lib.cgb_gather_sum(self.handle, csr.handle, _ptr(self._u64(x)),
+                                           _ptr(delta), _ptr(self._u64(out)), D))
+        return out
+
+    def expand_rows(self, idx, x, delta=None, out=None):
+        D = x.shape[1]
+        n_out = idx.numel()
+        assert idx.dtype == self.torch.int32 and idx.is_cuda
+        if out is None:
+            out = self.empty(n_out, D)
+        self.check(self.lib.cgb_expand_rows(self.handle, _ptr(idx), n_out, _ptr(self._u64(x)), _ptr(delta),
+                                            _ptr(out), D))
+        return out
+
+    def segsum(self, segptr, inp, dup):
+        D = inp.shape[1]
+        n_seg = segptr.numel() - 1
+        assert segptr.dtype == self.torch.int32 and segptr.is_cuda
+        out = self.empty(inp.shape[0] if dup else n_seg, D)
+        self.check(self.lib.cgb_segsum(self.handle, _ptr(segptr), n_seg, inp.shape[0], _ptr(self._u64(inp)),
+                                       _ptr(out), D, 1 if dup else 0))
+        return out
+
+    # -- (2) matmul --------------------------------------------------------------------------------------------
+    def matmul(self, A, B, transA=False, out=None, accumulate=False):
+        if transA:
+            K, M = A.shape
+        else:
+            M, K = A.shape
+        assert B.shape[0] == K
+        N = B.shape[1]
+        if out is None:
+            assert not accumulate
+            out = self.empty(M, N)
+        self.check(self.lib.cgb_matmul(self.handle, _ptr(self._u64(A)), _ptr(self._u64(B)), _ptr(self._u64(out)),
+                                       M, K, N, int(transA), int(accumulate)))
+        return out
+
+    def beaver_matmul_finish(self, E, F, U, V, Z, share, f=SCALER_BITS):
+        M, K = E.shape
+        N = F.shape[1]
+        out = self.empty(M, N)
+        self.check(self.lib.cgb_beaver_matmul_finish(self.handle, _ptr(self._u64(E)), _ptr(self._u64(F)),
+                                                     _ptr(self._u64(U)), _ptr(self._u64(V)), _ptr(self._u64(Z)),
+                                                     _ptr(out), M, K, N, share, f))
+        return out
+
+    # -- (3) elementwise ---------------------------------------------------------------------------------------
+    def add(self, a, b, out=None):
+        out = self.torch.empty_like(a) if out is None else out
+        self.check(self.lib.cgb_add(self.handle, _ptr(self._u64(a)), _ptr(self._u64(b)), _ptr(out), a.numel()))
+        return out
+
+    def sub(self, a, b, out=None):
+        out = self.torch.empty_like(a) if out is None else out
+        self.check(self.lib.cgb_sub(self.handle, _ptr(self._u64(a)), _ptr(self._u64(b)), _ptr(out), a.numel()))
+        return out
+
+    def trunc(self, x, share, f=SCALER_BITS, out=None):
+        out = self.torch.empty_like(x) if out is None else out
+        self.check(self.lib.cgb_trunc(self.handle, _ptr(self._u64(x)), _ptr(out), x.numel(), f, share))
+        return out
+
+    def scale_public(self, x, c, share, f=SCALER_BITS, out=None):
+        out = self.torch.empty_like(x) if out is None else out
+        self.check(self.lib.cgb_scale_public(self.handle, _ptr(self._u64(x)), C.c_uint64(c & (2**64 - 1)), _ptr(out),
+                                             x.numel(), f, share))
+        return out
+
+    def apply_gradient(self, W, d, lr, share, f=SCALER_BITS, out=None):
+        out = self.torch.empty_like(W) if out is None else out
+        self.check(self.lib.cgb_apply_gradient(self.handle, _ptr(self._u64(W)), _ptr(self._u64(d)),
+                                               C.c_uint64(lr & (2**64 - 1)), _ptr(out), W.numel(), f, share))
+        return out
+
+    def rowmul_beaver_finish(self, e, fv, a, b, c, share, f=SCALER_BITS, out=None):
+        rows, D = e.shape
+        out = self.torch.empty_like(e) if out is None else out
+        self.check(self.lib.cgb_rowmul_beaver_finish(self.handle, _ptr(self._u64(e)), _ptr(self._u64(fv)),
+                                                     _ptr(self._u64(a)), _ptr(self._u64(b)), _ptr(self._u64(c)),
+                                                     _ptr(out), rows, D, share, f))
+        return out
+
+    def cond_add(self, v, u, cond, out=None):
+        rows, D = v.shape
+        assert cond.dtype == self.torch.uint8 and cond.is_cuda
+        out = self.torch.empty_like(v) if out is None else out
+        self.check(self.lib.cgb_cond_add(self.handle, _ptr(self._u64(v)), _ptr(self._u64(u)), _ptr(cond), _ptr(out),
+                                         rows, D))
+        return out
+
+    def transpose(self, x):
+        rows, cols = x.shape
+        out = self.empty(cols, rows)
+        self.check(self.lib.cgb_transpose(self.handle, _ptr(self._u64(x)), _ptr(out), rows, cols))
+        return out
+
+    def encode(self, x, f=SCALER_BITS):
+        assert x.dtype == self.torch.float64 and x.is_cuda and x.is_contiguous()
+        out = self.torch.empty(x.shape, dtype=self.torch.int64, device=x.device)
+        self.check(self.lib.cgb_encode(self.handle, _ptr(x), _ptr(out), x.numel(), f))
+        return out
+
+    def decode(self, v, f=SCALER_BITS):
+        out = self.torch.empty(v.shape, dtype=self.torch.float64, device=v.device)
+        self.check(self.lib.cgb_decode(self.handle, _ptr(self._u64(v)), _ptr(out), v.numel(), f))
+        return out
+
+    def share_split(self, x, key, stream, word_offset=0, f=SCALER_BITS):
+        assert x.dtype == self.torch.float64 and x.is_cuda and x.is_contiguous()
+        s0 = self.torch.empty(x.shape, dtype=self.torch.int64, device=x.device)
+        s1 = self.torch.empty_like(s0)
+        self.check(self.lib.cgb_share_split(self.handle, _ptr(x), x.numel(), f, _lib.key_array(key), stream,
+                                            word_offset, _ptr(s0), _ptr(s1)))
+        return s0, s1
+
+    def open_decode(self, s0, s1, f=SCALER_BITS):
+        out = self.torch.empty(s0.shape, dtype=self.torch.float64, device=s0.device)
+        self.check(self.lib.cgb_open_decode(self.handle, _ptr(self._u64(s0)), _ptr(self._u64(s1)), _ptr(out),
+                                            s0.numel(), f))
+        return out
+
+    # -- (4) PRG -----------------------------------------------------------------------------------------------
+    def prg_fill(self, key, stream, word_offset, n_words, out=None):
+        if out is None:
+            out = self.empty(n_words)
+        self.check(self.lib.cgb_prg_fill(self.handle, _lib.key_array(key), stream, word_offset, _ptr(out), n_words))
+        return out
+
+    def prg_mask_sub(self, key, stream, word_offset, x, out=None):
+        out = self.torch.empty_like(x) if out is None else out
+        self.check(self.lib.cgb_prg_mask_sub(self.handle, _lib.key_array(key), stream, word_offset,
+                                             _ptr(self._u64(x)), _ptr(out), x.numel()))
+        return out

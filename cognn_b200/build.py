@@ -1,0 +1,73 @@
+"""Builds libcognn_b200.so (hand-written sm_100a CUDA kernels + the C ABI) in-tree with nvcc.
+
+The built .so stays next to this file (git-ignored, but it travels to the GPU box with the gpurun snapshot).
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libcognn_b200.so")
+SOURCES = ["capi.cu", "gather.cu", "matmul.cu", "elementwise.cu", "prg.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _host_cxx():
+    for cand in ("/usr/bin/g++", shutil.which("g++")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("g++ not found")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [
+        os.path.join(CSRC, "common.cuh"),
+        os.path.join(HERE, "..", "include", "cognn_b200.h"),
+        os.path.abspath(__file__),
+    ]
+    if not force and not _stale(LIB, deps):
+        return LIB
+    objs = []
+    flags = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", _host_cxx(),
+                    "--expt-relaxed-constexpr", "--extended-lambda"]
+    if verbose:
+        flags += ["-Xptxas", "-v"]
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    procs = []
+    for s in SOURCES:
+        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        objs.append(o)
+        cmd = [_nvcc()] + flags + ["-c", os.path.join(CSRC, s), "-o", o]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(out)
+        if p.returncode != 0:
+            failed = True
+    if failed:
+        raise RuntimeError("nvcc failed")
+    cmd = [_nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-ccbin", _host_cxx(), "-lcudart"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

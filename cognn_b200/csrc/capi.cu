@@ -1,0 +1,144 @@
+// capi.cu -- context, memory and error plumbing of the C ABI (include/cognn_b200.h).
+//
+// The reference reports errors with printf + exit(-1) (ss_vertex_centric_algo_kernel.h:794-797, 869-872) and has
+// no device code; here every entry point returns a status and the C++ shim in cognn_b200/host reproduces the
+// reference behaviour on top.  There is deliberately no CPU fallback: without a CUDA device context creation fails.
+#include <mutex>
+
+#include "common.cuh"
+
+static thread_local std::string g_last_error;
+
+int cgb_scratch_reserve(cgb_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return CGB_OK;
+    CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&ctx->scratch, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&ctx->scratch, want);
+    }
+    if (e != cudaSuccess) return cgb_fail(ctx, CGB_ERR_NOMEM, "cgb_scratch_reserve", cudaGetErrorString(e));
+    ctx->scratch_bytes = want;
+    return CGB_OK;
+}
+
+extern "C" {
+
+const char* cgb_version(void) { return "cognn_b200 0.1 (sm_100a)"; }
+
+int cgb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int cgb_ctx_create_on_stream(int device, void* cuda_stream, cgb_ctx** out) {
+    if (!out) return CGB_ERR_INVALID;
+    *out = nullptr;
+    int n = cgb_device_count();
+    if (n <= 0 || device < 0 || device >= n) {
+        g_last_error = "cgb_ctx_create: no CUDA device (this library has no CPU fallback)";
+        return CGB_ERR_NO_DEVICE;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        g_last_error = "cgb_ctx_create: cudaSetDevice failed";
+        return CGB_ERR_CUDA;
+    }
+    cgb_ctx* c = new cgb_ctx();
+    c->device = device;
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+    *out = c;
+    return CGB_OK;
+}
+
+int cgb_ctx_create(int device, cgb_ctx** out) {
+    int rc = cgb_ctx_create_on_stream(device, nullptr, out);
+    if (rc) return rc;
+    cudaStream_t s;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) {
+        delete *out;
+        *out = nullptr;
+        g_last_error = "cgb_ctx_create: cudaStreamCreate failed";
+        return CGB_ERR_CUDA;
+    }
+    (*out)->stream = s;
+    (*out)->own_stream = true;
+    return CGB_OK;
+}
+
+int cgb_ctx_destroy(cgb_ctx* ctx) {
+    if (!ctx) return CGB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return CGB_OK;
+}
+
+int cgb_ctx_sync(cgb_ctx* ctx) {
+    CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CGB_OK;
+}
+void* cgb_ctx_stream(cgb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+const char* cgb_last_error(cgb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+uint64_t cgb_ctx_launch_count(cgb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cgb_malloc(cgb_ctx* ctx, size_t bytes, void** d_out) {
+    CGB_REQUIRE(ctx, d_out, "cgb_malloc: null argument");
+    CGB_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(d_out, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return cgb_fail(ctx, CGB_ERR_NOMEM, "cgb_malloc", cudaGetErrorString(e));
+    }
+    return CGB_OK;
+}
+int cgb_free(cgb_ctx* ctx, void* d_ptr) {
+    if (!d_ptr) return CGB_OK;
+    CGB_CHECK_CUDA(ctx, cudaFree(d_ptr));
+    return CGB_OK;
+}
+int cgb_host_alloc(size_t bytes, void** h_out) {
+    if (!h_out) return CGB_ERR_INVALID;
+    cudaError_t e = cudaMallocHost(h_out, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        g_last_error = std::string("cgb_host_alloc: ") + cudaGetErrorString(e);
+        return CGB_ERR_NOMEM;
+    }
+    return CGB_OK;
+}
+int cgb_host_free(void* h_ptr) {
+    if (h_ptr) cudaFreeHost(h_ptr);
+    return CGB_OK;
+}
+int cgb_memset(cgb_ctx* ctx, void* d_ptr, int value, size_t bytes) {
+    CGB_CHECK_CUDA(ctx, cudaMemsetAsync(d_ptr, value, bytes, ctx->stream));
+    return CGB_OK;
+}
+int cgb_h2d(cgb_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+    CGB_CHECK_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return CGB_OK;
+}
+int cgb_d2h(cgb_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+    CGB_CHECK_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return CGB_OK;
+}
+int cgb_d2d(cgb_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
+    CGB_CHECK_CUDA(ctx, cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return CGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// common.cuh -- shared definitions for the sm_100a kernels behind include/cognn_b200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/cognn_b200.h"
+
+struct cgb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    std::string err;
+    uint64_t launches = 0;
+    // grow-only device scratch (split-K accumulators, Beaver temporaries)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+struct cgb_csr {
+    uint32_t n_rows = 0;
+    uint32_t n_src_rows = 0;
+    uint64_t n_edges = 0;
+    uint32_t* d_rowptr = nullptr;  // n_rows + 1
+    uint32_t* d_col = nullptr;     // n_edges
+    // rows with more than CGB_LONG_ROW edges are cut into slices of CGB_SLICE_EDGES edges
+    uint32_t n_long_rows = 0;
+    uint32_t n_slices = 0;
+    uint32_t* d_slice_row = nullptr;    // n_slices: destination row
+    uint32_t* d_slice_begin = nullptr;  // n_slices: first edge
+    uint32_t* d_slice_first = nullptr;  // n_slices: index of the row's first slice
+    uint32_t* d_slice_count = nullptr;  // n_slices: number of slices of the row
+    uint32_t* d_long_id = nullptr;      // n_slices: dense id of the long row (counter index)
+    uint32_t* d_counters = nullptr;     // n_long_rows * max_col_tiles arrival counters (self-resetting)
+    uint32_t counters_len = 0;
+    uint64_t* d_partial = nullptr;      // n_slices x D partial sums (grow-only)
+    size_t partial_words = 0;
+};
+
+#define CGB_LONG_ROW 256u
+#define CGB_SLICE_EDGES 256u
+
+static inline int cgb_fail(cgb_ctx* ctx, int code, const char* what, const char* detail) {
+    if (ctx) {
+        ctx->err = std::string(what) + ": " + (detail ? detail : "");
+    }
+    return code;
+}
+
+#define CGB_CHECK_CUDA(ctx, call)                                                   \
+    do {                                                                            \
+        cudaError_t _e = (call);                                                    \
+        if (_e != cudaSuccess) return cgb_fail((ctx), CGB_ERR_CUDA, #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define CGB_CHECK_LAUNCH(ctx, name)                                                 \
+    do {                                                                            \
+        cudaError_t _e = cudaGetLastError();                                        \
+        if (_e != cudaSuccess) return cgb_fail((ctx), CGB_ERR_CUDA, name, cudaGetErrorString(_e)); \
+        (ctx)->launches++;                                                          \
+    } while (0)
+
+#define CGB_REQUIRE(ctx, cond, msg)                                                 \
+    do {                                                                            \
+        if (!(cond)) return cgb_fail((ctx), CGB_ERR_INVALID, msg, #cond);           \
+    } while (0)
+
+int cgb_scratch_reserve(cgb_ctx* ctx, size_t bytes);
+
+// ---- device helpers ----------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 trunc_share(u64 z, int f, int share) {
+    // SecureML local truncation (DESIGN.md "Frozen semantics"): share 0 logical shift, share 1 negate-shift-negate
+    if (f <= 0) return z;
+    return share == 0 ? (z >> f) : (0ull - ((0ull - z) >> f));
+}
+
+// 128-bit read-only gather load, no L1 allocation (rows are re-used only through L2)
+__device__ __forceinline__ ulonglong2 ld_nc_v2(const u64* p) {
+    ulonglong2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ u64 ld_nc_u64(const u64* p) {
+    u64 r;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
+}
+// L2-coherent load (partials written by other CTAs in the same launch)
+__device__ __forceinline__ u64 ld_cg_u64(const u64* p) {
+    u64 r;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_cs_v2(u64* p, u64 a, u64 b) {
+    asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void st_cs_u64(u64* p, u64 a) {
+    asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(a) : "memory");
+}

@@ -1,0 +1,229 @@
+// elementwise.cu -- op (3): fused fixed-point truncation, share masking / opening, public scaling.
+//
+// Serves sci::twoPartyGCNMatrixScale / ApplyGradient / VectorScale / CondVectorAddition share-local parts
+// (optimize-gcn/gcn.h:247,456,476,676,678), sci::getPlainShareVecVec (gcn.h:604), CryptoUtil::intoShares /
+// encodeDoubleAsFixedPoint / mergeShareAsDouble (gcn.h:70,80,96,220) and transpose() (gcn.h:230,648).
+// All kernels are HBM-bound streams: 128-bit accesses when the buffers allow, grid sized to the SM count.
+#include "common.cuh"
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+inline unsigned ew_blocks(const cgb_ctx* ctx, uint64_t work_items) {
+    uint64_t b = (work_items + EW_THREADS - 1) / EW_THREADS;
+    uint64_t cap = (uint64_t)ctx->num_sms * 16;  // grid-stride beyond 16 resident CTAs' worth per SM
+    if (b > cap) b = cap;
+    if (b == 0) b = 1;
+    return (unsigned)b;
+}
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// generic binary/unary elementwise with a functor on u64; VEC2 path processes two words per thread-iteration
+template <typename F>
+__global__ void __launch_bounds__(EW_THREADS) ew2_kernel(const u64* a, const u64* b,
+                                                         u64* out, uint64_t n, bool vec, F f) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        const uint64_t n2 = n >> 1;
+        const ulonglong2* a2 = reinterpret_cast<const ulonglong2*>(a);
+        const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(b);
+        ulonglong2* o2 = reinterpret_cast<ulonglong2*>(out);
+        for (uint64_t k = i; k < n2; k += stride) {
+            ulonglong2 x = a2[k];
+            ulonglong2 y = b ? b2[k] : make_ulonglong2(0, 0);
+            o2[k] = make_ulonglong2(f(x.x, y.x), f(x.y, y.y));
+        }
+        if (i == 0 && (n & 1)) out[n - 1] = f(a[n - 1], b ? b[n - 1] : 0ull);
+    } else {
+        for (uint64_t k = i; k < n; k += stride) out[k] = f(a[k], b ? b[k] : 0ull);
+    }
+}
+
+struct OpAdd { __device__ u64 operator()(u64 x, u64 y) const { return x + y; } };
+struct OpSub { __device__ u64 operator()(u64 x, u64 y) const { return x - y; } };
+struct OpTrunc {
+    int f, share;
+    __device__ u64 operator()(u64 x, u64) const { return trunc_share(x, f, share); }
+};
+struct OpScale {
+    u64 c; int f, share;
+    __device__ u64 operator()(u64 x, u64) const { return trunc_share(x * c, f, share); }
+};
+struct OpApplyGrad {
+    u64 lr; int f, share;
+    __device__ u64 operator()(u64 w, u64 d) const { return w - trunc_share(d * lr, f, share); }
+};
+
+template <typename F>
+int launch_ew2(cgb_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n, F f, const char* name) {
+    if (n == 0) return CGB_OK;
+    bool vec = aligned16(a) && aligned16(out) && (b == nullptr || aligned16(b)) && n >= 2;
+    ew2_kernel<F><<<ew_blocks(ctx, vec ? n / 2 : n), EW_THREADS, 0, ctx->stream>>>((const u64*)a, (const u64*)b,
+                                                                                  (u64*)out, n, vec, f);
+    CGB_CHECK_LAUNCH(ctx, name);
+    return CGB_OK;
+}
+
+// out = trunc( c + e*b[row] + fv[row]*a + [share==0] e*fv[row] )
+__global__ void __launch_bounds__(EW_THREADS) rowmul_finish_kernel(const u64* e, const u64* fv,
+                                                                  const u64* a, const u64* b,
+                                                                  const u64* c, u64* out,
+                                                                  uint64_t rows, uint32_t D, int share, int f) {
+    const uint64_t n = rows * D;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t r = i / D;
+        const u64 fr = __ldg(fv + r), br = __ldg(b + r);
+        const u64 ei = e[i];
+        u64 z = c[i] + ei * br + fr * a[i];
+        if (share == 0) z += ei * fr;
+        out[i] = trunc_share(z, f, share);
+    }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) cond_add_kernel(const u64* v, const u64* u,
+                                                             const uint8_t* cond, u64* out,
+                                                             uint64_t rows, uint32_t D) {
+    const uint64_t n = rows * D;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t r = i / D;
+        out[i] = v[i] + (__ldg(cond + r) ? u[i] : 0ull);
+    }
+}
+
+// 32x32 tile transpose through shared memory (+1 padding column: no bank conflicts on the 8-byte reads)
+__global__ void __launch_bounds__(256) transpose_kernel(const u64* __restrict__ in, u64* __restrict__ out, uint32_t rows,
+                                                        uint32_t cols) {
+    __shared__ u64 tile[32][33];
+    const uint32_t bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (uint32_t j = ty; j < 32; j += 8) {
+        uint32_t r = by + j, c = bx + tx;
+        if (r < rows && c < cols) tile[j][tx] = in[(size_t)r * cols + c];
+    }
+    __syncthreads();
+    for (uint32_t j = ty; j < 32; j += 8) {
+        uint32_t r = bx + j, c = by + tx;  // out is cols x rows
+        if (r < cols && c < rows) out[(size_t)r * rows + c] = tile[tx][j];
+    }
+}
+
+__device__ __forceinline__ u64 encode_fixed(double x, int f) {
+    // C truncation toward zero through int64, as static_cast<uint64_t>(x * (1<<f)) at gcn.h:191,676
+    return (u64)(long long)(x * (double)(1ull << f));
+}
+__device__ __forceinline__ double decode_fixed(u64 v, int f) { return (double)(long long)v / (double)(1ull << f); }
+
+__global__ void __launch_bounds__(EW_THREADS) encode_kernel(const double* __restrict__ x, const u64* __restrict__ s1,
+                                                           u64* __restrict__ out, uint64_t n, int f) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = encode_fixed(x[i], f) - (s1 ? s1[i] : 0ull);
+}
+__global__ void __launch_bounds__(EW_THREADS) decode_kernel(const u64* __restrict__ s0, const u64* __restrict__ s1,
+                                                           double* __restrict__ out, uint64_t n, int f) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = decode_fixed(s0[i] + (s1 ? s1[i] : 0ull), f);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cgb_add(cgb_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint64_t n) {
+    CGB_REQUIRE(ctx, (d_a && d_b && d_out) || n == 0, "cgb_add: null argument");
+    return launch_ew2(ctx, d_a, d_b, d_out, n, OpAdd(), "ew_add");
+}
+int cgb_sub(cgb_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint64_t n) {
+    CGB_REQUIRE(ctx, (d_a && d_b && d_out) || n == 0, "cgb_sub: null argument");
+    return launch_ew2(ctx, d_a, d_b, d_out, n, OpSub(), "ew_sub");
+}
+int cgb_trunc(cgb_ctx* ctx, const uint64_t* d_x, uint64_t* d_out, uint64_t n, int f, int share) {
+    CGB_REQUIRE(ctx, (d_x && d_out) || n == 0, "cgb_trunc: null argument");
+    CGB_REQUIRE(ctx, f < 64 && (share == 0 || share == 1), "cgb_trunc: bad f/share");
+    return launch_ew2(ctx, d_x, nullptr, d_out, n, OpTrunc{f, share}, "ew_trunc");
+}
+int cgb_scale_public(cgb_ctx* ctx, const uint64_t* d_x, uint64_t c, uint64_t* d_out, uint64_t n, int f, int share) {
+    CGB_REQUIRE(ctx, (d_x && d_out) || n == 0, "cgb_scale_public: null argument");
+    CGB_REQUIRE(ctx, f < 64 && (share == 0 || share == 1), "cgb_scale_public: bad f/share");
+    return launch_ew2(ctx, d_x, nullptr, d_out, n, OpScale{(u64)c, f, share}, "ew_scale_public");
+}
+int cgb_apply_gradient(cgb_ctx* ctx, const uint64_t* d_W, const uint64_t* d_d, uint64_t lr, uint64_t* d_out,
+                       uint64_t n, int f, int share) {
+    CGB_REQUIRE(ctx, (d_W && d_d && d_out) || n == 0, "cgb_apply_gradient: null argument");
+    CGB_REQUIRE(ctx, f < 64 && (share == 0 || share == 1), "cgb_apply_gradient: bad f/share");
+    return launch_ew2(ctx, d_W, d_d, d_out, n, OpApplyGrad{(u64)lr, f, share}, "ew_apply_gradient");
+}
+int cgb_rowmul_beaver_finish(cgb_ctx* ctx, const uint64_t* d_e, const uint64_t* d_fv, const uint64_t* d_a,
+                             const uint64_t* d_b, const uint64_t* d_c, uint64_t* d_out, uint64_t rows, uint32_t D,
+                             int share, int f) {
+    CGB_REQUIRE(ctx, (d_e && d_fv && d_a && d_b && d_c && d_out) || rows == 0, "cgb_rowmul_beaver_finish: null argument");
+    CGB_REQUIRE(ctx, D > 0 && f < 64 && (share == 0 || share == 1), "cgb_rowmul_beaver_finish: bad D/f/share");
+    if (rows == 0) return CGB_OK;
+    rowmul_finish_kernel<<<ew_blocks(ctx, rows * D), EW_THREADS, 0, ctx->stream>>>(
+        (const u64*)d_e, (const u64*)d_fv, (const u64*)d_a, (const u64*)d_b, (const u64*)d_c, (u64*)d_out, rows, D,
+        share, f);
+    CGB_CHECK_LAUNCH(ctx, "rowmul_finish_kernel");
+    return CGB_OK;
+}
+int cgb_cond_add(cgb_ctx* ctx, const uint64_t* d_v, const uint64_t* d_u, const uint8_t* d_cond, uint64_t* d_out,
+                 uint64_t rows, uint32_t D) {
+    CGB_REQUIRE(ctx, (d_v && d_u && d_cond && d_out) || rows == 0, "cgb_cond_add: null argument");
+    if (rows == 0) return CGB_OK;
+    CGB_REQUIRE(ctx, D > 0, "cgb_cond_add: D == 0");
+    cond_add_kernel<<<ew_blocks(ctx, rows * D), EW_THREADS, 0, ctx->stream>>>((const u64*)d_v, (const u64*)d_u, d_cond,
+                                                                            (u64*)d_out, rows, D);
+    CGB_CHECK_LAUNCH(ctx, "cond_add_kernel");
+    return CGB_OK;
+}
+int cgb_transpose(cgb_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint32_t rows, uint32_t cols) {
+    CGB_REQUIRE(ctx, (d_in && d_out) || rows == 0 || cols == 0, "cgb_transpose: null argument");
+    CGB_REQUIRE(ctx, (const void*)d_in != (const void*)d_out, "cgb_transpose: out must not alias in");
+    if (rows == 0 || cols == 0) return CGB_OK;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    CGB_REQUIRE(ctx, grid.y <= 65535, "cgb_transpose: too many rows (max 2097120)");
+    transpose_kernel<<<grid, 256, 0, ctx->stream>>>((const u64*)d_in, (u64*)d_out, rows, cols);
+    CGB_CHECK_LAUNCH(ctx, "transpose_kernel");
+    return CGB_OK;
+}
+int cgb_encode(cgb_ctx* ctx, const double* d_x, uint64_t* d_out, uint64_t n, int f) {
+    CGB_REQUIRE(ctx, (d_x && d_out) || n == 0, "cgb_encode: null argument");
+    CGB_REQUIRE(ctx, f >= 0 && f < 63, "cgb_encode: bad f");
+    if (n == 0) return CGB_OK;
+    encode_kernel<<<ew_blocks(ctx, n), EW_THREADS, 0, ctx->stream>>>(d_x, nullptr, (u64*)d_out, n, f);
+    CGB_CHECK_LAUNCH(ctx, "encode_kernel");
+    return CGB_OK;
+}
+int cgb_decode(cgb_ctx* ctx, const uint64_t* d_v, double* d_out, uint64_t n, int f) {
+    CGB_REQUIRE(ctx, (d_v && d_out) || n == 0, "cgb_decode: null argument");
+    CGB_REQUIRE(ctx, f >= 0 && f < 63, "cgb_decode: bad f");
+    if (n == 0) return CGB_OK;
+    decode_kernel<<<ew_blocks(ctx, n), EW_THREADS, 0, ctx->stream>>>((const u64*)d_v, nullptr, d_out, n, f);
+    CGB_CHECK_LAUNCH(ctx, "decode_kernel");
+    return CGB_OK;
+}
+int cgb_share_split(cgb_ctx* ctx, const double* d_x, uint64_t n, int f, const uint32_t key[8], uint64_t stream,
+                    uint64_t word_offset, uint64_t* d_s0, uint64_t* d_s1) {
+    CGB_REQUIRE(ctx, (d_x && d_s0 && d_s1) || n == 0, "cgb_share_split: null argument");
+    CGB_REQUIRE(ctx, f >= 0 && f < 63, "cgb_share_split: bad f");
+    if (n == 0) return CGB_OK;
+    int rc = cgb_prg_fill(ctx, key, stream, word_offset, d_s1, n);
+    if (rc) return rc;
+    encode_kernel<<<ew_blocks(ctx, n), EW_THREADS, 0, ctx->stream>>>(d_x, (const u64*)d_s1, (u64*)d_s0, n, f);
+    CGB_CHECK_LAUNCH(ctx, "encode_kernel");
+    return CGB_OK;
+}
+int cgb_open_decode(cgb_ctx* ctx, const uint64_t* d_s0, const uint64_t* d_s1, double* d_out, uint64_t n, int f) {
+    CGB_REQUIRE(ctx, (d_s0 && d_s1 && d_out) || n == 0, "cgb_open_decode: null argument");
+    CGB_REQUIRE(ctx, f >= 0 && f < 63, "cgb_open_decode: bad f");
+    if (n == 0) return CGB_OK;
+    decode_kernel<<<ew_blocks(ctx, n), EW_THREADS, 0, ctx->stream>>>((const u64*)d_s0, (const u64*)d_s1, d_out, n, f);
+    CGB_CHECK_LAUNCH(ctx, "decode_kernel");
+    return CGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,450 @@
+// gather.cu -- op (1): edge-wise scatter / gather-sum of Z_2^64 share rows (CSR-by-destination SpMM).
+//
+// Serves: client_oblivious_mapper_online (ss_vertex_centric_algo_kernel.h:752,760,
+// 818,848), ScatterComp copy (optimize-gcn/gcn.h:300) and prefix_network_aggregate ADD_AGG (gcn.h:328-335).
+//
+// Layout: share rows are dense row-major u64, one row = D columns.  A "group" of LANES consecutive lanes owns one
+// destination row (x one column tile of VEC*LANES columns); each lane keeps VEC accumulators and issues U
+// independent 8*VEC-byte gather loads per step, so a warp has 32*U loads in flight.  Rows longer than
+// CGB_LONG_ROW edges are cut (once, at cgb_csr_create) into slices of CGB_SLICE_EDGES edges that are summed by
+// separate groups; the last slice to arrive (self-resetting arrival counter) folds the partial sums, so a
+// power-law tail cannot serialise on one group.  Integer addition mod 2^64 is associative and commutative, so
+// every schedule yields the same bits.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+struct GatherArgs {
+    const uint32_t* rowptr;
+    const uint32_t* col;
+    const u64* x;
+    const u64* delta;
+    u64* y;
+    uint32_t n_rows;
+    uint32_t D;
+    uint32_t n_ct;  // column tiles per row
+    // long-row slices
+    uint32_t n_slices;
+    const uint32_t* slice_row;
+    const uint32_t* slice_begin;
+    const uint32_t* slice_first;
+    const uint32_t* slice_count;
+    const uint32_t* long_id;
+    uint32_t* counters;
+    u64* partial;
+};
+
+template <int VEC>
+struct Acc;
+template <>
+struct Acc<1> {
+    u64 a;
+    __device__ __forceinline__ void zero() { a = 0; }
+    __device__ __forceinline__ void load_nc(const u64* p) { a = ld_nc_u64(p); }
+    __device__ __forceinline__ void load_cg(const u64* p) { a = ld_cg_u64(p); }
+    __device__ __forceinline__ void add(const Acc& o) { a += o.a; }
+    __device__ __forceinline__ void store(u64* p) const { *p = a; }
+    __device__ __forceinline__ void store_cs(u64* p) const { st_cs_u64(p, a); }
+};
+template <>
+struct Acc<2> {
+    u64 a, b;
+    __device__ __forceinline__ void zero() { a = 0; b = 0; }
+    __device__ __forceinline__ void load_nc(const u64* p) {
+        ulonglong2 v = ld_nc_v2(p);
+        a = v.x; b = v.y;
+    }
+    __device__ __forceinline__ void load_cg(const u64* p) {
+        a = ld_cg_u64(p); b = ld_cg_u64(p + 1);
+    }
+    __device__ __forceinline__ void add(const Acc& o) { a += o.a; b += o.b; }
+    __device__ __forceinline__ void store(u64* p) const { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(a, b); }
+    __device__ __forceinline__ void store_cs(u64* p) const { st_cs_v2(p, a, b); }
+};
+
+template <int LANES>
+__device__ __forceinline__ unsigned group_mask(int lane_in_warp) {
+    if (LANES == 32) return 0xffffffffu;
+    return ((1u << LANES) - 1u) << (lane_in_warp & ~(LANES - 1));
+}
+
+// sum of x[col[e], col0 .. col0+VEC) for e in [e0, e1)
+template <int VEC, int LANES, int U, bool IDENT>
+__device__ __forceinline__ Acc<VEC> accumulate_edges(const uint32_t* __restrict__ col, const u64* __restrict__ x,
+                                                     uint32_t e0, uint32_t e1, uint32_t D, uint32_t col0, bool active,
+                                                     int lane, unsigned mask) {
+    Acc<VEC> acc;
+    acc.zero();
+    for (uint32_t e = e0; e < e1; e += LANES) {
+        const uint32_t n = min((uint32_t)LANES, e1 - e);
+        uint32_t my = 0;
+        if (IDENT) my = e + lane;
+        else if ((uint32_t)lane < n) my = __ldg(col + e + lane);
+        for (uint32_t k0 = 0; k0 < n; k0 += U) {
+            Acc<VEC> v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t idx = __shfl_sync(mask, my, k0 + u, LANES);
+                if (active && (k0 + u < n)) v[u].load_nc(x + (size_t)idx * D + col0);
+                else v[u].zero();
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc.add(v[u]);
+        }
+    }
+    return acc;
+}
+
+template <int VEC, int LANES, int U>
+__global__ void __launch_bounds__(256) gather_sum_kernel(const GatherArgs a) {
+    constexpr int GROUPS = 256 / LANES;
+    const int lane = threadIdx.x & (LANES - 1);
+    const unsigned mask = group_mask<LANES>(threadIdx.x & 31);
+    const uint64_t gid = (uint64_t)blockIdx.x * GROUPS + threadIdx.x / LANES;
+    const uint64_t total = ((uint64_t)a.n_slices + a.n_rows) * a.n_ct;
+    if (gid >= total) return;
+    const uint32_t item = (uint32_t)(gid / a.n_ct);
+    const uint32_t ct = (uint32_t)(gid - (uint64_t)item * a.n_ct);
+    const uint32_t col0 = ct * (VEC * LANES) + lane * VEC;
+    const bool active = col0 < a.D;
+
+    if (item >= a.n_slices) {
+        // ---- one whole destination row ----
+        const uint32_t row = item - a.n_slices;
+        const uint32_t b = __ldg(a.rowptr + row), e = __ldg(a.rowptr + row + 1);
+        if (e - b > CGB_LONG_ROW) return;  // summed by its slices
+        Acc<VEC> acc = accumulate_edges<VEC, LANES, U, false>(a.col, a.x, b, e, a.D, col0, active, lane, mask);
+        if (active) {
+            const size_t o = (size_t)row * a.D + col0;
+            if (a.delta) {
+                Acc<VEC> d;
+                d.load_nc(a.delta + o);
+                acc.add(d);
+            }
+            acc.store_cs(a.y + o);
+        }
+    } else {
+        // ---- one slice of a long row ----
+        const uint32_t s = item;
+        const uint32_t row = __ldg(a.slice_row + s);
+        const uint32_t b = __ldg(a.slice_begin + s);
+        const uint32_t e = min(b + CGB_SLICE_EDGES, __ldg(a.rowptr + row + 1));
+        Acc<VEC> acc = accumulate_edges<VEC, LANES, U, false>(a.col, a.x, b, e, a.D, col0, active, lane, mask);
+        if (active) acc.store(a.partial + (size_t)s * a.D + col0);
+        __threadfence();
+        __syncwarp(mask);
+        const uint32_t cnt = __ldg(a.slice_count + s);
+        uint32_t* ctr = a.counters + (size_t)__ldg(a.long_id + s) * a.n_ct + ct;
+        uint32_t prev = 0;
+        if (lane == 0) prev = atomicAdd(ctr, 1u);
+        prev = __shfl_sync(mask, prev, 0, LANES);
+        if (prev == cnt - 1) {
+            __threadfence();
+            if (active) {
+                const uint32_t first = __ldg(a.slice_first + s);
+                const size_t o = (size_t)row * a.D + col0;
+                Acc<VEC> sum;
+                sum.zero();
+                if (a.delta) sum.load_nc(a.delta + o);
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    Acc<VEC> p;
+                    p.load_cg(a.partial + (size_t)(first + k) * a.D + col0);
+                    sum.add(p);
+                }
+                sum.store_cs(a.y + o);
+            }
+            if (lane == 0) *ctr = 0;  // ready for the next launch
+        }
+    }
+}
+
+// y[j, :] = (idx[j] == NO_ROW ? 0 : x[idx[j], :]) + delta[j, :]
+template <int VEC, int LANES>
+__global__ void __launch_bounds__(256) expand_rows_kernel(const uint32_t* __restrict__ idx, uint64_t n_out,
+                                                          const u64* __restrict__ x, const u64* __restrict__ delta,
+                                                          u64* __restrict__ y, uint32_t D, uint32_t n_ct) {
+    constexpr int GROUPS = 256 / LANES;
+    const int lane = threadIdx.x & (LANES - 1);
+    const uint64_t gid = (uint64_t)blockIdx.x * GROUPS + threadIdx.x / LANES;
+    if (gid >= n_out * n_ct) return;
+    const uint64_t j = gid / n_ct;
+    const uint32_t ct = (uint32_t)(gid - j * n_ct);
+    const uint32_t col0 = ct * (VEC * LANES) + lane * VEC;
+    if (col0 >= D) return;
+    const uint32_t src = __ldg(idx + j);
+    Acc<VEC> v;
+    if (src == CGB_NO_ROW) v.zero();
+    else v.load_nc(x + (size_t)src * D + col0);
+    if (delta) {
+        Acc<VEC> d;
+        d.load_nc(delta + j * D + col0);
+        v.add(d);
+    }
+    v.store_cs(y + j * D + col0);
+}
+
+// segmented sum over dst-sorted rows; dup: write the sum to every row of the segment
+template <int VEC, int LANES, int U>
+__global__ void __launch_bounds__(256) segsum_kernel(const uint32_t* __restrict__ segptr, uint32_t n_seg,
+                                                     const u64* __restrict__ in, u64* __restrict__ out, uint32_t D,
+                                                     uint32_t n_ct, int dup) {
+    constexpr int GROUPS = 256 / LANES;
+    const int lane = threadIdx.x & (LANES - 1);
+    const unsigned mask = group_mask<LANES>(threadIdx.x & 31);
+    const uint64_t gid = (uint64_t)blockIdx.x * GROUPS + threadIdx.x / LANES;
+    if (gid >= (uint64_t)n_seg * n_ct) return;
+    const uint32_t s = (uint32_t)(gid / n_ct);
+    const uint32_t ct = (uint32_t)(gid - (uint64_t)s * n_ct);
+    const uint32_t col0 = ct * (VEC * LANES) + lane * VEC;
+    const bool active = col0 < D;
+    const uint32_t b = __ldg(segptr + s), e = __ldg(segptr + s + 1);
+    Acc<VEC> acc = accumulate_edges<VEC, LANES, U, true>(nullptr, in, b, e, D, col0, active, lane, mask);
+    if (!active) return;
+    if (dup) {
+        for (uint32_t r = b; r < e; ++r) acc.store_cs(out + (size_t)r * D + col0);
+    } else {
+        acc.store_cs(out + (size_t)s * D + col0);
+    }
+}
+
+struct Shape {
+    int vec, lanes;
+    uint32_t n_ct;
+};
+inline Shape pick_shape(uint32_t D, bool aligned16) {
+    Shape s;
+    s.vec = (D % 2 == 0 && aligned16) ? 2 : 1;
+    uint32_t need = (D + s.vec - 1) / s.vec;
+    int lanes = 2;
+    while ((uint32_t)lanes < need && lanes < 32) lanes *= 2;
+    s.lanes = lanes;
+    s.n_ct = (D + s.vec * lanes - 1) / (s.vec * lanes);
+    return s;
+}
+inline bool is_aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename F>
+int dispatch_shape(const Shape& s, F&& f) {
+#define CGB_CASE(V, L, U_)                         \
+    if (s.vec == V && s.lanes == L) {              \
+        f(std::integral_constant<int, V>(), std::integral_constant<int, L>(), std::integral_constant<int, U_>()); \
+        return 0;                                  \
+    }
+    CGB_CASE(1, 2, 2) CGB_CASE(1, 4, 4) CGB_CASE(1, 8, 8) CGB_CASE(1, 16, 8) CGB_CASE(1, 32, 8)
+    CGB_CASE(2, 2, 2) CGB_CASE(2, 4, 4) CGB_CASE(2, 8, 8) CGB_CASE(2, 16, 8) CGB_CASE(2, 32, 8)
+#undef CGB_CASE
+    return -1;
+}
+
+int build_slices(cgb_ctx* ctx, cgb_csr* c, const uint32_t* h_rowptr) {
+    std::vector<uint32_t> srow, sbeg, sfirst, scnt, lid;
+    uint32_t n_long = 0;
+    for (uint32_t v = 0; v < c->n_rows; ++v) {
+        uint32_t deg = h_rowptr[v + 1] - h_rowptr[v];
+        if (deg <= CGB_LONG_ROW) continue;
+        uint32_t ns = (deg + CGB_SLICE_EDGES - 1) / CGB_SLICE_EDGES;
+        uint32_t first = (uint32_t)srow.size();
+        for (uint32_t k = 0; k < ns; ++k) {
+            srow.push_back(v);
+            sbeg.push_back(h_rowptr[v] + k * CGB_SLICE_EDGES);
+            sfirst.push_back(first);
+            scnt.push_back(ns);
+            lid.push_back(n_long);
+        }
+        ++n_long;
+    }
+    c->n_long_rows = n_long;
+    c->n_slices = (uint32_t)srow.size();
+    if (c->n_slices == 0) return 0;
+    size_t b = (size_t)c->n_slices * sizeof(uint32_t);
+    uint32_t** dst[5] = {&c->d_slice_row, &c->d_slice_begin, &c->d_slice_first, &c->d_slice_count, &c->d_long_id};
+    const std::vector<uint32_t>* src[5] = {&srow, &sbeg, &sfirst, &scnt, &lid};
+    for (int i = 0; i < 5; ++i) {
+        CGB_CHECK_CUDA(ctx, cudaMalloc((void**)dst[i], b));
+        CGB_CHECK_CUDA(ctx, cudaMemcpyAsync(*dst[i], src[i]->data(), b, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cgb_csr_create(cgb_ctx* ctx, const uint32_t* h_rowptr, const uint32_t* h_col, uint32_t n_rows, uint64_t n_edges,
+                   uint32_t n_src_rows, cgb_csr** out) {
+    CGB_REQUIRE(ctx, out && h_rowptr && (h_col || n_edges == 0), "cgb_csr_create: null argument");
+    CGB_REQUIRE(ctx, n_edges < 0xFFFFFFFFull, "cgb_csr_create: edge count must fit 32 bits");
+    CGB_REQUIRE(ctx, h_rowptr[0] == 0 && h_rowptr[n_rows] == n_edges, "cgb_csr_create: rowptr does not span the edges");
+    for (uint32_t v = 0; v < n_rows; ++v)
+        CGB_REQUIRE(ctx, h_rowptr[v] <= h_rowptr[v + 1], "cgb_csr_create: rowptr not monotone");
+    for (uint64_t e = 0; e < n_edges; ++e)
+        CGB_REQUIRE(ctx, h_col[e] < n_src_rows, "cgb_csr_create: column index out of range");
+    CGB_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cgb_csr* c = new cgb_csr();
+    c->n_rows = n_rows;
+    c->n_edges = n_edges;
+    c->n_src_rows = n_src_rows;
+    CGB_CHECK_CUDA(ctx, cudaMalloc((void**)&c->d_rowptr, ((size_t)n_rows + 1) * sizeof(uint32_t)));
+    CGB_CHECK_CUDA(ctx, cudaMalloc((void**)&c->d_col, std::max<size_t>(n_edges, 1) * sizeof(uint32_t)));
+    CGB_CHECK_CUDA(ctx, cudaMemcpyAsync(c->d_rowptr, h_rowptr, ((size_t)n_rows + 1) * sizeof(uint32_t),
+                                        cudaMemcpyHostToDevice, ctx->stream));
+    if (n_edges)
+        CGB_CHECK_CUDA(ctx, cudaMemcpyAsync(c->d_col, h_col, n_edges * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                            ctx->stream));
+    CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int rc = build_slices(ctx, c, h_rowptr);
+    if (rc) return rc;
+    *out = c;
+    return CGB_OK;
+}
+
+int cgb_csr_create_device(cgb_ctx* ctx, const uint32_t* d_rowptr, const uint32_t* d_col, uint32_t n_rows,
+                          uint64_t n_edges, uint32_t n_src_rows, cgb_csr** out) {
+    CGB_REQUIRE(ctx, out && d_rowptr && (d_col || n_edges == 0), "cgb_csr_create_device: null argument");
+    CGB_REQUIRE(ctx, n_edges < 0xFFFFFFFFull, "cgb_csr_create_device: edge count must fit 32 bits");
+    CGB_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<uint32_t> h_rowptr((size_t)n_rows + 1);
+    CGB_CHECK_CUDA(ctx, cudaMemcpyAsync(h_rowptr.data(), d_rowptr, h_rowptr.size() * sizeof(uint32_t),
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+    CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CGB_REQUIRE(ctx, h_rowptr[0] == 0 && h_rowptr[n_rows] == n_edges, "cgb_csr_create_device: rowptr does not span the edges");
+    cgb_csr* c = new cgb_csr();
+    c->n_rows = n_rows;
+    c->n_edges = n_edges;
+    c->n_src_rows = n_src_rows;
+    CGB_CHECK_CUDA(ctx, cudaMalloc((void**)&c->d_rowptr, ((size_t)n_rows + 1) * sizeof(uint32_t)));
+    CGB_CHECK_CUDA(ctx, cudaMalloc((void**)&c->d_col, std::max<size_t>(n_edges, 1) * sizeof(uint32_t)));
+    CGB_CHECK_CUDA(ctx, cudaMemcpyAsync(c->d_rowptr, d_rowptr, ((size_t)n_rows + 1) * sizeof(uint32_t),
+                                        cudaMemcpyDeviceToDevice, ctx->stream));
+    if (n_edges)
+        CGB_CHECK_CUDA(ctx, cudaMemcpyAsync(c->d_col, d_col, n_edges * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                                            ctx->stream));
+    CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int rc = build_slices(ctx, c, h_rowptr.data());
+    if (rc) return rc;
+    *out = c;
+    return CGB_OK;
+}
+
+int cgb_csr_destroy(cgb_ctx* ctx, cgb_csr* c) {
+    if (!c) return CGB_OK;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFree(c->d_rowptr); cudaFree(c->d_col);
+    cudaFree(c->d_slice_row); cudaFree(c->d_slice_begin); cudaFree(c->d_slice_first);
+    cudaFree(c->d_slice_count); cudaFree(c->d_long_id); cudaFree(c->d_counters); cudaFree(c->d_partial);
+    delete c;
+    return CGB_OK;
+}
+uint64_t cgb_csr_num_edges(const cgb_csr* c) { return c ? c->n_edges : 0; }
+uint32_t cgb_csr_num_rows(const cgb_csr* c) { return c ? c->n_rows : 0; }
+const uint32_t* cgb_csr_rowptr(const cgb_csr* c) { return c ? c->d_rowptr : nullptr; }
+const uint32_t* cgb_csr_col(const cgb_csr* c) { return c ? c->d_col : nullptr; }
+
+int cgb_gather_sum(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, const uint64_t* d_delta, uint64_t* d_y,
+                   uint32_t D) {
+    cgb_csr* csr = const_cast<cgb_csr*>(csr_c);
+    CGB_REQUIRE(ctx, csr && d_x && d_y && D > 0, "cgb_gather_sum: null argument");
+    CGB_REQUIRE(ctx, (const void*)d_x != (const void*)d_y, "cgb_gather_sum: y must not alias x");
+    if (csr->n_rows == 0) return CGB_OK;
+    const Shape s = pick_shape(D, is_aligned16(d_x) && is_aligned16(d_delta) && is_aligned16(d_y));
+    if (csr->n_slices) {
+        size_t need = (size_t)csr->n_slices * D;
+        if (need > csr->partial_words || !is_aligned16(csr->d_partial)) {
+            CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(csr->d_partial);
+            CGB_CHECK_CUDA(ctx, cudaMalloc((void**)&csr->d_partial, need * sizeof(u64)));
+            csr->partial_words = need;
+        }
+        uint32_t need_ctr = csr->n_long_rows * s.n_ct;
+        if (need_ctr > csr->counters_len) {
+            CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(csr->d_counters);
+            CGB_CHECK_CUDA(ctx, cudaMalloc((void**)&csr->d_counters, need_ctr * sizeof(uint32_t)));
+            CGB_CHECK_CUDA(ctx, cudaMemsetAsync(csr->d_counters, 0, need_ctr * sizeof(uint32_t), ctx->stream));
+            csr->counters_len = need_ctr;
+        }
+    }
+    GatherArgs a;
+    a.rowptr = csr->d_rowptr; a.col = csr->d_col;
+    a.x = (const u64*)d_x; a.delta = (const u64*)d_delta; a.y = (u64*)d_y;
+    a.n_rows = csr->n_rows; a.D = D; a.n_ct = s.n_ct;
+    a.n_slices = csr->n_slices;
+    a.slice_row = csr->d_slice_row; a.slice_begin = csr->d_slice_begin; a.slice_first = csr->d_slice_first;
+    a.slice_count = csr->d_slice_count; a.long_id = csr->d_long_id; a.counters = csr->d_counters;
+    a.partial = (u64*)csr->d_partial;
+    const uint64_t total = ((uint64_t)csr->n_slices + csr->n_rows) * s.n_ct;
+    int rc = dispatch_shape(s, [&](auto V, auto L, auto U_) {
+        constexpr int GROUPS = 256 / decltype(L)::value;
+        uint64_t blocks = (total + GROUPS - 1) / GROUPS;
+        gather_sum_kernel<decltype(V)::value, decltype(L)::value, decltype(U_)::value>
+            <<<(unsigned)blocks, 256, 0, ctx->stream>>>(a);
+    });
+    CGB_REQUIRE(ctx, rc == 0, "cgb_gather_sum: no kernel for this shape");
+    CGB_CHECK_LAUNCH(ctx, "gather_sum_kernel");
+    return CGB_OK;
+}
+
+int cgb_expand_rows(cgb_ctx* ctx, const uint32_t* d_idx, uint64_t n_out, const uint64_t* d_x,
+                    const uint64_t* d_delta, uint64_t* d_y, uint32_t D) {
+    CGB_REQUIRE(ctx, d_idx && d_x && d_y && D > 0, "cgb_expand_rows: null argument");
+    CGB_REQUIRE(ctx, (const void*)d_x != (const void*)d_y, "cgb_expand_rows: y must not alias x");
+    if (n_out == 0) return CGB_OK;
+    const Shape s = pick_shape(D, is_aligned16(d_x) && is_aligned16(d_delta) && is_aligned16(d_y));
+    const uint64_t total = n_out * s.n_ct;
+    int rc = dispatch_shape(s, [&](auto V, auto L, auto) {
+        constexpr int GROUPS = 256 / decltype(L)::value;
+        uint64_t blocks = (total + GROUPS - 1) / GROUPS;
+        expand_rows_kernel<decltype(V)::value, decltype(L)::value><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+            d_idx, n_out, (const u64*)d_x, (const u64*)d_delta, (u64*)d_y, D, s.n_ct);
+    });
+    CGB_REQUIRE(ctx, rc == 0, "cgb_expand_rows: no kernel for this shape");
+    CGB_CHECK_LAUNCH(ctx, "expand_rows_kernel");
+    return CGB_OK;
+}
+
+int cgb_segsum(cgb_ctx* ctx, const uint32_t* d_segptr, uint32_t n_seg, uint64_t n_in, const uint64_t* d_in,
+               uint64_t* d_out, uint32_t D, int dup) {
+    CGB_REQUIRE(ctx, d_segptr && d_out && D > 0 && (d_in || n_in == 0), "cgb_segsum: null argument");
+    CGB_REQUIRE(ctx, (const void*)d_in != (const void*)d_out, "cgb_segsum: out must not alias in");
+    CGB_REQUIRE(ctx, n_in < 0xFFFFFFFFull, "cgb_segsum: row count must fit 32 bits");
+    if (n_seg == 0) return CGB_OK;
+    const Shape s = pick_shape(D, is_aligned16(d_in) && is_aligned16(d_out));
+    const uint64_t total = (uint64_t)n_seg * s.n_ct;
+    int rc = dispatch_shape(s, [&](auto V, auto L, auto U_) {
+        constexpr int GROUPS = 256 / decltype(L)::value;
+        uint64_t blocks = (total + GROUPS - 1) / GROUPS;
+        segsum_kernel<decltype(V)::value, decltype(L)::value, decltype(U_)::value>
+            <<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_segptr, n_seg, (const u64*)d_in, (u64*)d_out, D, s.n_ct, dup);
+    });
+    CGB_REQUIRE(ctx, rc == 0, "cgb_segsum: no kernel for this shape");
+    CGB_CHECK_LAUNCH(ctx, "segsum_kernel");
+    return CGB_OK;
+}
+
+int cgb_host_gather_sum(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* h_x, const uint64_t* h_delta,
+                        uint64_t* h_y, uint32_t D) {
+    CGB_REQUIRE(ctx, csr && h_x && h_y && D > 0, "cgb_host_gather_sum: null argument");
+    const size_t xb = (size_t)csr->n_src_rows * D * sizeof(u64);
+    const size_t yb = (size_t)csr->n_rows * D * sizeof(u64);
+    const size_t need = xb + yb + (h_delta ? yb : 0) + 3 * 256;
+    int rc = cgb_scratch_reserve(ctx, need);
+    if (rc) return rc;
+    auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    char* base = (char*)ctx->scratch;
+    u64* d_x = (u64*)base;
+    u64* d_y = (u64*)(base + align(xb));
+    u64* d_delta = h_delta ? (u64*)(base + align(xb) + align(yb)) : nullptr;
+    CGB_CHECK_CUDA(ctx, cudaMemcpyAsync(d_x, h_x, xb, cudaMemcpyHostToDevice, ctx->stream));
+    if (h_delta) CGB_CHECK_CUDA(ctx, cudaMemcpyAsync(d_delta, h_delta, yb, cudaMemcpyHostToDevice, ctx->stream));
+    rc = cgb_gather_sum(ctx, csr, (const uint64_t*)d_x, (const uint64_t*)d_delta, (uint64_t*)d_y, D);
+    if (rc) return rc;
+    CGB_CHECK_CUDA(ctx, cudaMemcpyAsync(h_y, d_y, yb, cudaMemcpyDeviceToHost, ctx->stream));
+    CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CGB_OK;
+}
+
+}  // extern "C"

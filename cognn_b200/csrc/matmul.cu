@@ -1,0 +1,257 @@
+// matmul.cu -- op (2): dense contraction mod 2^64 and the Beaver-triple recombination of the Apply step.
+//
+// Serves sci::twoPartyGCNMatMul (optimize-gcn/gcn.h:233, 665, 671, 710): X (N_p x F) * W (F x H), (p-y) * W^T,
+// h_t * v.  This is the 64-bit integer IMAD path of the north star: every u64 multiply-add is one
+// IMAD.WIDE.U32 (lo*lo) plus two 32-bit IMADs for the cross terms that land in the low 64 bits; operands are
+// staged through shared memory in BK-deep tiles, each thread keeps a TM x TN block of u64 accumulators.
+// The kernel takes up to two (A, B) operand pairs that accumulate into the same tile, an optional addend Z and a
+// fused truncation, so the Beaver finish  C_i = trunc(Z_i + E*(V_i [+F]) + U_i*F)  is one launch.
+// Small output tiles with a long K (the weight-gradient h_t * v, K = N_p) are split along K and combined with
+// 64-bit atomics (addition mod 2^64 is order-independent, so this stays bit exact).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+struct MatmulArgs {
+    const u64* A[2];
+    const u64* B[2];
+    int n_pairs;
+    const u64* Z;  // optional addend (M x N), only with k_splits == 1
+    u64* C;
+    uint32_t M, K, N;
+    int transA;      // A stored K x M
+    int accumulate;  // C += (k_splits == 1: read-modify-write; else atomics onto existing C)
+    int f, share;    // fused truncation (f <= 0: none), only with k_splits == 1
+    uint32_t k_chunk;  // K range per split (multiple of BK)
+    uint32_t k_splits;
+};
+
+template <int BM, int BN, int BK, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN), (TM * TN >= 32) ? 1 : 2) matmul_kernel(const MatmulArgs a) {
+    constexpr int THREADS = (BM / TM) * (BN / TN);
+    constexpr int A_LD = BM * BK / THREADS;
+    constexpr int B_LD = (BK * BN + THREADS - 1) / THREADS;
+    constexpr int AS = BM + 2, BS = BN + 2;  // even padding keeps 16-byte alignment of the fragment reads
+    __shared__ __align__(16) u64 As[BK][AS];
+    __shared__ __align__(16) u64 Bs[BK][BS];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const uint32_t m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const uint32_t kb = blockIdx.z * a.k_chunk;
+    const uint32_t ke = min(a.K, kb + a.k_chunk);
+
+    u64 acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0;
+
+    u64 ra[A_LD], rb[B_LD];
+
+    auto load_tiles = [&](const u64* __restrict__ A, const u64* __restrict__ B, uint32_t k0) {
+#pragma unroll
+        for (int i = 0; i < A_LD; ++i) {
+            const int idx = tid + i * THREADS;
+            uint32_t m, k;
+            if (a.transA) { m = idx % BM; k = idx / BM; }  // consecutive threads walk M (contiguous in K x M storage)
+            else { k = idx % BK; m = idx / BK; }           // consecutive threads walk K (contiguous in M x K storage)
+            const uint32_t gm = m0 + m, gk = k0 + k;
+            u64 v = 0;
+            if (gm < a.M && gk < ke) v = a.transA ? __ldg(A + (size_t)gk * a.M + gm) : __ldg(A + (size_t)gm * a.K + gk);
+            ra[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < B_LD; ++i) {
+            const int idx = tid + i * THREADS;
+            const uint32_t n = idx % BN, k = idx / BN;
+            const uint32_t gn = n0 + n, gk = k0 + k;
+            u64 v = 0;
+            if (idx < BK * BN && gn < a.N && gk < ke) v = __ldg(B + (size_t)gk * a.N + gn);
+            rb[i] = v;
+        }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int i = 0; i < A_LD; ++i) {
+            const int idx = tid + i * THREADS;
+            int m, k;
+            if (a.transA) { m = idx % BM; k = idx / BM; }
+            else { k = idx % BK; m = idx / BK; }
+            As[k][m] = ra[i];
+        }
+#pragma unroll
+        for (int i = 0; i < B_LD; ++i) {
+            const int idx = tid + i * THREADS;
+            if (idx < BK * BN) Bs[idx / BN][idx % BN] = rb[i];
+        }
+    };
+
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        if (p >= a.n_pairs || kb >= ke) break;
+        const u64* A = p == 0 ? a.A[0] : a.A[1];
+        const u64* B = p == 0 ? a.B[0] : a.B[1];
+        load_tiles(A, B, kb);
+        for (uint32_t k0 = kb; k0 < ke; k0 += BK) {
+            __syncthreads();  // previous tile fully consumed
+            store_tiles();
+            __syncthreads();
+            if (k0 + BK < ke) load_tiles(A, B, k0 + BK);  // prefetch next tile into registers
+#pragma unroll 4
+            for (int k = 0; k < BK; ++k) {
+                u64 fa[TM], fb[TN];
+#pragma unroll
+                for (int i = 0; i < TM; ++i) fa[i] = As[k][ty * TM + i];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) fb[j] = Bs[k][tx * TN + j];
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] += fa[i] * fb[j];
+            }
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const uint32_t gm = m0 + ty * TM + i;
+        if (gm >= a.M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const uint32_t gn = n0 + tx * TN + j;
+            if (gn >= a.N) continue;
+            const size_t o = (size_t)gm * a.N + gn;
+            if (a.k_splits > 1) {
+                atomicAdd(a.C + o, acc[i][j]);
+            } else {
+                u64 v = acc[i][j];
+                if (a.Z) v += a.Z[o];
+                if (a.accumulate) v += a.C[o];
+                a.C[o] = trunc_share(v, a.f, a.share);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) add_trunc_kernel(const u64* t, const u64* z, u64* out, uint64_t n, int f, int share) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = trunc_share(t[i] + (z ? z[i] : 0ull), f, share);
+}
+
+template <int BM, int BN, int BK, int TM, int TN>
+void launch_cfg(cgb_ctx* ctx, MatmulArgs& a) {
+    dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.k_splits);
+    matmul_kernel<BM, BN, BK, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, ctx->stream>>>(a);
+}
+
+// Runs the (up to two pair) product with optional Z / truncation epilogue.
+int run_matmul(cgb_ctx* ctx, MatmulArgs a) {
+    if (a.M == 0 || a.N == 0) return CGB_OK;
+    constexpr uint32_t BK = 16;
+    uint32_t BM, BN;
+    if (a.N > 32) { BM = 128; BN = 64; }
+    else if (a.N > 8) { BM = 128; BN = 16; }
+    else { BM = 256; BN = 8; }
+    const uint64_t tiles = (uint64_t)((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
+    // split K when the output alone cannot fill the machine
+    uint32_t splits = 1;
+    const uint64_t want = 2ull * ctx->num_sms;
+    if (tiles < want && a.K >= 8 * BK) {
+        uint64_t s = (want + tiles - 1) / tiles;
+        uint64_t max_s = a.K / (4 * BK);
+        splits = (uint32_t)std::max<uint64_t>(1, std::min(s, max_s));
+    }
+    uint32_t k_chunk = (a.K + splits - 1) / splits;
+    k_chunk = (k_chunk + BK - 1) / BK * BK;
+    if (k_chunk == 0) k_chunk = BK;
+    splits = a.K == 0 ? 1 : (a.K + k_chunk - 1) / k_chunk;
+    a.k_chunk = k_chunk;
+    a.k_splits = splits;
+
+    const u64* Z = a.Z;
+    u64* C = a.C;
+    const int f = a.f, share = a.share, accumulate = a.accumulate;
+    const bool needs_finish = splits > 1 && (Z != nullptr || f > 0);
+    if (splits > 1) {
+        // atomics accumulate onto a zeroed buffer (or onto C itself when accumulating without epilogue)
+        if (needs_finish || !accumulate) {
+            u64* T = C;
+            if (needs_finish) {
+                int rc = cgb_scratch_reserve(ctx, (size_t)a.M * a.N * sizeof(u64));
+                if (rc) return rc;
+                T = (u64*)ctx->scratch;
+            }
+            CGB_CHECK_CUDA(ctx, cudaMemsetAsync(T, 0, (size_t)a.M * a.N * sizeof(u64), ctx->stream));
+            a.C = T;
+        }
+        a.Z = nullptr; a.f = 0; a.accumulate = 0;
+    }
+    if (BN == 64) launch_cfg<128, 64, 16, 8, 4>(ctx, a);
+    else if (BN == 16) launch_cfg<128, 16, 16, 4, 2>(ctx, a);
+    else launch_cfg<256, 8, 16, 8, 1>(ctx, a);
+    CGB_CHECK_LAUNCH(ctx, "matmul_kernel");
+    if (needs_finish) {
+        const uint64_t n = (uint64_t)a.M * a.N;
+        // accumulate + finish: C = trunc(T + Z + (accumulate ? C : 0)) is only needed without accumulate here
+        unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->num_sms * 16);
+        add_trunc_kernel<<<blocks, 256, 0, ctx->stream>>>((const u64*)ctx->scratch, Z, C, n, f, share);
+        CGB_CHECK_LAUNCH(ctx, "add_trunc_kernel");
+    }
+    return CGB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cgb_matmul(cgb_ctx* ctx, const uint64_t* d_A, const uint64_t* d_B, uint64_t* d_C, uint32_t M, uint32_t K,
+               uint32_t N, int transA, int accumulate) {
+    CGB_REQUIRE(ctx, (d_A && d_B && d_C) || M == 0 || N == 0 || K == 0, "cgb_matmul: null argument");
+    CGB_REQUIRE(ctx, (const void*)d_C != (const void*)d_A && (const void*)d_C != (const void*)d_B,
+                "cgb_matmul: C must not alias A or B");
+    MatmulArgs a{};
+    a.A[0] = (const u64*)d_A; a.B[0] = (const u64*)d_B; a.n_pairs = 1;
+    a.Z = nullptr; a.C = (u64*)d_C; a.M = M; a.K = K; a.N = N;
+    a.transA = transA; a.accumulate = accumulate; a.f = 0; a.share = 0;
+    if (K == 0) {
+        if (!accumulate && M && N) CGB_CHECK_CUDA(ctx, cudaMemsetAsync(d_C, 0, (size_t)M * N * sizeof(u64), ctx->stream));
+        return CGB_OK;
+    }
+    return run_matmul(ctx, a);
+}
+
+int cgb_beaver_matmul_finish(cgb_ctx* ctx, const uint64_t* d_E, const uint64_t* d_F, const uint64_t* d_U,
+                             const uint64_t* d_V, const uint64_t* d_Z, uint64_t* d_C, uint32_t M, uint32_t K,
+                             uint32_t N, int share, int f) {
+    CGB_REQUIRE(ctx, d_E && d_F && d_U && d_V && d_Z && d_C, "cgb_beaver_matmul_finish: null argument");
+    CGB_REQUIRE(ctx, share == 0 || share == 1, "cgb_beaver_matmul_finish: bad share");
+    CGB_REQUIRE(ctx, f < 64, "cgb_beaver_matmul_finish: bad f");
+    CGB_REQUIRE(ctx, d_C != d_E && d_C != d_F && d_C != d_U && d_C != d_V && d_C != d_Z,
+                "cgb_beaver_matmul_finish: C must not alias the inputs");
+    if (M == 0 || N == 0) return CGB_OK;
+    // share 0 folds the E*F term into the first product: E*(V+F) + U*F
+    const u64* Bfirst = (const u64*)d_V;
+    if (share == 0) {
+        // keep V+F in the tail of the scratch buffer, after the split-K accumulator
+        const size_t acc_bytes = ((size_t)M * N * sizeof(u64) + 255) & ~(size_t)255;
+        int rc = cgb_scratch_reserve(ctx, acc_bytes + (size_t)K * N * sizeof(u64));
+        if (rc) return rc;
+        u64* VF = (u64*)((char*)ctx->scratch + acc_bytes);
+        rc = cgb_add(ctx, d_V, d_F, (uint64_t*)VF, (uint64_t)K * N);
+        if (rc) return rc;
+        Bfirst = VF;
+    }
+    MatmulArgs a{};
+    a.A[0] = (const u64*)d_E; a.B[0] = Bfirst;
+    a.A[1] = (const u64*)d_U; a.B[1] = (const u64*)d_F;
+    a.n_pairs = 2;
+    a.Z = (const u64*)d_Z; a.C = (u64*)d_C; a.M = M; a.K = K; a.N = N;
+    a.transA = 0; a.accumulate = 0; a.f = f; a.share = share;
+    return run_matmul(ctx, a);
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// prg.cu -- op (4): device-side PRG for correlated randomness (OM masks r/s, Beaver triples, share splitting).
+//
+// The reference draws its randomness inside the absent Task-Worker / SCI trees (CryptoUtil::intoShares,
+// optimize-gcn/gcn.h:70,96; OM preprocessing ss_vertex_centric_algo_kernel.h:536-613).  Here it is the RFC 8439
+// ChaCha20 block function used as a counter-mode PRG, so streams are reproducible bit for bit on CPU and GPU:
+//   word w (u64, little endian) of stream S = bytes [8*(w%8), +8) of block b = w/8,
+//   block b: key = key, counter = (u32) b, nonce = { (u32) S, (u32)(S>>32), (u32)(b>>32) }.
+// One thread computes one 64-byte block in registers (ALU-bound, ~1000 integer ops per block); a warp stages its
+// 32 blocks through shared memory so global stores (and the loads of the fused mask-subtract) are coalesced.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t rotl32(uint32_t v, int c) { return __funnelshift_l(v, v, c); }
+
+#define CGB_QR(a, b, c, d)              \
+    a += b; d ^= a; d = rotl32(d, 16);  \
+    c += d; b ^= c; b = rotl32(b, 12);  \
+    a += b; d ^= a; d = rotl32(d, 8);   \
+    c += d; b ^= c; b = rotl32(b, 7);
+
+struct Key { uint32_t k[8]; };
+
+constexpr int PRG_THREADS = 128;  // 4 warps, 32 blocks (2 KB) each
+
+// MODE 0: out = ks;  MODE 1: out = in - ks
+template <int MODE>
+__global__ void __launch_bounds__(PRG_THREADS) prg_kernel(const Key key, uint64_t stream, uint64_t word_offset,
+                                                         const u64* in, u64* out, uint64_t n_words,
+                                                         uint64_t first_blk, uint64_t n_blks) {
+    __shared__ uint32_t stage[PRG_THREADS / 32][32][17];  // +1 word padding: conflict-free column reads
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t warps_total = (uint64_t)gridDim.x * (PRG_THREADS / 32);
+    for (uint64_t wb = (uint64_t)blockIdx.x * (PRG_THREADS / 32) + warp; wb * 32 < n_blks; wb += warps_total) {
+        const uint64_t blk = first_blk + wb * 32 + lane;
+        uint32_t s[16], x[16];
+        s[0] = 0x61707865u; s[1] = 0x3320646eu; s[2] = 0x79622d32u; s[3] = 0x6b206574u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[4 + i] = key.k[i];
+        s[12] = (uint32_t)blk;
+        s[13] = (uint32_t)stream; s[14] = (uint32_t)(stream >> 32); s[15] = (uint32_t)(blk >> 32);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = s[i];
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            CGB_QR(x[0], x[4], x[8], x[12])
+            CGB_QR(x[1], x[5], x[9], x[13])
+            CGB_QR(x[2], x[6], x[10], x[14])
+            CGB_QR(x[3], x[7], x[11], x[15])
+            CGB_QR(x[0], x[5], x[10], x[15])
+            CGB_QR(x[1], x[6], x[11], x[12])
+            CGB_QR(x[2], x[7], x[8], x[13])
+            CGB_QR(x[3], x[4], x[9], x[14])
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) stage[warp][lane][i] = x[i] + s[i];
+        __syncwarp();
+        // the warp's 32 blocks = 256 consecutive u64 words starting at word (first_blk + wb*32) * 8
+        const uint64_t w0 = (first_blk + wb * 32) * 8;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int j = it * 32 + lane;  // word within the warp's span
+            const uint64_t w = w0 + j;
+            if (w >= word_offset && w < word_offset + n_words) {
+                const int b = j >> 3, q = j & 7;
+                const u64 ks = (u64)stage[warp][b][2 * q] | ((u64)stage[warp][b][2 * q + 1] << 32);
+                const uint64_t o = w - word_offset;
+                out[o] = MODE == 0 ? ks : in[o] - ks;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+int launch_prg(cgb_ctx* ctx, int mode, const uint32_t key[8], uint64_t stream, uint64_t word_offset, const u64* in,
+               u64* out, uint64_t n_words) {
+    if (n_words == 0) return CGB_OK;
+    Key k;
+    for (int i = 0; i < 8; ++i) k.k[i] = key[i];
+    const uint64_t first_blk = word_offset / 8, last_blk = (word_offset + n_words - 1) / 8;
+    const uint64_t n_blks = last_blk - first_blk + 1;
+    uint64_t warps = (n_blks + 31) / 32;
+    uint64_t blocks = (warps + (PRG_THREADS / 32) - 1) / (PRG_THREADS / 32);
+    const uint64_t cap = (uint64_t)ctx->num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    if (mode == 0)
+        prg_kernel<0><<<(unsigned)blocks, PRG_THREADS, 0, ctx->stream>>>(k, stream, word_offset, in, out, n_words,
+                                                                        first_blk, n_blks);
+    else
+        prg_kernel<1><<<(unsigned)blocks, PRG_THREADS, 0, ctx->stream>>>(k, stream, word_offset, in, out, n_words,
+                                                                        first_blk, n_blks);
+    CGB_CHECK_LAUNCH(ctx, "prg_kernel");
+    return CGB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cgb_prg_fill(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, uint64_t word_offset, uint64_t* d_out,
+                 uint64_t n_words) {
+    CGB_REQUIRE(ctx, key && (d_out || n_words == 0), "cgb_prg_fill: null argument");
+    return launch_prg(ctx, 0, key, stream, word_offset, nullptr, (u64*)d_out, n_words);
+}
+int cgb_prg_mask_sub(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, uint64_t word_offset,
+                     const uint64_t* d_in, uint64_t* d_out, uint64_t n_words) {
+    CGB_REQUIRE(ctx, key && ((d_in && d_out) || n_words == 0), "cgb_prg_mask_sub: null argument");
+    return launch_prg(ctx, 1, key, stream, word_offset, (const u64*)d_in, (u64*)d_out, n_words);
+}
+
+}  // extern "C"

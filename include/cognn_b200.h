@@ -1,0 +1,160 @@
+/*
+ * cognn_b200.h -- C ABI of the B200-native share-local engine for CoGNN's secret-shared GCN path.
+ *
+ * This is the drop-in boundary ("level B" of SURVEY.md 8b): the entry points a CoGNN build binds in place of
+ * the primitives its operators call but /root/reference does not define (Task-Worker / SCI-SilentOT / troy):
+ *
+ *   reference call site (file:line)                                     entry point here
+ *   ------------------------------------------------------------------  -------------------------------------
+ *   client/server_oblivious_mapper_online   ssk.h:752,760,818,848 /     cgb_expand_rows, cgb_sub (server mask)
+ *                                           ssk.h:1011,1016,1057,1075
+ *   prefix_network_aggregate(ADD_AGG)       optimize-gcn/gcn.h:328      cgb_segsum
+ *   expand+ScatterComp+OGA+extract fused    ssk.h:751-821, gcn.h:300    cgb_csr_create + cgb_gather_sum
+ *   sci::twoPartyGCNMatMul                  gcn.h:233,665,671,710       cgb_matmul, cgb_beaver_matmul_finish
+ *   sci::twoPartyGCNVectorScale             gcn.h:247,476               cgb_rowmul_beaver_finish
+ *   sci::twoPartyGCNCondVectorAddition      gcn.h:456                   cgb_rowmul_beaver_finish(f<0) + cgb_add,
+ *                                                                       cgb_cond_add (selector local)
+ *   sci::twoPartyGCNMatrixScale             gcn.h:676,723,764           cgb_scale_public
+ *   sci::twoPartyGCNApplyGradient           gcn.h:678,730               cgb_apply_gradient
+ *   sci::getPlainShareVecVec                gcn.h:604                   cgb_open_decode
+ *   CryptoUtil::intoShares / encode / merge gcn.h:70,96,220,80          cgb_share_split, cgb_encode, cgb_decode
+ *   transpose()                             gcn.h:230,648               cgb_transpose
+ *   correlated randomness (OM masks, Beaver triples)                    cgb_prg_fill
+ *   ("ssk.h" = include/ss_vertex_centric_algo_kernel.h, "gcn.h" = algo_kernels/vertex_centric/optimize-gcn/gcn.h)
+ *
+ * Conventions
+ *   - Every tensor is a dense row-major array of uint64_t additive shares in Z_2^64 (no padding, ld == cols).
+ *   - Pointers named d_* are DEVICE pointers on the context's GPU; h_* are HOST pointers.  No torch types.
+ *   - `share` is 0 for the owner's share (sci::ALICE == 1 in the reference) and 1 for the helper's (sci::BOB == 2).
+ *   - `f` is the number of fractional bits (SCALER_BIT_LENGTH in the reference, absent there; default CGB_SCALER_BITS).
+ *   - All device entry points enqueue on the context's stream and return without synchronising unless stated.
+ *   - Return value: 0 (CGB_OK) or a negative cgb_status; cgb_last_error() gives text.  The reference has no error
+ *     returns (printf + exit(-1), ssk.h:794-797); the C++ shim in cognn_b200/host maps non-zero to that behaviour.
+ *   - A context is single-threaded; distinct contexts are independent (one per (peer, role) thread of ssk.h:702-704).
+ *   - There is NO CPU fallback: creating a context without a CUDA device fails with CGB_ERR_NO_DEVICE.
+ */
+#ifndef COGNN_B200_H_
+#define COGNN_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGB_SCALER_BITS 16          /* default SCALER_BIT_LENGTH (must be < 31, gcn.h:191 uses int 1<<f) */
+#define CGB_NO_ROW 0xFFFFFFFFu      /* expand_rows: position missing in source (allowMissing, ssk.h:848-851) */
+
+typedef enum cgb_status {
+    CGB_OK = 0,
+    CGB_ERR_NO_DEVICE = -1,
+    CGB_ERR_CUDA = -2,
+    CGB_ERR_INVALID = -3,
+    CGB_ERR_NOMEM = -4
+} cgb_status;
+
+typedef struct cgb_ctx cgb_ctx; /* device + stream + scratch */
+typedef struct cgb_csr cgb_csr; /* device-resident CSR-by-destination + balanced work list */
+
+/* ---- library / context ---------------------------------------------------------------------------------- */
+const char* cgb_version(void);
+int cgb_device_count(void);
+int cgb_ctx_create(int device, cgb_ctx** out);
+/* adopt an existing cudaStream_t (e.g. torch's current stream); stream == NULL -> legacy default stream */
+int cgb_ctx_create_on_stream(int device, void* cuda_stream, cgb_ctx** out);
+int cgb_ctx_destroy(cgb_ctx* ctx);
+int cgb_ctx_sync(cgb_ctx* ctx);
+void* cgb_ctx_stream(cgb_ctx* ctx);
+const char* cgb_last_error(cgb_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t cgb_ctx_launch_count(cgb_ctx* ctx);
+
+/* ---- memory --------------------------------------------------------------------------------------------- */
+int cgb_malloc(cgb_ctx* ctx, size_t bytes, void** d_out);
+int cgb_free(cgb_ctx* ctx, void* d_ptr);
+int cgb_host_alloc(size_t bytes, void** h_out); /* pinned */
+int cgb_host_free(void* h_ptr);
+int cgb_memset(cgb_ctx* ctx, void* d_ptr, int value, size_t bytes);
+int cgb_h2d(cgb_ctx* ctx, void* d_dst, const void* h_src, size_t bytes); /* async on ctx stream */
+int cgb_d2h(cgb_ctx* ctx, void* h_dst, const void* d_src, size_t bytes); /* async on ctx stream */
+int cgb_d2d(cgb_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
+
+/* ---- (1) scatter / gather-sum ---------------------------------------------------------------------------- */
+/* Builds the device CSR for one destination block from HOST arrays (index vectors are built once in
+ * preprocessing, ssk.h:295-534): rowptr[n_rows+1], col[n_edges] (source row of each edge, rows grouped by
+ * destination ascending = updateSrcVertexPos order).  Also builds the balanced work list used by
+ * cgb_gather_sum.  Synchronises. */
+int cgb_csr_create(cgb_ctx* ctx, const uint32_t* h_rowptr, const uint32_t* h_col, uint32_t n_rows, uint64_t n_edges,
+                   uint32_t n_src_rows, cgb_csr** out);
+/* same, from DEVICE arrays (copied; caller keeps ownership of its arrays) */
+int cgb_csr_create_device(cgb_ctx* ctx, const uint32_t* d_rowptr, const uint32_t* d_col, uint32_t n_rows,
+                          uint64_t n_edges, uint32_t n_src_rows, cgb_csr** out);
+int cgb_csr_destroy(cgb_ctx* ctx, cgb_csr* csr);
+uint64_t cgb_csr_num_edges(const cgb_csr* csr);
+uint32_t cgb_csr_num_rows(const cgb_csr* csr);
+const uint32_t* cgb_csr_rowptr(const cgb_csr* csr); /* device pointers */
+const uint32_t* cgb_csr_col(const cgb_csr* csr);
+
+/* y[v,:] = (d_delta ? d_delta[v,:] : 0) + sum_{e in row v} d_x[col[e],:]
+ * d_x: n_src_rows x D;  d_delta, d_y: n_rows x D.  With d_x = x0 + (x1 - r) (own share plus the helper's OM online
+ * message, one cgb_add) and d_delta = A*r - s (offline correlation) this is the whole client side of
+ * expand -> ScatterComp -> prefix_network_aggregate -> extract in one pass over the edges.  d_y must not alias d_x. */
+int cgb_gather_sum(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x, const uint64_t* d_delta, uint64_t* d_y,
+                   uint32_t D);
+/* OM online, client side: y[j,:] = (idx[j]==CGB_NO_ROW ? 0 : x[idx[j],:]) + (delta ? delta[j,:] : 0) */
+int cgb_expand_rows(cgb_ctx* ctx, const uint32_t* d_idx, uint64_t n_out, const uint64_t* d_x,
+                    const uint64_t* d_delta, uint64_t* d_y, uint32_t D);
+/* prefix_network_aggregate ADD_AGG over dst-sorted rows: segment s = rows [segptr[s], segptr[s+1]).
+ * dup != 0: d_out is n_in x D and every row of a segment receives the segment sum; dup == 0: d_out is n_seg x D.
+ * d_in and d_out must not alias. */
+int cgb_segsum(cgb_ctx* ctx, const uint32_t* d_segptr, uint32_t n_seg, uint64_t n_in, const uint64_t* d_in,
+               uint64_t* d_out, uint32_t D, int dup);
+
+/* ---- (2) dense contraction mod 2^64 ---------------------------------------------------------------------- */
+/* C (M x N) = (accumulate ? C : 0) + op(A) * B.  op(A) = A (M x K), or A^T with A stored K x M if transA. */
+int cgb_matmul(cgb_ctx* ctx, const uint64_t* d_A, const uint64_t* d_B, uint64_t* d_C, uint32_t M, uint32_t K,
+               uint32_t N, int transA, int accumulate);
+/* Beaver recombination: C_i = trunc_i( Z_i + E*V_i + U_i*F + [share==0] E*F ), E = X-U (M x K), F = W-V (K x N)
+ * opened; f < 0 skips the truncation.  C must not alias the inputs. */
+int cgb_beaver_matmul_finish(cgb_ctx* ctx, const uint64_t* d_E, const uint64_t* d_F, const uint64_t* d_U,
+                             const uint64_t* d_V, const uint64_t* d_Z, uint64_t* d_C, uint32_t M, uint32_t K,
+                             uint32_t N, int share, int f);
+
+/* ---- (3) fused elementwise: truncation, masking / opening, scaling ---------------------------------------- */
+int cgb_add(cgb_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint64_t n);
+int cgb_sub(cgb_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint64_t n);
+int cgb_trunc(cgb_ctx* ctx, const uint64_t* d_x, uint64_t* d_out, uint64_t n, int f, int share);
+int cgb_scale_public(cgb_ctx* ctx, const uint64_t* d_x, uint64_t c, uint64_t* d_out, uint64_t n, int f, int share);
+int cgb_apply_gradient(cgb_ctx* ctx, const uint64_t* d_W, const uint64_t* d_d, uint64_t lr, uint64_t* d_out,
+                       uint64_t n, int f, int share);
+/* out = trunc_i( c + e*b[row] + fv[row]*a + [share==0] e*fv[row] ), f < 0: no truncation. */
+int cgb_rowmul_beaver_finish(cgb_ctx* ctx, const uint64_t* d_e, const uint64_t* d_fv, const uint64_t* d_a,
+                             const uint64_t* d_b, const uint64_t* d_c, uint64_t* d_out, uint64_t rows, uint32_t D,
+                             int share, int f);
+int cgb_cond_add(cgb_ctx* ctx, const uint64_t* d_v, const uint64_t* d_u, const uint8_t* d_cond, uint64_t* d_out,
+                 uint64_t rows, uint32_t D);
+int cgb_transpose(cgb_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint32_t rows, uint32_t cols);
+int cgb_encode(cgb_ctx* ctx, const double* d_x, uint64_t* d_out, uint64_t n, int f);
+int cgb_decode(cgb_ctx* ctx, const uint64_t* d_v, double* d_out, uint64_t n, int f);
+/* s1 = PRG(key, stream, word_offset ...), s0 = enc(x) - s1 */
+int cgb_share_split(cgb_ctx* ctx, const double* d_x, uint64_t n, int f, const uint32_t key[8], uint64_t stream,
+                    uint64_t word_offset, uint64_t* d_s0, uint64_t* d_s1);
+int cgb_open_decode(cgb_ctx* ctx, const uint64_t* d_s0, const uint64_t* d_s1, double* d_out, uint64_t n, int f);
+
+/* ---- (4) device PRG (ChaCha20 block function, RFC 8439; stream layout in DESIGN.md) ------------------------ */
+int cgb_prg_fill(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, uint64_t word_offset, uint64_t* d_out,
+                 uint64_t n_words);
+/* out = in - PRG(...): the server side of the OM online message (x1 - r) without materialising r */
+int cgb_prg_mask_sub(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, uint64_t word_offset,
+                     const uint64_t* d_in, uint64_t* d_out, uint64_t n_words);
+
+/* ---- host-buffer entry point (what a CoGNN operator holding std::vector data calls) ------------------------ */
+/* One gather-sum step with HOST share rows: H2D of x (and delta if given), kernel, D2H of y,
+ * synchronises.  h_x / h_y should be pinned (cgb_host_alloc) for full PCIe rate.  The CSR stays device resident.  bench.py's `e2e` times this. */
+int cgb_host_gather_sum(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* h_x, const uint64_t* h_delta,
+                        uint64_t* h_y, uint32_t D);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COGNN_B200_H_ */

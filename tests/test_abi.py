@@ -1,0 +1,53 @@
+"""The C-ABI library loads and exports every symbol include/cognn_b200.h declares (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import cognn_b200
+from cognn_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "cognn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cgb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_is_built_in_tree():
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    assert os.path.dirname(_lib.LIB_PATH) == os.path.join(ROOT, "cognn_b200")
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = cognn_b200.load()
+    names = declared_symbols()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    for n in _lib.SIGNATURES:
+        assert n in names, f"{n} bound but not declared in the header"
+
+
+def test_version_and_no_cpu_fallback():
+    lib = cognn_b200.load()
+    assert b"sm_100a" in lib.cgb_version()
+    if lib.cgb_device_count() == 0:
+        h = ctypes.c_void_p()
+        rc = lib.cgb_ctx_create(0, ctypes.byref(h))
+        assert rc == -1 and not h.value  # CGB_ERR_NO_DEVICE: the product path fails loudly without a GPU
+        assert b"no CPU fallback" in lib.cgb_last_error(None)
+
+
+def test_sass_is_sm100a_only():
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        return
+    out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
