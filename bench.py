@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- share-gather throughput of the secret-shared GCN path (BASELINE.json metric), B200 vs host CPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA kernels through the C ABI)
+  python bench.py --impl reference [...]                          the reference's CPU path (oracle port, see below)
+  torchrun ... bench.py --gpus N ...                              one rank per GPU == one party per GPU
+
+Workload (config.workload): BASELINE.json configs[4], the largest single-GPU configuration -- gather-sum of Z_2^64
+share rows over a synthetic RMAT power-law graph, E = 100M edges, N = E/16 vertices, D = 16 u64 columns (hidden_dim
+of every reference config).  One "step" = one pass of the fused scatter/gather-sum (expand -> ScatterComp copy ->
+prefix_network_aggregate -> extract of one GAS iteration, ss_vertex_centric_algo_kernel.h:751-821) over all edges
+a party owns.  With N > 1 ranks every rank is one party holding E edges whose destinations are spread over all
+parties by `vid % N` (tools/data_transform.py:25): the step is the fused gather into one N_p x D block per
+destination party, the NCCL all-to-all of those mirror-update blocks (ssk.h:835 -> 1067/1090) and
+the share-local sum of the received blocks (GatherComp add, optimize-gcn/gcn.h:456).  Weak scaling: edges per GPU
+are fixed.  WAN / 2PC-residual costs are out of scope on both arms.
+
+The reference cannot be built here (its arithmetic is in un-vendored trees), so `--impl reference` and
+`cpu_baseline` time the CPU oracle (oracle/cgb_oracle.c, a restatement of the same path; kind = "port") with all
+host threads on a bounded sample of the same graph.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "share_gather_edges_per_sec"
+UNIT = "edges/s"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# synthetic graph (torch; runs on the GPU for the full size, on the CPU for small local checks)
+# ------------------------------------------------------------------------------------------------------------
+def rmat_edges(torch, n_vertices, n_edges, seed, device, a=0.57, b=0.19, c=0.19):
+    """RMAT(a,b,c) directed edge list folded onto [0, n_vertices): returns (src, dst) int64."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    bits = max(1, (n_vertices - 1).bit_length())
+    src = torch.zeros(n_edges, dtype=torch.int64, device=device)
+    dst = torch.zeros(n_edges, dtype=torch.int64, device=device)
+    for _ in range(bits):
+        r = torch.rand(n_edges, device=device, generator=g)
+        sbit = (r >= a + b).long()                       # quadrants c, d -> source bit 1
+        dbit = ((r >= a) & (r < a + b) | (r >= a + b + c)).long()  # quadrants b, d -> destination bit 1
+        src = (src << 1) | sbit
+        dst = (dst << 1) | dbit
+        del r, sbit, dbit
+    # decorrelate ids from degree (RMAT puts the hubs at small ids) with a fixed odd multiplier, then fold
+    src = (src * 2654435761 + 12345) % n_vertices
+    dst = (dst * 2246822519 + 54321) % n_vertices
+    return src, dst
+
+
+def build_party_csr(torch, n_local, n_edges, n_parties, rank, seed, device):
+    """CSR-by-destination of the edges party `rank` owns.  Sources are its local vertices (row index 0..n_local),
+    destinations are global vertices grouped by owner: output row of global vertex v = (v % P) * n_local + v // P."""
+    n_global = n_local * n_parties
+    src, dst = rmat_edges(torch, n_global, n_edges, seed + 1000 * rank, device)
+    src = src % n_local  # the party's own vertices (local row index)
+    out_row = (dst % n_parties) * n_local + dst // n_parties
+    del dst
+    key = out_row * n_local + src  # sort by destination row, sources ascending inside a row (ssk.h:295-314 order)
+    del out_row, src
+    key = torch.sort(key).values
+    out_row = key // n_local
+    col = (key - out_row * n_local).int()
+    del key
+    counts = torch.bincount(out_row, minlength=n_global)
+    del out_row
+    rowptr = torch.zeros(n_global + 1, dtype=torch.int64, device=device)
+    rowptr[1:] = torch.cumsum(counts, 0)
+    return rowptr.int(), col
+
+
+def algorithmic_bytes(n_rows, n_edges, D):
+    # SURVEY.md 8d, fused SpMM form: every edge = one 8*D-byte row read + a 4-byte index, no cache-reuse credit
+    return (8 * D + 4) * n_edges + 4 * (n_rows + 1) + 8 * D * n_rows
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for (_, l) in self.lines]
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in rows:
+            p = [x.strip() for x in l.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx = float(p[1])
+            except ValueError:
+                continue
+            for nme, val in zip(names, p[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(D):
+    """dram bytes per gather_sum launch from the committed ncu --set full capture of this command, or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("gather_sum_kernel", {}).get(f"D{D}_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def cpu_sample(torch, rowptr, col, x, D, frac_rows, reps=3, threads=None):
+    """Times the CPU oracle on the first `frac_rows` destination rows of the SAME graph (same index skew, same
+    random row reads into the full x).  Returns (edges/s, description, threads)."""
+    import numpy as np
+
+    from oracle import pyoracle
+
+    pyoracle.build()
+    if threads:
+        pyoracle.set_num_threads(threads)
+    n_rows = rowptr.numel() - 1
+    rows = max(1, int(n_rows * frac_rows))
+    rp = rowptr[: rows + 1].cpu().numpy().view(np.uint32).copy()
+    e = int(rp[-1])
+    cl = col[:e].cpu().numpy().view(np.uint32).copy()
+    xh = x.cpu().numpy().view(np.uint64)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        pyoracle.gather_sum_csr(rp, cl, xh)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return e / best, f"first {rows} of {n_rows} destination rows ({e} edges) of the same graph, best of {reps}", \
+        pyoracle.num_threads(), best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--edges", type=int, default=100_000_000, help="edges per party (per GPU)")
+    ap.add_argument("--dim", type=int, default=16, help="u64 columns per share row (hidden_dim)")
+    ap.add_argument("--cpu-frac", type=float, default=0.25, help="fraction of rows in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    K = max(args.steps, 1)
+    D = args.dim
+    E = args.edges
+    n_local = max(1, E // 16)
+    P = world if world > 1 else 1
+    config = {
+        "workload": f"configs[4] kernel sweep: fused share gather-sum, RMAT(0.57,0.19,0.19) power-law graph, "
+                    f"{E} edges and {n_local} vertices per party, D={D} u64 columns, {P} part{'y' if P == 1 else 'ies'}",
+        "edges_per_party": E, "vertices_per_party": n_local, "D": D, "parties": P,
+        "l2": "inputs larger than L2 (share rows + indices >> 126 MB); no flush needed",
+        "seed": 42,
+    }
+
+    # -------------------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        if dev == "cpu":
+            E_ref = min(E, 2_000_000)  # local smoke only
+            n_ref = max(1, E_ref // 16)
+        else:
+            E_ref, n_ref = E, n_local
+        rowptr, col = build_party_csr(torch, n_ref, E_ref, 1, 0, 42, dev)
+        g = torch.Generator(device=dev).manual_seed(43)
+        x = torch.randint(-2**63, 2**63 - 1, (n_ref, D), dtype=torch.int64, device=dev, generator=g)
+        import numpy as np
+
+        from oracle import pyoracle
+
+        pyoracle.build()
+        rows = max(1, int(n_ref * args.cpu_frac))
+        rp = rowptr[: rows + 1].cpu().numpy().view(np.uint32).copy()
+        e = int(rp[-1])
+        cl = col[:e].cpu().numpy().view(np.uint32).copy()
+        xh = x.cpu().numpy().view(np.uint64)
+        del rowptr, col, x
+        for _ in range(args.warmup):
+            pyoracle.gather_sum_csr(rp, cl, xh)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            pyoracle.gather_sum_csr(rp, cl, xh)
+        dt = time.perf_counter() - t0
+        val = e * K / dt
+        sample = f"each step = first {rows} of {n_ref} destination rows ({e} edges) of the same graph"
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+                "warmup": args.warmup, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": pyoracle.num_threads(), "kind": "port",
+                                 "sample": sample},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0,
+                "note": "CPU oracle port of the reference path (reference unbuildable here, SURVEY.md 8c); host cores only"}
+        print(json.dumps(line))
+        return 0
+
+    # -------------------------------------------------------------------------------------------------------
+    import cognn_b200
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = cognn_b200.Context(local_rank)
+
+    rowptr, col = build_party_csr(torch, n_local, E, P, rank, 42, dev)
+    csr = ctx.csr_create(rowptr, col, n_local)
+    g = torch.Generator(device=dev).manual_seed(43 + rank)
+    x = torch.randint(-2**63, 2**63 - 1, (n_local, D), dtype=torch.int64, device=dev, generator=g)
+    y = torch.empty((n_local * P, D), dtype=torch.int64, device=dev)
+    recv = torch.empty_like(y) if P > 1 else None
+    v = torch.empty((n_local, D), dtype=torch.int64, device=dev) if P > 1 else None
+
+    def step():
+        ctx.gather_sum(csr, x, None, out=y)
+        if P > 1:
+            dist.all_to_all_single(recv, y)  # mirror-update blocks: block i of y -> party i
+            blocks = recv.view(P, n_local, D)
+            ctx.add(blocks[0], blocks[1], out=v)
+            for j in range(2, P):
+                ctx.add(v, blocks[j], out=v)
+
+    def barrier():
+        if P > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        step()
+    barrier()
+    # kernel-only duration of the dominant kernel (gather_sum) for the roofline, CUDA events on the launch stream
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    launches0 = ctx.launches
+    t_wall0 = time.time()
+    torch.cuda.profiler.start()  # ncu --profile-from-start off captures exactly the timed region
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        if P == 1:
+            kev[i][0].record()
+            step()
+            kev[i][1].record()
+        else:
+            kev[i][0].record()
+            ctx.gather_sum(csr, x, None, out=y)
+            kev[i][1].record()
+            dist.all_to_all_single(recv, y)
+            blocks = recv.view(P, n_local, D)
+            ctx.add(blocks[0], blocks[1], out=v)
+            for j in range(2, P):
+                ctx.add(v, blocks[j], out=v)
+    e1.record()
+    barrier()
+    torch.cuda.profiler.stop()
+    t_wall1 = time.time()
+    launches = ctx.launches - launches0
+    clocks = sampler.stop(t_wall0, t_wall1)
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / K
+    if P > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / K
+    value = E * P / (ms_per_step * 1e-3)
+
+    peak, peak_src = measured_peak_hbm()
+    n_rows = n_local * P
+    alg = algorithmic_bytes(n_rows, E, D)
+    achieved = alg / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "gather_sum_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(D), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "kernel_ms": kernel_ms,
+                "frac_of_8TBs_nominal": achieved / 8000.0}
+
+    # ---- e2e: host buffers through the C-ABI host entry point, H2D + D2H inside the timed region -----------
+    e2e = None
+    if not args.no_e2e:
+        import ctypes as C
+
+        lib = ctx.lib
+        xb, yb = n_local * D * 8, n_rows * D * 8
+        hx = torch.empty((n_local, D), dtype=torch.int64).pin_memory()
+        hy = torch.empty((n_rows, D), dtype=torch.int64).pin_memory()
+        hx.copy_(x.cpu())
+        hv = torch.empty((n_local, D), dtype=torch.int64).pin_memory() if P > 1 else None
+
+        def e2e_step():
+            if P == 1:
+                ctx.check(lib.cgb_host_gather_sum(ctx.handle, csr.handle, C.c_void_p(hx.data_ptr()), None,
+                                                  C.c_void_p(hy.data_ptr()), D))
+            else:
+                x.copy_(hx, non_blocking=True)
+                step()
+                hv.copy_(v, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        k2 = max(3, min(K, 10))
+        t0 = time.perf_counter()
+        for _ in range(k2):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if P > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": E * P * k2 / dt, "unit": UNIT, "h2d_bytes_per_step": xb,
+               "d2h_bytes_per_step": yb if P == 1 else n_local * D * 8, "steps": k2,
+               "api": "cgb_host_gather_sum (pinned host share rows in, gathered rows out; CSR resident)" if P == 1
+               else "host share rows -> H2D -> gather + NCCL exchange + sum -> D2H"}
+        # spot check of the e2e result against the device-resident result
+        if P == 1:
+            assert torch.equal(hy[:1000], y[:1000].cpu())
+
+    # ---- CPU baseline on rank 0 at N == 1 -------------------------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and P == 1 and not args.no_cpu_baseline:
+        val, sample, cores, secs = cpu_sample(torch, rowptr, col, x, D, args.cpu_frac)
+        cpu_baseline = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                        "seconds": secs}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": P, "steps": K, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line))
+    if P > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,116 @@
+"""GPU parity (bit exact) of ops (2), (3), (4) against the CPU oracle, through the C ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import rand_u64, to_dev, to_np
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("M,K,N", [(1, 1, 1), (5, 3, 2), (130, 17, 7), (257, 1433, 16), (300, 64, 40), (129, 500, 3),
+                                    (64, 128, 256), (1000, 33, 65)])
+def test_matmul_matches_oracle(cgb, oracle, M, K, N):
+    rng = np.random.default_rng(M * 7 + K * 3 + N)
+    A, B = rand_u64(rng, M, K), rand_u64(rng, K, N)
+    want = oracle.matmul(A, B)
+    assert np.array_equal(to_np(cgb.matmul(to_dev(A), to_dev(B))), want)
+    At = np.ascontiguousarray(A.T)
+    assert np.array_equal(to_np(cgb.matmul(to_dev(At), to_dev(B), transA=True)), want)
+    C0 = rand_u64(rng, M, N)
+    out = to_dev(C0)
+    cgb.matmul(to_dev(A), to_dev(B), out=out, accumulate=True)
+    assert np.array_equal(to_np(out), oracle.matmul(A, B, C_in=C0))
+
+
+def test_matmul_split_k_weight_gradient_shape(cgb, oracle):
+    # d = h_t * v (gcn.h:671): K = N_p is long, the output F x H tile is small -> split-K with 64-bit atomics
+    rng = np.random.default_rng(11)
+    n_p, F, H = 5000, 128, 16
+    X, G = rand_u64(rng, n_p, F), rand_u64(rng, n_p, H)
+    want = oracle.matmul(X, G, transA=True)
+    assert np.array_equal(to_np(cgb.matmul(to_dev(X), to_dev(G), transA=True)), want)
+    C0 = rand_u64(rng, F, H)
+    out = to_dev(C0)
+    cgb.matmul(to_dev(X), to_dev(G), transA=True, out=out, accumulate=True)
+    assert np.array_equal(to_np(out), oracle.matmul(X, G, transA=True, C_in=C0))
+
+
+@pytest.mark.parametrize("M,K,N", [(9, 6, 4), (700, 500, 16), (64, 4000, 8), (300, 128, 256)])
+@pytest.mark.parametrize("f", [-1, 16])
+def test_beaver_matmul_finish_matches_oracle(cgb, oracle, M, K, N, f):
+    rng = np.random.default_rng(M + K + N)
+    E, F, U, V, Z = (rand_u64(rng, M, K), rand_u64(rng, K, N), rand_u64(rng, M, K), rand_u64(rng, K, N),
+                     rand_u64(rng, M, N))
+    for share in (0, 1):
+        want = oracle.beaver_matmul_finish(E, F, U, V, Z, share, f)
+        got = cgb.beaver_matmul_finish(to_dev(E), to_dev(F), to_dev(U), to_dev(V), to_dev(Z), share, f)
+        assert np.array_equal(to_np(got), want)
+
+
+def test_elementwise_match_oracle(cgb, oracle):
+    rng = np.random.default_rng(21)
+    for n in (1, 2, 3, 1000, 4097):
+        a, b = rand_u64(rng, n), rand_u64(rng, n)
+        da, db = to_dev(a), to_dev(b)
+        assert np.array_equal(to_np(cgb.add(da, db)), oracle.add(a, b))
+        assert np.array_equal(to_np(cgb.sub(da, db)), oracle.sub(a, b))
+        for share in (0, 1):
+            assert np.array_equal(to_np(cgb.trunc(da, share, 16)), oracle.trunc(a, 16, share))
+            assert np.array_equal(to_np(cgb.scale_public(da, 12345, share, 16)), oracle.scale_public(a, 12345, 16, share))
+            assert np.array_equal(to_np(cgb.apply_gradient(da, db, 32768, share, 16)),
+                                  oracle.apply_gradient(a, b, 32768, 16, share))
+        # unaligned views (odd element offset -> scalar path) and in-place (reference aliases in/out, gcn.h:676)
+        if n > 3:
+            assert np.array_equal(to_np(cgb.add(da[1:], db[1:])), oracle.add(a[1:], b[1:]))
+            tmp = da.clone()
+            cgb.scale_public(tmp, 777, 0, 16, out=tmp)
+            assert np.array_equal(to_np(tmp), oracle.scale_public(a, 777, 16, 0))
+
+
+@pytest.mark.parametrize("rows,D", [(1, 1), (11, 6), (1354, 16), (500, 7)])
+def test_rowmul_cond_transpose_match_oracle(cgb, oracle, rows, D):
+    rng = np.random.default_rng(rows + D)
+    e, a, c = rand_u64(rng, rows, D), rand_u64(rng, rows, D), rand_u64(rng, rows, D)
+    fv, b = rand_u64(rng, rows), rand_u64(rng, rows)
+    for share in (0, 1):
+        for f in (-1, 16):
+            want = oracle.rowmul_beaver_finish(e, fv, a, b, c, share, f)
+            got = cgb.rowmul_beaver_finish(to_dev(e), to_dev(fv), to_dev(a), to_dev(b), to_dev(c), share, f)
+            assert np.array_equal(to_np(got), want)
+    cond = (rng.integers(0, 2, size=rows)).astype(np.uint8)
+    assert np.array_equal(to_np(cgb.cond_add(to_dev(e), to_dev(a), to_dev(cond))), oracle.cond_add(e, a, cond))
+    assert np.array_equal(to_np(cgb.transpose(to_dev(e))), oracle.transpose(e))
+
+
+def test_encode_split_open_match_oracle(cgb, oracle):
+    rng = np.random.default_rng(33)
+    x = rng.normal(size=(123, 17)) * 50
+    x.ravel()[:4] = [0.0, -0.0, 1.0 / 3.0, -1.0 / 3.0]
+    key = [9, 8, 7, 6, 5, 4, 3, 2]
+    assert np.array_equal(to_np(cgb.encode(to_dev(x))), oracle.encode(x, 16))
+    s0, s1 = cgb.share_split(to_dev(x), key, stream=77, word_offset=5)
+    w0, w1 = oracle.share_split(x, 16, key, 77, 5)
+    assert np.array_equal(to_np(s0), w0) and np.array_equal(to_np(s1), w1)
+    assert np.array_equal(to_np(cgb.open_decode(s0, s1)), oracle.open_decode(w0, w1, 16))
+    assert np.array_equal(to_np(cgb.decode(s0)), oracle.decode(w0, 16))
+
+
+def test_prg_matches_openssl_golden_and_oracle(cgb, oracle):
+    cases = json.load(open(os.path.join(HERE, "golden", "chacha20_openssl.json")))["cases"]
+    for c in cases:
+        words = np.array([int(w) for w in c["words"]], dtype=np.uint64)
+        got = cgb.prg_fill(c["key"], c["stream"], c["word_offset"], words.size)
+        assert np.array_equal(to_np(got), words)
+        got = cgb.prg_fill(c["key"], c["stream"], c["word_offset"] + 3, words.size - 5)
+        assert np.array_equal(to_np(got), words[3:-2])
+    key = [45, 0, 1, 2, 3, 4, 5, 6]
+    for off, n in [(0, 1), (7, 1), (8, 300), (13, 100_003)]:
+        want = oracle.prg_fill(key, 0x1234567890, off, n)
+        assert np.array_equal(to_np(cgb.prg_fill(key, 0x1234567890, off, n)), want)
+        x = rand_u64(np.random.default_rng(n), n)
+        assert np.array_equal(to_np(cgb.prg_mask_sub(key, 0x1234567890, off, to_dev(x))), x - want)
+    assert cgb.prg_fill(key, 1, 0, 0).numel() == 0

@@ -1,0 +1,125 @@
+"""GPU parity (bit exact) of op (1) -- gather-sum / expand / segsum -- against the CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+from tests.util import power_law_csr, rand_u64, to_dev, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("D", [1, 2, 3, 7, 16, 40, 64, 100, 128, 131])
+def test_gather_sum_matches_oracle(cgb, oracle, D):
+    rng = np.random.default_rng(100 + D)
+    n_dst, n_src = 3000, 2500
+    rowptr, col = power_law_csr(rng, n_dst, n_src, 40000)
+    assert (np.diff(rowptr.astype(np.int64)) > 256).any(), "case must contain long (sliced) rows"
+    x, delta = rand_u64(rng, n_src, D), rand_u64(rng, n_dst, D)
+    csr = cgb.csr_create(to_dev(rowptr, "cpu"), to_dev(col, "cpu"), n_src)
+    dx, dd = to_dev(x), to_dev(delta)
+    for use_delta in (False, True):
+        want = oracle.gather_sum_csr(rowptr, col, x, delta if use_delta else None)
+        got = cgb.gather_sum(csr, dx, dd if use_delta else None)
+        assert np.array_equal(to_np(got), want)
+        # second launch reuses the self-resetting arrival counters
+        got = cgb.gather_sum(csr, dx, dd if use_delta else None)
+        assert np.array_equal(to_np(got), want)
+    csr.destroy()
+
+
+def test_gather_sum_device_csr_and_edge_cases(cgb, oracle):
+    import torch
+
+    rng = np.random.default_rng(7)
+    # empty graph rows, single row, all edges in one row (one very long row), zero rows
+    for n_dst, degs in [(5, [0, 0, 0, 0, 0]), (1, [1]), (3, [0, 5000, 0]), (4, [257, 256, 255, 1])]:
+        rowptr = np.zeros(n_dst + 1, dtype=np.uint32)
+        rowptr[1:] = np.cumsum(degs)
+        n_src = 50
+        col = rng.integers(0, n_src, size=int(rowptr[-1])).astype(np.uint32)
+        x = rand_u64(rng, n_src, 16)
+        csr = cgb.csr_create(to_dev(rowptr), to_dev(col) if col.size else torch.empty(0, dtype=torch.int32, device="cuda"),
+                             n_src)
+        got = cgb.gather_sum(csr, to_dev(x))
+        assert np.array_equal(to_np(got), oracle.gather_sum_csr(rowptr, col, x))
+        csr.destroy()
+
+
+def test_cora_small_worked_example(cgb, oracle):
+    """party 0 of the cora_small shape; U_loc = [X2, X0], mirror block = [X0+X2, X2]."""
+    from oracle import graph_index as gi
+
+    edges = [(0, 1), (1, 0), (1, 2), (2, 1), (2, 3), (3, 2), (0, 2), (2, 0)]
+    tiles, ivs = gi.build_all(edges, [0, 1, 0, 1], 2)
+    iv = ivs[0]
+    rng = np.random.default_rng(3)
+    X = rand_u64(rng, 2, 3)  # rows: vertex 0, vertex 2
+    rp, col = gi.csr_from_pos(iv["updateSrcVertexPos"][0], iv["updateDstVertexPos"][0], iv["localVertexPos"], iv["localVertexPos"])
+    csr = cgb.csr_create(to_dev(rp, "cpu"), to_dev(col, "cpu"), 2)
+    got = to_np(cgb.gather_sum(csr, to_dev(X)))
+    assert np.array_equal(got, np.stack([X[1], X[0]]))
+    rp, col = gi.csr_from_pos(iv["updateSrcVertexPos"][1], iv["updateDstVertexPos"][1], iv["localVertexPos"], ivs[1]["localVertexPos"])
+    csr1 = cgb.csr_create(to_dev(rp, "cpu"), to_dev(col, "cpu"), 2)
+    got = to_np(cgb.gather_sum(csr1, to_dev(X)))
+    assert np.array_equal(got, np.stack([X[0] + X[1], X[1]]))
+    csr.destroy(); csr1.destroy()
+
+
+@pytest.mark.parametrize("D", [3, 16, 40, 130])
+def test_expand_and_segsum_match_oracle(cgb, oracle, D):
+    rng = np.random.default_rng(200 + D)
+    n_dst, n_src = 800, 700
+    rowptr, col = power_law_csr(rng, n_dst, n_src, 9000)
+    x = rand_u64(rng, n_src, D)
+    delta = rand_u64(rng, col.size, D)
+    idx = col.copy()
+    idx[::17] = 0xFFFFFFFF  # allowMissing positions
+    for dl in (None, delta):
+        want = oracle.expand_rows(idx, x, dl)
+        got = cgb.expand_rows(to_dev(idx), to_dev(x), None if dl is None else to_dev(dl))
+        assert np.array_equal(to_np(got), want)
+    exp = oracle.expand_rows(col, x)
+    for dup in (False, True):
+        want = oracle.segsum(rowptr, exp, dup)
+        got = cgb.segsum(to_dev(rowptr), to_dev(exp), dup)
+        assert np.array_equal(to_np(got), want)
+    # four-step dataflow of the reference == fused gather
+    fused = cgb.gather_sum(cgb.csr_create(to_dev(rowptr), to_dev(col), n_src), to_dev(x))
+    assert np.array_equal(to_np(fused), oracle.segsum(rowptr, exp, False))
+
+
+def test_om_online_protocol_reconstructs(cgb, oracle):
+    """Client y0 = A(x0 + (x1 - r)) + (A r - s), server y1 = s  =>  y0 + y1 = A x  (ssk.h:751-821 composite)."""
+    rng = np.random.default_rng(9)
+    n_dst, n_src, D = 500, 400, 16
+    rowptr, col = power_law_csr(rng, n_dst, n_src, 6000)
+    key = [45, 1, 2, 3, 4, 5, 6, 7]
+    x = rand_u64(rng, n_src, D)
+    x1 = rand_u64(rng, n_src, D)
+    x0 = x - x1
+    csr = cgb.csr_create(to_dev(rowptr), to_dev(col), n_src)
+    r = cgb.prg_fill(key, 1, 0, n_src * D).view(n_src, D)
+    s = cgb.prg_fill(key, 2, 0, n_dst * D).view(n_dst, D)
+    delta = cgb.sub(cgb.gather_sum(csr, r), s)           # offline: A r - s
+    m = cgb.prg_mask_sub(key, 1, 0, to_dev(x1))           # server message x1 - r
+    y0 = cgb.gather_sum(csr, cgb.add(to_dev(x0), m), delta)
+    y = to_np(y0) + to_np(s)
+    assert np.array_equal(y, oracle.gather_sum_csr(rowptr, col, x))
+
+
+def test_large_graph_properties(cgb):
+    """At bench scale the oracle is too slow: check linearity and the checksum identity sum(y) = sum_e x[col[e]]."""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n, E, D = 200_000, 3_000_000, 16
+    dst = torch.sort((torch.rand(E, device="cuda", generator=g) ** 3 * n).long().clamp_(max=n - 1)).values
+    col = (torch.rand(E, device="cuda", generator=g) ** 2 * n).long().clamp_(max=n - 1).int()
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=n), 0)
+    csr = cgb.csr_create(rowptr.int(), col, n)
+    a = torch.randint(-2**63, 2**63 - 1, (n, D), device="cuda", dtype=torch.int64, generator=g)
+    b = torch.randint(-2**63, 2**63 - 1, (n, D), device="cuda", dtype=torch.int64, generator=g)
+    ya, yb, yab = cgb.gather_sum(csr, a), cgb.gather_sum(csr, b), cgb.gather_sum(csr, a + b)
+    assert torch.equal(ya + yb, yab)  # int64 wraps like Z_2^64
+    assert torch.equal(ya.sum(0), a[col.long()].sum(0))
+    csr.destroy()
