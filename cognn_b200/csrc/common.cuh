@@ -37,7 +37,20 @@ struct cgb_csr {
     uint32_t counters_len = 0;
     uint64_t* d_partial = nullptr;      // n_slices x D partial sums (grow-only)
     size_t partial_words = 0;
+    // ---- edge-balanced schedule (gather_chunk_kernel): fixed chunks of CGB_CHUNK_EDGES edges ----
+    uint32_t* d_colf = nullptr;         // col | CGB_END_FLAG on the last edge of every row
+    uint32_t* d_nz_row = nullptr;       // ids of the non-empty rows, ascending
+    uint32_t* d_empty_row = nullptr;    // ids of the empty rows
+    uint32_t* d_chunk_nz = nullptr;     // per chunk: index into nz_row of the row holding its first edge;
+                                        // bit 31: that row started in an earlier chunk
+    uint32_t n_nz = 0, n_empty = 0, n_chunks = 0;
+    uint32_t* d_chunk_ctr = nullptr;    // n_chunks * col tiles arrival counters (self-resetting)
+    uint32_t chunk_ctr_len = 0;
+    uint64_t* d_piece = nullptr;        // 2 * n_chunks x D: [head pieces | tail pieces] (grow-only)
+    size_t piece_words = 0;
 };
+#define CGB_CHUNK_EDGES 64u
+#define CGB_END_FLAG 0x80000000u
 
 #define CGB_LONG_ROW 256u
 #define CGB_SLICE_EDGES 256u
