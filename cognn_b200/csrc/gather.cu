@@ -189,13 +189,11 @@ struct ChunkArgs {
     u64* piece_tail;  // n_chunks x D: sum of the chunk's trailing edges when their row continues in a later chunk
 };
 
-// a row segment cut by a chunk boundary; rare relative to the edge loop, so kept out of line
+// A row segment cut by a chunk boundary has been stored as a "piece"; count the arrival and, if this was the last
+// piece of the row, fold them.  Rare relative to the edge loop, so kept out of line.
 template <int VEC, int LANES>
-__device__ __noinline__ void chunk_piece(const ChunkArgs& a, Acc<VEC> acc, uint32_t row, uint32_t c, uint32_t ct,
-                                         uint32_t col0, bool active, int kind /*1 head piece, 2 tail piece*/,
-                                         int lane, unsigned mask) {
-    u64* slot = (kind == 1 ? a.piece_head : a.piece_tail) + (size_t)c * a.D + col0;
-    if (active) acc.store(slot);
+__device__ __noinline__ void piece_arrive(const ChunkArgs& a, uint32_t row, uint32_t ct, uint32_t col0, bool active,
+                                          int lane, unsigned mask) {
     __threadfence();
     __syncwarp(mask);
     const uint32_t rb = __ldg(a.rowptr + row), re = __ldg(a.rowptr + row + 1);
@@ -224,8 +222,8 @@ __device__ __noinline__ void chunk_piece(const ChunkArgs& a, Acc<VEC> acc, uint3
     }
 }
 
-template <int VEC, int LANES, int U, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (U >= 8 ? 1024 : 1280) / BLOCK)
+template <int VEC, int LANES, int U, int BLOCK, int OCC_THREADS>
+__global__ void __launch_bounds__(BLOCK, OCC_THREADS / BLOCK)
 gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
     constexpr int GROUPS = BLOCK / LANES;
     const int lane = threadIdx.x & (LANES - 1);
@@ -257,9 +255,8 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
     bool head_open = (cn & CGB_END_FLAG) != 0;
     bool open = false, have_head = false;
     uint32_t head_row = 0;
-    Acc<VEC> acc, head_acc;
+    Acc<VEC> acc;
     acc.zero();
-    head_acc.zero();
     uint32_t my = (e + lane < end) ? __ldg(a.colf + e + lane) : 0u;
     while (e < end) {
         const uint32_t n = min((uint32_t)LANES, end - e);
@@ -298,8 +295,8 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
                                     }
                                     acc.store_cs(a.y + o);
                                 }
-                            } else {  // end of a row that began in an earlier chunk: fold it after the loop
-                                head_acc = acc;
+                            } else {  // end of a row that began in an earlier chunk: leave a head piece
+                                if (active) acc.store(a.piece_head + (size_t)c * a.D + col0);
                                 head_row = row;
                                 have_head = true;
                             }
@@ -315,9 +312,11 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
         e += LANES;
         my = nxt;
     }
-    if (have_head) chunk_piece<VEC, LANES>(a, head_acc, head_row, c, ct, col0, active, 1, lane, mask);
-    if (open)  // the last row of the chunk continues in the next chunk
-        chunk_piece<VEC, LANES>(a, acc, __ldg(a.nz_row + k), c, ct, col0, active, head_open ? 1 : 2, lane, mask);
+    if (have_head) piece_arrive<VEC, LANES>(a, head_row, ct, col0, active, lane, mask);
+    if (open) {  // the chunk ends inside a row
+        if (active) acc.store((head_open ? a.piece_head : a.piece_tail) + (size_t)c * a.D + col0);
+        piece_arrive<VEC, LANES>(a, __ldg(a.nz_row + k), ct, col0, active, lane, mask);
+    }
 }
 
 __global__ void __launch_bounds__(256) set_end_flags_kernel(const uint32_t* __restrict__ rowptr, uint32_t n_rows,
@@ -607,19 +606,22 @@ int cgb_gather_sum(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, cons
         a.piece_head = (u64*)csr->d_piece;
         a.piece_tail = (u64*)csr->d_piece + (size_t)csr->n_chunks * D;
         const uint64_t total = ((uint64_t)csr->n_chunks + csr->n_empty) * s.n_ct;
-        static const int half_u = getenv("CGB_GATHER_U4") ? 1 : 0;
+        // tuning knobs (round 1 experiments): CGB_GATHER_U8=1 -> 8 loads in flight per lane at 32 warps/SM;
+        // CGB_GATHER_OCC=1024|1280|1536|2048 -> register cap for that many resident threads per SM (U = 4)
+        static const int use_u8 = getenv("CGB_GATHER_U8") ? 1 : 0;
+        static const int occ = getenv("CGB_GATHER_OCC") ? atoi(getenv("CGB_GATHER_OCC")) : 1280;
         int rc = dispatch_shape(s, [&](auto V, auto L, auto U_) {
             constexpr int BLOCK = 128;
-            constexpr int GROUPS = BLOCK / decltype(L)::value;
+            constexpr int VV = decltype(V)::value, LL = decltype(L)::value;
+            constexpr int GROUPS = BLOCK / LL;
             constexpr int UU = decltype(U_)::value;
             constexpr int UH = UU >= 8 ? 4 : UU;
-            uint64_t blocks = (total + GROUPS - 1) / GROUPS;
-            if (half_u)
-                gather_chunk_kernel<decltype(V)::value, decltype(L)::value, UH, BLOCK>
-                    <<<(unsigned)blocks, BLOCK, 0, ctx->stream>>>(a);
-            else
-                gather_chunk_kernel<decltype(V)::value, decltype(L)::value, UU, BLOCK>
-                    <<<(unsigned)blocks, BLOCK, 0, ctx->stream>>>(a);
+            const unsigned blocks = (unsigned)((total + GROUPS - 1) / GROUPS);
+            if (use_u8) gather_chunk_kernel<VV, LL, UU, BLOCK, 1024><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+            else if (occ == 1024) gather_chunk_kernel<VV, LL, UH, BLOCK, 1024><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+            else if (occ == 1536) gather_chunk_kernel<VV, LL, UH, BLOCK, 1536><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+            else if (occ == 2048) gather_chunk_kernel<VV, LL, UH, BLOCK, 2048><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+            else gather_chunk_kernel<VV, LL, UH, BLOCK, 1280><<<blocks, BLOCK, 0, ctx->stream>>>(a);
         });
         CGB_REQUIRE(ctx, rc == 0, "cgb_gather_sum: no kernel for this shape");
         CGB_CHECK_LAUNCH(ctx, "gather_chunk_kernel");

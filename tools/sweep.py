@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--dims", default="16,64,128")
     ap.add_argument("--matmul-rows", type=int, default=1 << 20)
     ap.add_argument("--skip-matmul", action="store_true")
+    ap.add_argument("--mm", default=None, help="only this matmul shape, e.g. 512x512 (K x N)")
+    ap.add_argument("--skip-stream", action="store_true")
     ap.add_argument("--uniform", action="store_true", help="add a uniform-degree control graph at the largest size")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -81,9 +83,12 @@ def main():
 
     if not args.skip_matmul:
         M = args.matmul_rows
-        for F in (128, 256, 512):
+        Fs, Hs = (128, 256, 512), (16, 128, 256, 512)
+        if args.mm:
+            Fs, Hs = (int(args.mm.split("x")[0]),), (int(args.mm.split("x")[1]),)
+        for F in Fs:
             A = torch.randint(-2**63, 2**63 - 1, (M, F), dtype=torch.int64, device=dev, generator=g)
-            for H in (16, 128, 256, 512):
+            for H in Hs:
                 B = torch.randint(-2**63, 2**63 - 1, (F, H), dtype=torch.int64, device=dev, generator=g)
                 C = torch.empty((M, H), dtype=torch.int64, device=dev)
                 for _ in range(2):
@@ -95,7 +100,7 @@ def main():
                 del B, C
             del A
         # weight-gradient shape (split-K): X^T (F x N_p) * G (N_p x H)
-        for (Np, F, H) in [(21168, 128, 256), (1 << 20, 128, 16)]:
+        for (Np, F, H) in ([] if args.mm else [(21168, 128, 256), (1 << 20, 128, 16)]):
             X = torch.randint(-2**63, 2**63 - 1, (Np, F), dtype=torch.int64, device=dev, generator=g)
             G = torch.randint(-2**63, 2**63 - 1, (Np, H), dtype=torch.int64, device=dev, generator=g)
             for _ in range(2):
@@ -104,8 +109,17 @@ def main():
             emit({"kernel": "matmul_u64_transA_splitK", "M": F, "K": Np, "N": H, "ms_median": med, "ms_best": best,
                   "u64_mac_per_s": Np * F * H / (med * 1e-3)})
 
-    # stream kernels: 1 Gi words would be 8 GB; use 256 Mi words (2 GB per buffer)
-    n = 256 << 20
+    if args.skip_stream:
+        n = 0
+    else:
+        n = 256 << 20
+    if n == 0:
+        if args.out:
+            with open(args.out, "w") as f:
+                for r in out:
+                    f.write(json.dumps(r) + "\n")
+        return
+    # stream kernels: 256 Mi words (2 GB per buffer)
     a = torch.randint(-2**63, 2**63 - 1, (n,), dtype=torch.int64, device=dev, generator=g)
     b = torch.randint(-2**63, 2**63 - 1, (n,), dtype=torch.int64, device=dev, generator=g)
     o = torch.empty_like(a)
