@@ -319,6 +319,166 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Shared-memory staged variant of the edge-balanced schedule.  ncu on gather_chunk_kernel (round 1): 42% DRAM
+// utilisation, long-scoreboard stalls dominate, and occupancy is capped by the registers that hold loads in
+// flight.  Here the row loads are cp.async (LDGSTS) copies into a double-buffered shared-memory ring -- every
+// thread copies and later reads only its own 16-byte column slot, so no barrier is needed -- which moves the
+// bytes in flight from the register file (about 80 KB/SM) to shared memory (about 220 KB/SM).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(uint32_t smem_addr, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int VEC>
+__device__ __forceinline__ Acc<VEC> lds_acc(uint32_t smem_addr);
+template <>
+__device__ __forceinline__ Acc<2> lds_acc<2>(uint32_t smem_addr) {
+    Acc<2> r;
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(r.a), "=l"(r.b) : "r"(smem_addr));
+    return r;
+}
+template <>
+__device__ __forceinline__ Acc<1> lds_acc<1>(uint32_t smem_addr) {
+    Acc<1> r;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(r.a) : "r"(smem_addr));
+    return r;
+}
+
+template <int VEC, int LANES, int U, int BLOCK, int NBUF>
+__global__ void __launch_bounds__(BLOCK) gather_chunk_async_kernel(const __grid_constant__ ChunkArgs a) {
+    constexpr int GROUPS = BLOCK / LANES;
+    constexpr uint32_t SLOT = VEC * 8;  // bytes per thread per staged edge
+    extern __shared__ __align__(16) unsigned char stage_raw[];
+    const int lane = threadIdx.x & (LANES - 1);
+    const unsigned mask = group_mask<LANES>(threadIdx.x & 31);
+    const uint64_t gid = (uint64_t)blockIdx.x * GROUPS + threadIdx.x / LANES;
+    const uint64_t total = ((uint64_t)a.n_chunks + a.n_empty) * a.n_ct;
+    if (gid >= total) return;
+    const uint32_t item = (uint32_t)(gid / a.n_ct);
+    const uint32_t ct = (uint32_t)(gid - (uint64_t)item * a.n_ct);
+    const uint32_t col0 = ct * (VEC * LANES) + lane * VEC;
+    const bool active = col0 < a.D;
+
+    if (item >= a.n_chunks) {  // a row without edges: y = delta (or 0)
+        if (active) {
+            const uint32_t row = __ldg(a.empty_row + (item - a.n_chunks));
+            const size_t o = (size_t)row * a.D + col0;
+            Acc<VEC> v;
+            v.zero();
+            if (a.delta) v.load_nc(a.delta + o);
+            v.store_cs(a.y + o);
+        }
+        return;
+    }
+    // slot(buf, u) = base + ((buf * U + u) * BLOCK + tid) * SLOT : consecutive threads, consecutive slots
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(stage_raw) + threadIdx.x * SLOT;
+    const u64* xcol = a.x + col0;
+
+    const uint32_t c = item;
+    uint32_t e = c * CGB_CHUNK_EDGES;
+    const uint32_t end = min(a.n_edges, e + CGB_CHUNK_EDGES);
+    const uint32_t cn = __ldg(a.chunk_nz + c);
+    uint32_t k = cn & ~CGB_END_FLAG;
+    bool head_open = (cn & CGB_END_FLAG) != 0;
+    bool open = false, have_head = false;
+    uint32_t head_row = 0;
+    Acc<VEC> acc;
+    acc.zero();
+
+    // consume one staged sub-batch: add its rows in edge order, finishing rows where the end flag is set
+    auto consume = [&](uint32_t buf, uint32_t fmask, uint32_t cnt) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if ((uint32_t)u < cnt) {
+                if (active) acc.add(lds_acc<VEC>(smem_base + (buf * U + u) * (BLOCK * SLOT)));
+                open = true;
+                if ((fmask >> u) & 1u) {
+                    const uint32_t row = __ldg(a.nz_row + k);
+                    if (!head_open) {
+                        if (active) {
+                            const size_t o = (size_t)row * a.D + col0;
+                            if (a.delta) {
+                                Acc<VEC> d;
+                                d.load_nc(a.delta + o);
+                                acc.add(d);
+                            }
+                            acc.store_cs(a.y + o);
+                        }
+                    } else {
+                        if (active) acc.store(a.piece_head + (size_t)c * a.D + col0);
+                        head_row = row;
+                        have_head = true;
+                    }
+                    acc.zero();
+                    head_open = false;
+                    open = false;
+                    ++k;
+                }
+            }
+        }
+    };
+
+    uint32_t my = (e + lane < end) ? __ldg(a.colf + e + lane) : 0u;
+    uint32_t issued = 0;                 // sub-batches issued so far
+    uint32_t q_mask[NBUF - 1], q_cnt[NBUF - 1];  // flags / sizes of the sub-batches still in flight (oldest first)
+#pragma unroll
+    for (int i = 0; i < NBUF - 1; ++i) { q_mask[i] = 0; q_cnt[i] = 0; }
+    uint32_t inflight = 0;
+    while (e < end) {
+        const uint32_t n = min((uint32_t)LANES, end - e);
+        const uint32_t nxt = (e + LANES + lane < end) ? __ldg(a.colf + e + LANES + lane) : 0u;  // prefetch indices
+        for (uint32_t k0 = 0; k0 < n; k0 += U) {
+            const uint32_t buf = issued % NBUF;
+            uint32_t fmask = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t id = __shfl_sync(mask, my, k0 + u, LANES);
+                if (k0 + u < n) {
+                    fmask |= (id >> 31) << u;
+                    if (active) {
+                        const u64* src = xcol + (size_t)(id & ~CGB_END_FLAG) * a.D;
+                        const uint32_t dst = smem_base + (buf * U + u) * (BLOCK * SLOT);
+                        if (VEC == 2) cp_async_16(dst, src);
+                        else cp_async_8(dst, src);
+                    }
+                }
+            }
+            cp_async_commit();
+            ++issued;
+            if (inflight == NBUF - 1) {  // ring full: retire the oldest sub-batch
+                cp_async_wait<NBUF - 1>();
+                consume((issued - NBUF) % NBUF, q_mask[0], q_cnt[0]);
+#pragma unroll
+                for (int i = 0; i + 1 < NBUF - 1; ++i) { q_mask[i] = q_mask[i + 1]; q_cnt[i] = q_cnt[i + 1]; }
+                --inflight;
+            }
+            q_mask[inflight] = fmask;
+            q_cnt[inflight] = min((uint32_t)U, n - k0);
+            ++inflight;
+        }
+        e += LANES;
+        my = nxt;
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int i = 0; i < NBUF - 1; ++i)
+        if ((uint32_t)i < inflight) consume((issued - inflight + i) % NBUF, q_mask[i], q_cnt[i]);
+
+    if (have_head) piece_arrive<VEC, LANES>(a, head_row, ct, col0, active, lane, mask);
+    if (open) {  // the chunk ends inside a row
+        if (active) acc.store((head_open ? a.piece_head : a.piece_tail) + (size_t)c * a.D + col0);
+        piece_arrive<VEC, LANES>(a, __ldg(a.nz_row + k), ct, col0, active, lane, mask);
+    }
+}
+
 __global__ void __launch_bounds__(256) set_end_flags_kernel(const uint32_t* __restrict__ rowptr, uint32_t n_rows,
                                                             uint32_t* __restrict__ colf) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -606,10 +766,35 @@ int cgb_gather_sum(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, cons
         a.piece_head = (u64*)csr->d_piece;
         a.piece_tail = (u64*)csr->d_piece + (size_t)csr->n_chunks * D;
         const uint64_t total = ((uint64_t)csr->n_chunks + csr->n_empty) * s.n_ct;
-        // tuning knobs (round 1 experiments): CGB_GATHER_U8=1 -> 8 loads in flight per lane at 32 warps/SM;
+        // tuning knobs (round 1 experiments): CGB_GATHER_IMPL=async -> cp.async staged variant (CGB_GATHER_NBUF=2|3);
+        // CGB_GATHER_U8=1 -> 8 register loads in flight per lane at 32 warps/SM;
         // CGB_GATHER_OCC=1024|1280|1536|2048 -> register cap for that many resident threads per SM (U = 4)
+        static const bool use_async = getenv("CGB_GATHER_IMPL") && std::string(getenv("CGB_GATHER_IMPL")) == "async";
+        static const int nbuf = getenv("CGB_GATHER_NBUF") ? atoi(getenv("CGB_GATHER_NBUF")) : 2;
+        if (use_async) {
+            int rc = dispatch_shape(s, [&](auto V, auto L, auto U_) {
+                constexpr int BLOCK = 128;
+                constexpr int VV = decltype(V)::value, LL = decltype(L)::value, UU = decltype(U_)::value;
+                constexpr int GROUPS = BLOCK / LL;
+                const unsigned blocks = (unsigned)((total + GROUPS - 1) / GROUPS);
+                if (nbuf == 3) {
+                    constexpr size_t smem = (size_t)3 * UU * BLOCK * VV * 8;
+                    auto kfn = gather_chunk_async_kernel<VV, LL, UU, BLOCK, 3>;
+                    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    kfn<<<blocks, BLOCK, smem, ctx->stream>>>(a);
+                } else {
+                    constexpr size_t smem = (size_t)2 * UU * BLOCK * VV * 8;
+                    auto kfn = gather_chunk_async_kernel<VV, LL, UU, BLOCK, 2>;
+                    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    kfn<<<blocks, BLOCK, smem, ctx->stream>>>(a);
+                }
+            });
+            CGB_REQUIRE(ctx, rc == 0, "cgb_gather_sum: no kernel for this shape");
+            CGB_CHECK_LAUNCH(ctx, "gather_chunk_async_kernel");
+            return CGB_OK;
+        }
         static const int use_u8 = getenv("CGB_GATHER_U8") ? 1 : 0;
-        static const int occ = getenv("CGB_GATHER_OCC") ? atoi(getenv("CGB_GATHER_OCC")) : 1280;
+        static const int occ = getenv("CGB_GATHER_OCC") ? atoi(getenv("CGB_GATHER_OCC")) : 1536;
         int rc = dispatch_shape(s, [&](auto V, auto L, auto U_) {
             constexpr int BLOCK = 128;
             constexpr int VV = decltype(V)::value, LL = decltype(L)::value;

@@ -1,0 +1,36 @@
+"""Builds libcognn_b200_host.so: the C++ host engine above the C ABI (links libcognn_b200.so, cudart, NCCL)."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+LIB = os.path.join(PKG, "libcognn_b200_host.so")
+SOURCES = ["engine.cpp", "comm.cpp", "capi_engine.cpp"]
+
+
+def _cxx():
+    for cand in ("/usr/bin/g++", shutil.which("g++")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("g++ not found")
+
+
+def build(force=False):
+    deps = [os.path.join(HERE, s) for s in SOURCES] + [os.path.join(HERE, "engine.h"),
+                                                       os.path.join(PKG, "..", "include", "cognn_b200_engine.h"),
+                                                       os.path.join(PKG, "..", "include", "cognn_b200.h"),
+                                                       os.path.abspath(__file__)]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
+        return LIB
+    cmd = [_cxx(), "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", LIB] + \
+          [os.path.join(HERE, s) for s in SOURCES] + \
+          ["-I/usr/local/cuda/include", "-L" + PKG, "-l:libcognn_b200.so", "-Wl,-rpath,$ORIGIN",
+           "-L/usr/local/cuda/lib64", "-lcudart", "-lnccl"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

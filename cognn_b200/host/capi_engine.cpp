@@ -1,0 +1,181 @@
+// capi_engine.cpp -- C entry points of the host engine (declared in include/cognn_b200_engine.h) so that tests and
+// bench.py can drive the C++ engine through ctypes, and a C/C++ harness (the reference's harness.cpp:50-212 shape)
+// can link it directly.
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/cognn_b200_engine.h"
+#include "engine.h"
+
+using namespace cognn;
+
+struct cge_engine {
+    cgb_ctx* ctx = nullptr;
+    std::unique_ptr<Comm> comm;
+    std::unique_ptr<SSGcnEngine> eng;
+    std::string err;
+    int T = 0;
+    uint32_t F = 0;
+};
+
+static thread_local std::string g_err;
+
+#define CGE_TRY(h, body)                         \
+    try {                                        \
+        body;                                    \
+        return 0;                                \
+    } catch (const std::exception& e) {          \
+        if (h) (h)->err = e.what();              \
+        g_err = e.what();                        \
+        return -1;                               \
+    }
+
+extern "C" {
+
+const char* cge_last_error(cge_engine* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int cge_nccl_unique_id(void* out128) { CGE_TRY((cge_engine*)nullptr, nccl_get_unique_id(out128)); }
+
+static int create_common(cge_engine* h, const cge_config* c) {
+    GNNConfig cfg;
+    cfg.num_layers = c->num_layers; cfg.num_labels = c->num_labels; cfg.input_dim = c->input_dim;
+    cfg.hidden_dim = c->hidden_dim; cfg.num_samples = c->num_samples; cfg.num_edges = c->num_edges;
+    cfg.learning_rate = c->learning_rate; cfg.train_ratio = c->train_ratio; cfg.val_ratio = c->val_ratio;
+    cfg.test_ratio = c->test_ratio;
+    h->eng.reset(new SSGcnEngine(h->comm.get(), cfg, c->scaler_bits, c->key));
+    h->comm->record = c->record_messages != 0;
+    h->eng->verbose = c->verbose != 0;
+    h->F = c->input_dim;
+    return 0;
+}
+
+int cge_create_loopback(int device, void* cuda_stream, int n_parties, const cge_config* cfg, cge_engine** out) {
+    cge_engine* h = new cge_engine();
+    try {
+        int rc = cuda_stream ? cgb_ctx_create_on_stream(device, cuda_stream, &h->ctx) : cgb_ctx_create(device, &h->ctx);
+        if (rc != CGB_OK) throw std::runtime_error(std::string("cgb_ctx_create: ") + cgb_last_error(nullptr));
+        h->T = n_parties;
+        h->comm = make_loopback_comm(n_parties, h->ctx);
+        create_common(h, cfg);
+        *out = h;
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        delete h;
+        return -1;
+    }
+}
+
+int cge_create_nccl(int device, void* cuda_stream, int rank, int n_parties, const void* nccl_uid128, const cge_config* cfg,
+                    cge_engine** out) {
+    cge_engine* h = new cge_engine();
+    try {
+        int rc = cuda_stream ? cgb_ctx_create_on_stream(device, cuda_stream, &h->ctx) : cgb_ctx_create(device, &h->ctx);
+        if (rc != CGB_OK) throw std::runtime_error(std::string("cgb_ctx_create: ") + cgb_last_error(nullptr));
+        h->T = n_parties;
+        h->comm = make_nccl_comm(rank, n_parties, h->ctx, nccl_uid128);
+        create_common(h, cfg);
+        *out = h;
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        delete h;
+        return -1;
+    }
+}
+
+int cge_destroy(cge_engine* h) {
+    if (!h) return 0;
+    h->eng.reset();
+    h->comm.reset();
+    if (h->ctx) cgb_ctx_destroy(h->ctx);
+    delete h;
+    return 0;
+}
+
+int cge_add_party(cge_engine* h, int party, const int64_t* edges, uint64_t n_edges, const int64_t* tid, uint64_t n_vertices,
+                  const double* feats_global, const int32_t* labels_global) {
+    CGE_TRY(h, {
+        PartyGraph g = build_party_graph(edges, n_edges, tid, n_vertices, h->T, party);
+        const size_t n = g.vids.size();
+        std::vector<double> feats(n * h->F);
+        std::vector<int32_t> labels(n);
+        for (size_t i = 0; i < n; ++i) {
+            memcpy(&feats[i * h->F], feats_global + g.vids[i] * h->F, h->F * sizeof(double));
+            labels[i] = labels_global[g.vids[i]];
+        }
+        h->eng->add_party(g, feats.data(), labels.data());
+    });
+}
+
+int cge_setup(cge_engine* h) { CGE_TRY(h, h->eng->setup()); }
+int cge_run(cge_engine* h, uint64_t n_iters) { CGE_TRY(h, h->eng->run(n_iters)); }
+
+int64_t cge_download(cge_engine* h, int owner, int role, const char* name, uint64_t* out, uint64_t capacity, uint32_t* rows,
+                     uint32_t* cols) {
+    try {
+        std::vector<uint64_t> v = h->eng->download(owner, role, name, rows, cols);
+        if (out) {
+            if (v.size() > capacity) throw std::runtime_error("cge_download: buffer too small");
+            if (!v.empty()) memcpy(out, v.data(), v.size() * 8);
+        }
+        return (int64_t)v.size();
+    } catch (const std::exception& e) {
+        h->err = e.what();
+        return -1;
+    }
+}
+
+uint64_t cge_message_count(cge_engine* h) { return h->comm->transcript.size(); }
+int cge_message_info(cge_engine* h, uint64_t i, uint64_t* iter, int* src, int* dst, char* tag, uint64_t tag_cap, uint64_t* n_words) {
+    if (i >= h->comm->transcript.size()) return -1;
+    const Message& m = h->comm->transcript[i];
+    *iter = m.iter; *src = m.src; *dst = m.dst; *n_words = m.data.size();
+    snprintf(tag, tag_cap, "%s", m.tag.c_str());
+    return 0;
+}
+int cge_message_data(cge_engine* h, uint64_t i, uint64_t* out, uint64_t capacity) {
+    if (i >= h->comm->transcript.size()) return -1;
+    const Message& m = h->comm->transcript[i];
+    if (m.data.size() > capacity) return -1;
+    if (!m.data.empty()) memcpy(out, m.data.data(), m.data.size() * 8);
+    return 0;
+}
+uint64_t cge_words_sent(cge_engine* h) { return h->comm->words_sent; }
+uint64_t cge_rounds(cge_engine* h) { return h->comm->rounds; }
+uint64_t cge_launch_count(cge_engine* h) { return cgb_ctx_launch_count(h->ctx); }
+double cge_seconds_online(cge_engine* h) { return h->eng->seconds_online; }
+
+uint64_t cge_metrics_count(cge_engine* h) { return h->eng->metrics().size(); }
+int cge_metrics_get(cge_engine* h, uint64_t i, uint64_t* iter, int* party, double* loss, double* acc_full, double* acc_train,
+                    double* acc_test) {
+    if (i >= h->eng->metrics().size()) return -1;
+    const Metrics& m = h->eng->metrics()[i];
+    *iter = m.iter; *party = m.party; *loss = m.loss; *acc_full = m.acc_full; *acc_train = m.acc_train; *acc_test = m.acc_test;
+    return 0;
+}
+
+int cge_build_party_graph(const int64_t* edges, uint64_t n_edges, const int64_t* tid, uint64_t n_vertices, int T, int me,
+                          uint64_t* vids, uint64_t* in_deg_raw, uint64_t* in_deg, uint32_t* offsets, uint32_t* rowptr,
+                          uint32_t* col, uint64_t* n_local, uint64_t* n_rows, uint64_t* n_col) {
+    try {
+        PartyGraph g = build_party_graph(edges, n_edges, tid, n_vertices, T, me);
+        *n_local = g.vids.size(); *n_rows = g.offsets[T]; *n_col = g.col.size();
+        if (vids) memcpy(vids, g.vids.data(), g.vids.size() * 8);
+        if (in_deg_raw) memcpy(in_deg_raw, g.in_deg_raw.data(), g.in_deg_raw.size() * 8);
+        if (in_deg) memcpy(in_deg, g.in_deg.data(), g.in_deg.size() * 8);
+        if (offsets) memcpy(offsets, g.offsets.data(), g.offsets.size() * 4);
+        if (rowptr) memcpy(rowptr, g.rowptr.data(), g.rowptr.size() * 4);
+        if (col) memcpy(col, g.col.data(), g.col.size() * 4);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,888 @@
+// engine.cpp -- device-resident secure-GCN engine (CoGNN-Opt operators) above the C ABI.  See engine.h.
+//
+// Reference dataflow being served (file:line in /root/reference):
+//   iteration driver            include/ss_vertex_centric_algo_kernel.h:680-910 (ALICE), 912-1189 (BOB)
+//   PreScatterComp              algo_kernels/vertex_centric/optimize-gcn/gcn.h:198-255
+//   ScatterComp/UpdatePreMerge  gcn.h:257-342  (fused with the OM expand / extract of ssk.h:751-821 into one gather)
+//   GatherComp                  gcn.h:375-494
+//   ApplyComp                   gcn.h:515-811  (forward, prediction, two-step backward, gradient, FedAvg 747-802)
+//   onAlgoKernelStart           gcn.h:819-887  (feature normalisation, Glorot weights with srand(42), weight sharing)
+// Protocol (frozen in DESIGN.md): Beaver triples for every multiplication, masked fused gather for Scatter/Gather,
+// SecureML local truncation, dealer randomness from the device ChaCha20 PRG.  ReLU / softmax / ReLU' are
+// 2PC-RESIDUAL: they stay on the reference's MPC backend; here a clearly labelled ideal-functionality stand-in on
+// the HOST lets an epoch run end to end (not secure, not accelerated).
+#include "engine.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <numeric>
+#include <stdexcept>
+
+namespace cognn {
+
+// ------------------------------------------------------------------------------------------------------------------
+// errors: the reference prints and exit(-1)s (ssk.h:794-797); library code throws, the C shim maps to exit(-1)
+// ------------------------------------------------------------------------------------------------------------------
+static void ck(cgb_ctx* ctx, int rc, const char* what) {
+    if (rc != CGB_OK) throw std::runtime_error(std::string(what) + ": " + cgb_last_error(ctx));
+}
+
+bool GNNConfig::read(const std::string& file, std::string* err) {
+    std::ifstream fin(file);
+    if (!fin.is_open()) {
+        if (err) *err = "Failed to open the file: " + file;
+        return false;
+    }
+    std::string param;
+    char colon;
+    while (fin >> param >> colon) {  // task.h:123-160: "<name> : <value>"
+        if (colon != ':') {
+            if (err) *err = "Invalid format: expected a colon after " + param;
+            return false;
+        }
+        if (param == "num_layers") fin >> num_layers;
+        else if (param == "num_labels") fin >> num_labels;
+        else if (param == "input_dim") fin >> input_dim;
+        else if (param == "hidden_dim") fin >> hidden_dim;
+        else if (param == "num_samples") fin >> num_samples;
+        else if (param == "num_edges") fin >> num_edges;
+        else if (param == "learning_rate") fin >> learning_rate;
+        else if (param == "train_ratio") fin >> train_ratio;
+        else if (param == "val_ratio") fin >> val_ratio;
+        else if (param == "test_ratio") fin >> test_ratio;
+        else {
+            if (err) *err = "Unknown parameter: " + param;
+            return false;
+        }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// graph tile + index vectors (graph_io_util.h:40-208, graph.h:607-641, ssk.h:295-534 with -r 1)
+// ------------------------------------------------------------------------------------------------------------------
+PartyGraph build_party_graph(const int64_t* edges, size_t n_edges, const int64_t* tid, size_t n_vertices, int T, int me) {
+    PartyGraph g;
+    g.T = T;
+    g.me = me;
+    std::vector<uint32_t> local_index(n_vertices);
+    std::vector<uint32_t> count(T, 0);
+    for (size_t v = 0; v < n_vertices; ++v) {
+        if (tid[v] < 0 || tid[v] >= T) throw std::runtime_error("build_party_graph: tile id out of range");
+        local_index[v] = count[tid[v]]++;  // ascending vid inside a party (ssk.h:462-464)
+    }
+    g.offsets.assign(T + 1, 0);
+    for (int t = 0; t < T; ++t) g.offsets[t + 1] = g.offsets[t] + count[t];
+    const uint32_t n_local = count[me];
+    g.vids.reserve(n_local);
+    for (size_t v = 0; v < n_vertices; ++v)
+        if (tid[v] == me) g.vids.push_back(v);
+    std::vector<uint64_t> in_deg(n_local, 0), local_in(n_local, 0);
+    g.is_border.assign(n_local, 0);
+    struct E { uint32_t row, col; };
+    std::vector<E> mine;
+    for (size_t e = 0; e < n_edges; ++e) {
+        const int64_t s = edges[2 * e], d = edges[2 * e + 1];
+        if (s < 0 || d < 0 || (size_t)s >= n_vertices || (size_t)d >= n_vertices)
+            throw std::runtime_error("build_party_graph: vertex id out of range");
+        if (tid[d] == me) in_deg[local_index[d]]++;  // graph.h:627-632 (local) and graph_io_util.h:170-175 (remote)
+        if (tid[s] == me) {
+            mine.push_back({g.offsets[tid[d]] + local_index[d], local_index[s]});
+            if (tid[d] == me) local_in[local_index[d]]++;
+            else g.is_border[local_index[s]] = 1;
+        }
+    }
+    // rows grouped by destination ascending, sources ascending inside a row (edges are (src,dst)-sorted, graph.h:636-641)
+    std::sort(mine.begin(), mine.end(), [](const E& a, const E& b) { return a.row != b.row ? a.row < b.row : a.col < b.col; });
+    const uint32_t n_rows = g.offsets[T];
+    g.rowptr.assign((size_t)n_rows + 1, 0);
+    g.col.resize(mine.size());
+    for (size_t i = 0; i < mine.size(); ++i) {
+        g.rowptr[mine[i].row + 1]++;
+        g.col[i] = mine[i].col;
+    }
+    for (uint32_t r = 0; r < n_rows; ++r) g.rowptr[r + 1] += g.rowptr[r];
+    g.in_deg_raw = in_deg;
+    g.in_deg = in_deg;
+    // ssk.h:412-418: a local vertex without LOCAL in-edge gets a dummy self edge and its degrees are incremented; the
+    // edge itself carries no value (dropped at Gather via isGatherDstVertexDummy), so only the increment survives here
+    for (uint32_t i = 0; i < n_local; ++i)
+        if (local_in[i] == 0) g.in_deg[i] += 1;
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// device matrices
+// ------------------------------------------------------------------------------------------------------------------
+struct DMat {
+    cgb_ctx* ctx = nullptr;
+    uint64_t* p = nullptr;
+    uint32_t rows = 0, cols = 0;
+    size_t cap = 0;
+    DMat() {}
+    DMat(const DMat&) = delete;
+    DMat& operator=(const DMat&) = delete;
+    DMat(DMat&& o) noexcept { *this = std::move(o); }
+    DMat& operator=(DMat&& o) noexcept {
+        if (this != &o) {
+            release();
+            ctx = o.ctx; p = o.p; rows = o.rows; cols = o.cols; cap = o.cap;
+            o.p = nullptr; o.cap = 0; o.rows = o.cols = 0;
+        }
+        return *this;
+    }
+    ~DMat() { release(); }
+    void release() {
+        if (p) cgb_free(ctx, p);
+        p = nullptr;
+        cap = 0;
+    }
+    size_t n() const { return (size_t)rows * cols; }
+    void resize(cgb_ctx* c, uint32_t r, uint32_t cl) {
+        ctx = c;
+        const size_t need = (size_t)r * cl;
+        if (need > cap) {
+            // buffers may still be read by queued kernels: the stream is in order, and cudaFree synchronises
+            release();
+            void* q = nullptr;
+            ck(c, cgb_malloc(c, std::max<size_t>(need, 2) * sizeof(uint64_t), &q), "cgb_malloc");
+            p = (uint64_t*)q;
+            cap = need;
+        }
+        rows = r;
+        cols = cl;
+    }
+    void copy_from(const DMat& o) {
+        resize(o.ctx, o.rows, o.cols);
+        if (n()) ck(ctx, cgb_d2d(ctx, p, o.p, n() * sizeof(uint64_t)), "cgb_d2d");
+    }
+};
+
+// PRG stream ids (DESIGN.md "Randomness"); must match oracle/epoch.py
+enum Kind : uint64_t { K_FEAT = 1, K_WEIGHT, K_OM_R, K_OM_S, K_MM_U0, K_MM_U1, K_MM_V0, K_MM_V1, K_MM_Z0,
+                       K_RM_A0, K_RM_A1, K_RM_B0, K_RM_B1, K_RM_C0, K_RESHARE };
+static uint64_t stream_id(uint64_t kind, uint64_t it, uint64_t owner, uint64_t sub) {
+    return (kind << 48) | (it << 16) | (owner << 8) | sub;
+}
+
+// one share-side of one owner's state: share 0 lives on the owner, share 1 on its primary helper (owner + 1) % T
+struct Side {
+    int owner = 0, share = 0, peer = 0;
+    uint32_t n = 0;
+    DMat X, X_backup, W[2], h_t[2], z[2], g;
+    // per-iteration temporaries
+    DMat Xp, V, Y, m, tmp, tmp2;
+    DMat mmU, mmV, mmZ, mm_mine, mm_peer, mmE, mmF;
+    DMat rmA, rmB, rmC, rm_mine, rm_peer, rmE;
+    DMat res_in, res_out[2], P, Ppeer;
+    std::vector<DMat> upd_recv;  // helper side: masked sums received from the other owners
+    DMat delta, S;
+};
+
+struct PartyData {
+    PartyGraph g;
+    cgb_csr* csr = nullptr;
+    DMat norm;  // enc((inDeg+1)^-1/2), private to the owner
+    std::vector<int32_t> labels;
+    std::vector<double> feats;  // normalised, n x F
+};
+
+struct SSGcnEngine::Impl {
+    Comm* comm;
+    cgb_ctx* ctx;
+    GNNConfig cfg;
+    int f;
+    uint32_t key[8];
+    int T;
+    uint32_t F, H, C;
+    std::map<int, PartyData> party;
+    std::map<int, Side> own, hlp;
+    std::vector<uint32_t> n_of;  // vertices per party (global knowledge: the partition file is public)
+    uint64_t lr_fixed = 0;
+
+    int q(int p) const { return (p + 1) % T; }
+    Side* side(int owner, int share) {
+        auto& m = share == 0 ? own : hlp;
+        auto it = m.find(owner);
+        return it == m.end() ? nullptr : &it->second;
+    }
+
+    // ---- thin wrappers ------------------------------------------------------------------------------------------
+    void prg(uint64_t kind, uint64_t it, int owner, int sub, DMat& out, uint32_t r, uint32_t c) {
+        out.resize(ctx, r, c);
+        ck(ctx, cgb_prg_fill(ctx, key, stream_id(kind, it, owner, sub), 0, out.p, out.n()), "cgb_prg_fill");
+    }
+    void vadd(const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n) { ck(ctx, cgb_add(ctx, a, b, o, n), "cgb_add"); }
+    void vsub(const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n) { ck(ctx, cgb_sub(ctx, a, b, o, n), "cgb_sub"); }
+    void send(int src, int dst, const DMat& m, const std::string& tag) { comm->post_send(src, dst, m.p, m.n(), tag); }
+    void recv(int dst, int src, DMat& m) { comm->post_recv(dst, src, m.p, m.n()); }
+    static std::string tagf(const char* base, int sub, int owner) {
+        char b[64];
+        if (sub >= 0) snprintf(b, sizeof b, "%s%d.o%d", base, sub, owner);
+        else snprintf(b, sizeof b, "%s.o%d", base, owner);
+        return b;
+    }
+
+    // ---- Beaver matmul (sci::twoPartyGCNMatMul, gcn.h:233,665,671,710): prepare -> exchange -> finish --------------
+    void mm_prepare(Side& s, uint64_t it, int sub, const DMat& A, const DMat& B) {
+        const uint32_t M = A.rows, K = A.cols, N = B.cols;
+        if (s.share == 0) {
+            prg(K_MM_U0, it, s.owner, sub, s.mmU, M, K);
+            prg(K_MM_V0, it, s.owner, sub, s.mmV, K, N);
+            prg(K_MM_Z0, it, s.owner, sub, s.mmZ, M, N);
+        } else {
+            // dealer emulation (offline phase): Z1 = (U0+U1)(V0+V1) - Z0
+            DMat U0, V0, Z0;
+            prg(K_MM_U0, it, s.owner, sub, U0, M, K);
+            prg(K_MM_V0, it, s.owner, sub, V0, K, N);
+            prg(K_MM_Z0, it, s.owner, sub, Z0, M, N);
+            prg(K_MM_U1, it, s.owner, sub, s.mmU, M, K);
+            prg(K_MM_V1, it, s.owner, sub, s.mmV, K, N);
+            vadd(U0.p, s.mmU.p, U0.p, U0.n());
+            vadd(V0.p, s.mmV.p, V0.p, V0.n());
+            s.mmZ.resize(ctx, M, N);
+            ck(ctx, cgb_matmul(ctx, U0.p, V0.p, s.mmZ.p, M, K, N, 0, 0), "cgb_matmul(dealer)");
+            vsub(s.mmZ.p, Z0.p, s.mmZ.p, s.mmZ.n());
+            ck(ctx, cgb_ctx_sync(ctx), "sync");  // U0/V0/Z0 are freed at scope exit
+        }
+        // [E_i | F_i] in one message
+        s.mm_mine.resize(ctx, 1, M * K + K * N);
+        s.mm_peer.resize(ctx, 1, M * K + K * N);
+        vsub(A.p, s.mmU.p, s.mm_mine.p, (size_t)M * K);
+        vsub(B.p, s.mmV.p, s.mm_mine.p + (size_t)M * K, (size_t)K * N);
+    }
+    void mm_post(Side& s, int sub) {
+        const int holder = s.share == 0 ? s.owner : q(s.owner);
+        const int other = s.share == 0 ? q(s.owner) : s.owner;
+        send(holder, other, s.mm_mine, tagf("mm", sub, s.owner));
+        recv(holder, other, s.mm_peer);
+    }
+    void mm_finish(Side& s, uint32_t M, uint32_t K, uint32_t N, DMat& C_out) {
+        vadd(s.mm_mine.p, s.mm_peer.p, s.mm_mine.p, s.mm_mine.n());  // E | F opened
+        C_out.resize(ctx, M, N);
+        ck(ctx, cgb_beaver_matmul_finish(ctx, s.mm_mine.p, s.mm_mine.p + (size_t)M * K, s.mmU.p, s.mmV.p, s.mmZ.p,
+                                         C_out.p, M, K, N, s.share, f), "cgb_beaver_matmul_finish");
+    }
+
+    // ---- Beaver row scaling (sci::twoPartyGCNVectorScale, gcn.h:247,476): scaler private to the owner -------------
+    void rm_prepare(Side& s, uint64_t it, int sub, const DMat& x, const DMat* scaler) {
+        const uint32_t rows = x.rows, D = x.cols;
+        if (s.share == 0) {
+            prg(K_RM_A0, it, s.owner, sub, s.rmA, rows, D);
+            prg(K_RM_B0, it, s.owner, sub, s.rmB, 1, rows);
+            prg(K_RM_C0, it, s.owner, sub, s.rmC, rows, D);
+        } else {
+            DMat a0, b0, c0, ones;
+            prg(K_RM_A0, it, s.owner, sub, a0, rows, D);
+            prg(K_RM_B0, it, s.owner, sub, b0, 1, rows);
+            prg(K_RM_C0, it, s.owner, sub, c0, rows, D);
+            prg(K_RM_A1, it, s.owner, sub, s.rmA, rows, D);
+            prg(K_RM_B1, it, s.owner, sub, s.rmB, 1, rows);
+            vadd(a0.p, s.rmA.p, a0.p, a0.n());
+            vadd(b0.p, s.rmB.p, b0.p, b0.n());
+            // c1 = (a0+a1) * (b0+b1)[row] - c0  ==  rowmul_finish(e = a, fv = b, a' = 0, b' = 0, c = -c0) on share 0
+            // computed with the generic kernel: out = c + e*b' + fv*a' + e*fv with a' = b' = 0, c = 0 - c0
+            DMat zero_mat, zero_vec, negc;
+            zero_mat.resize(ctx, rows, D);
+            zero_vec.resize(ctx, 1, rows);
+            ck(ctx, cgb_memset(ctx, zero_mat.p, 0, zero_mat.n() * 8), "memset");
+            ck(ctx, cgb_memset(ctx, zero_vec.p, 0, zero_vec.n() * 8), "memset");
+            negc.resize(ctx, rows, D);
+            vsub(zero_mat.p, c0.p, negc.p, negc.n());
+            s.rmC.resize(ctx, rows, D);
+            ck(ctx, cgb_rowmul_beaver_finish(ctx, a0.p, b0.p, zero_mat.p, zero_vec.p, negc.p, s.rmC.p, rows, D, 0, -1),
+               "rowmul(dealer)");
+            ck(ctx, cgb_ctx_sync(ctx), "sync");
+        }
+        s.rm_mine.resize(ctx, 1, rows * D + rows);
+        s.rm_peer.resize(ctx, 1, rows * D + rows);
+        vsub(x.p, s.rmA.p, s.rm_mine.p, (size_t)rows * D);
+        if (s.share == 0) {
+            vsub(scaler->p, s.rmB.p, s.rm_mine.p + (size_t)rows * D, rows);
+        } else {
+            ck(ctx, cgb_memset(ctx, s.rm_mine.p + (size_t)rows * D, 0, (size_t)rows * 8), "memset");
+            vsub(s.rm_mine.p + (size_t)rows * D, s.rmB.p, s.rm_mine.p + (size_t)rows * D, rows);
+        }
+    }
+    void rm_post(Side& s, int sub) {
+        const int holder = s.share == 0 ? s.owner : q(s.owner);
+        const int other = s.share == 0 ? q(s.owner) : s.owner;
+        send(holder, other, s.rm_mine, tagf("rm", sub, s.owner));
+        recv(holder, other, s.rm_peer);
+    }
+    void rm_finish(Side& s, uint32_t rows, uint32_t D, DMat& out) {
+        vadd(s.rm_mine.p, s.rm_peer.p, s.rm_mine.p, s.rm_mine.n());
+        out.resize(ctx, rows, D);
+        ck(ctx, cgb_rowmul_beaver_finish(ctx, s.rm_mine.p, s.rm_mine.p + (size_t)rows * D, s.rmA.p, s.rmB.p, s.rmC.p,
+                                         out.p, rows, D, s.share, f), "cgb_rowmul_beaver_finish");
+    }
+
+    // run `fn(side)` for every locally hosted side in the canonical order (owner 0 share 0, owner 0 share 1, ...)
+    template <typename Fn>
+    void for_sides(Fn&& fn) {
+        for (int o = 0; o < T; ++o)
+            for (int sh = 0; sh < 2; ++sh)
+                if (Side* s = side(o, sh)) fn(*s);
+    }
+
+    // a full two-party row scaling of `x` (both sides), result in `out` chosen by the accessor
+    template <typename GetX, typename GetOut>
+    void rowscale_all(uint64_t it, int sub, GetX&& getx, GetOut&& getout) {
+        for_sides([&](Side& s) {
+            DMat& x = getx(s);
+            rm_prepare(s, it, sub, x, s.share == 0 ? &party[s.owner].norm : nullptr);
+            rm_post(s, sub);
+        });
+        comm->exchange();
+        for_sides([&](Side& s) {
+            DMat& x = getx(s);
+            DMat& o = getout(s);
+            if (&o == &x) {
+                rm_finish(s, x.rows, x.cols, s.tmp);
+                std::swap(s.tmp, x);
+            } else {
+                rm_finish(s, x.rows, x.cols, o);
+            }
+        });
+    }
+
+    // ---- Scatter / Gather of one GAS iteration: V = Xp + sum over in-edges (ssk.h:748-880 share-local composite) ---
+    void gas(uint64_t it) {
+        // round 1: helper -> owner OM online message m = Xp1 - r
+        for_sides([&](Side& s) {
+            const uint32_t D = s.Xp.cols;
+            if (s.share == 1) {
+                s.m.resize(ctx, s.n, D);
+                ck(ctx, cgb_prg_mask_sub(ctx, key, stream_id(K_OM_R, it, s.owner, 0), 0, s.Xp.p, s.m.p, s.m.n()), "mask");
+                send(q(s.owner), s.owner, s.m, tagf("om", -1, s.owner));
+            } else {
+                s.m.resize(ctx, s.n, D);
+                recv(s.owner, q(s.owner), s.m);
+            }
+        });
+        comm->exchange();
+        // owner: fused gather over all its out-edges, one block of rows per destination party
+        for_sides([&](Side& s) {
+            if (s.share != 0) return;
+            PartyData& pd = party[s.owner];
+            const uint32_t D = s.Xp.cols, n_rows = pd.g.offsets[T];
+            // dealer emulation (offline): delta = A r - S
+            DMat r;
+            prg(K_OM_R, it, s.owner, 0, r, s.n, D);
+            s.S.resize(ctx, n_rows, D);
+            for (int t = 0; t < T; ++t) {
+                const size_t off = (size_t)pd.g.offsets[t] * D, cnt = (size_t)n_of[t] * D;
+                ck(ctx, cgb_prg_fill(ctx, key, stream_id(K_OM_S, it, s.owner, t), 0, s.S.p + off, cnt), "prg S");
+            }
+            s.delta.resize(ctx, n_rows, D);
+            ck(ctx, cgb_gather_sum(ctx, pd.csr, r.p, nullptr, s.delta.p, D), "gather(dealer)");
+            vsub(s.delta.p, s.S.p, s.delta.p, s.delta.n());
+            // online: Y = A (Xp0 + m) + delta
+            vadd(s.Xp.p, s.m.p, s.m.p, s.m.n());
+            s.Y.resize(ctx, n_rows, D);
+            ck(ctx, cgb_gather_sum(ctx, pd.csr, s.m.p, s.delta.p, s.Y.p, D), "cgb_gather_sum");
+            ck(ctx, cgb_ctx_sync(ctx), "sync");  // r freed at scope exit
+        });
+        // round 2: mirror-update blocks to the primary helper of each destination owner (ssk.h:1090)
+        for (int p = 0; p < T; ++p) {
+            for (int t = 0; t < T; ++t) {
+                if (t == p || q(t) == p) continue;
+                if (Side* s = side(p, 0)) {
+                    const uint32_t D = s->Xp.cols;
+                    char tg[64];
+                    snprintf(tg, sizeof tg, "upd.o%d.t%d", p, t);
+                    comm->post_send(p, q(t), s->Y.p + (size_t)party[p].g.offsets[t] * D, (size_t)n_of[t] * D, tg);
+                }
+                if (Side* h = side(t, 1)) {
+                    const uint32_t D = h->Xp.cols;
+                    if (h->upd_recv.size() < (size_t)T) h->upd_recv.resize(T);
+                    h->upd_recv[p].resize(ctx, h->n, D);
+                    comm->post_recv(q(t), p, h->upd_recv[p].p, h->upd_recv[p].n());
+                }
+            }
+        }
+        comm->exchange();
+        // GatherComp additions (gcn.h:456-463)
+        for_sides([&](Side& s) {
+            const uint32_t D = s.Xp.cols;
+            const int t = s.owner;
+            s.V.resize(ctx, s.n, D);
+            if (s.share == 0) {
+                PartyData& pd = party[t];
+                vadd(s.Xp.p, s.Y.p + (size_t)pd.g.offsets[t] * D, s.V.p, s.V.n());
+                for (int p = 0; p < T; ++p) {
+                    if (p == t) continue;
+                    prg(K_OM_S, it, p, t, s.tmp, s.n, D);  // the owner holds the mask share s_{p->t}
+                    vadd(s.V.p, s.tmp.p, s.V.p, s.V.n());
+                }
+            } else {
+                prg(K_OM_S, it, t, t, s.tmp, s.n, D);
+                vadd(s.Xp.p, s.tmp.p, s.V.p, s.V.n());
+                for (int p = 0; p < T; ++p) {
+                    if (p == t) continue;
+                    const uint64_t* blk;
+                    if (q(t) == p) blk = own.at(p).Y.p + (size_t)party[p].g.offsets[t] * D;  // computed on this very party
+                    else blk = s.upd_recv[p].p;
+                    vadd(s.V.p, blk, s.V.p, s.V.n());
+                }
+            }
+        });
+    }
+
+    // ---- 2PC-RESIDUAL stand-in (ideal functionality on the host; NOT secure, NOT accelerated) ----------------------
+    // helper sends its shares; the owner evaluates fn on the reconstructed values on the host and re-shares: the
+    // helper's new share is a PRG stream both know from the dealer, the owner's is fn(x) - PRG.
+    typedef void (*ResidualFn)(Impl&, int owner, const std::vector<std::vector<uint64_t>>& in,
+                               std::vector<std::vector<uint64_t>>& out);
+    void residual(uint64_t it, ResidualFn fn, int n_in, int n_out, DMat* (*in_sel)(Side&, int), DMat* (*out_sel)(Side&, int)) {
+        for_sides([&](Side& s) {
+            size_t total = 0;
+            for (int i = 0; i < n_in; ++i) total += in_sel(s, i)->n();
+            s.res_in.resize(ctx, 1, (uint32_t)total);
+            if (s.share == 1) {
+                size_t off = 0;
+                for (int i = 0; i < n_in; ++i) {
+                    DMat* m = in_sel(s, i);
+                    ck(ctx, cgb_d2d(ctx, s.res_in.p + off, m->p, m->n() * 8), "d2d");
+                    off += m->n();
+                }
+                send(q(s.owner), s.owner, s.res_in, tagf("res", 0, s.owner));
+            } else {
+                recv(s.owner, q(s.owner), s.res_in);
+            }
+        });
+        comm->exchange();
+        for_sides([&](Side& s) {
+            std::vector<std::pair<uint32_t, uint32_t>> shapes;
+            if (s.share == 0) {
+                std::vector<std::vector<uint64_t>> in(n_in), out;
+                size_t off = 0;
+                std::vector<uint64_t> peer(s.res_in.n());
+                ck(ctx, cgb_d2h(ctx, peer.data(), s.res_in.p, peer.size() * 8), "d2h");
+                for (int i = 0; i < n_in; ++i) {
+                    DMat* m = in_sel(s, i);
+                    in[i].resize(m->n());
+                    ck(ctx, cgb_d2h(ctx, in[i].data(), m->p, m->n() * 8), "d2h");
+                }
+                ck(ctx, cgb_ctx_sync(ctx), "sync");
+                for (int i = 0; i < n_in; ++i) {
+                    for (size_t j = 0; j < in[i].size(); ++j) in[i][j] += peer[off + j];
+                    off += in[i].size();
+                }
+                fn(*this, s.owner, in, out);
+                for (int k = 0; k < n_out; ++k) {
+                    DMat* o = out_sel(s, k);
+                    DMat plain;
+                    plain.resize(ctx, o->rows, o->cols);
+                    ck(ctx, cgb_h2d(ctx, plain.p, out[k].data(), out[k].size() * 8), "h2d");
+                    ck(ctx, cgb_prg_mask_sub(ctx, key, stream_id(K_RESHARE, it, s.owner, k), 0, plain.p, o->p, o->n()), "reshare");
+                    ck(ctx, cgb_ctx_sync(ctx), "sync");
+                }
+            } else {
+                for (int k = 0; k < n_out; ++k) {
+                    DMat* o = out_sel(s, k);
+                    ck(ctx, cgb_prg_fill(ctx, key, stream_id(K_RESHARE, it, s.owner, k), 0, o->p, o->n()), "reshare");
+                }
+            }
+        });
+    }
+
+    // ---- weight averaging (gcn.h:747-802): reduce to parties 0 and 1, public scale 1/T, redistribute ---------------
+    void weight_average(uint64_t it, int layer) {
+        if (T == 1) return;
+        char tg[64];
+        std::map<int, DMat> rx_own, rx_hlp;  // at party 1: W0_i of i >= 2; at party 0: W1_{i-1}
+        for (int i = 2; i < T; ++i) {
+            if (Side* s = side(i, 0)) {
+                snprintf(tg, sizeof tg, "w%d.own%d", layer, i);
+                comm->post_send(i, 1, s->W[layer].p, s->W[layer].n(), tg);
+            }
+            if (comm->is_local(1)) {
+                rx_own[i].resize(ctx, own.at(1).W[layer].rows, own.at(1).W[layer].cols);
+                comm->post_recv(1, i, rx_own[i].p, rx_own[i].n());
+            }
+            if (Side* h = side(i - 1, 1)) {  // lives on party i
+                snprintf(tg, sizeof tg, "w%d.hlp%d", layer, i - 1);
+                comm->post_send(i, 0, h->W[layer].p, h->W[layer].n(), tg);
+            }
+            if (comm->is_local(0)) {
+                rx_hlp[i].resize(ctx, own.at(0).W[layer].rows, own.at(0).W[layer].cols);
+                comm->post_recv(0, i, rx_hlp[i].p, rx_hlp[i].n());
+            }
+        }
+        comm->exchange();
+        const uint64_t c = (uint64_t)(int64_t)((1.0 / T) * (double)(1ull << f));  // gcn.h:763-764
+        DMat A0, A1;
+        if (comm->is_local(0)) {
+            DMat& w = own.at(0).W[layer];
+            A0.copy_from(w);
+            for (int i = 2; i < T; ++i) vadd(A0.p, rx_hlp[i].p, A0.p, A0.n());
+            vadd(A0.p, hlp.at(T - 1).W[layer].p, A0.p, A0.n());  // party 0's remoteWeight: share 1 of party T-1's replica
+            ck(ctx, cgb_scale_public(ctx, A0.p, c, A0.p, A0.n(), f, 0), "scale");
+        }
+        if (comm->is_local(1)) {
+            DMat& w = own.at(1).W[layer];
+            A1.copy_from(w);
+            for (int i = 2; i < T; ++i) vadd(A1.p, rx_own[i].p, A1.p, A1.n());
+            vadd(A1.p, hlp.at(0).W[layer].p, A1.p, A1.n());
+            ck(ctx, cgb_scale_public(ctx, A1.p, c, A1.p, A1.n(), f, 1), "scale");
+        }
+        std::map<int, DMat> rxA1, rxA0;
+        for (int i = 2; i < T; ++i) {
+            snprintf(tg, sizeof tg, "wavg%d.A1", layer);
+            if (comm->is_local(1)) comm->post_send(1, i, A1.p, A1.n(), tg);
+            snprintf(tg, sizeof tg, "wavg%d.A0", layer);
+            if (comm->is_local(0)) comm->post_send(0, i, A0.p, A0.n(), tg);
+            if (comm->is_local(i)) {
+                DMat& w = own.at(i).W[layer];
+                rxA1[i].resize(ctx, w.rows, w.cols);
+                rxA0[i].resize(ctx, w.rows, w.cols);
+                comm->post_recv(i, 1, rxA1[i].p, rxA1[i].n());
+                comm->post_recv(i, 0, rxA0[i].p, rxA0[i].n());
+            }
+        }
+        comm->exchange();
+        // afterwards: party 0 holds (A0, A0), party 1 (A1, A1), party i >= 2 (local A1, remote A0)  (gcn.h:765-777)
+        for (int p = 0; p < T; ++p) {
+            if (!comm->is_local(p)) continue;
+            const DMat& local_w = p == 0 ? A0 : (p == 1 ? A1 : rxA1[p]);
+            const DMat& remote_w = p == 0 ? A0 : (p == 1 ? A1 : rxA0[p]);
+            own.at(p).W[layer].copy_from(local_w);
+            hlp.at((p - 1 + T) % T).W[layer].copy_from(remote_w);  // this party's remoteWeight
+        }
+        ck(ctx, cgb_ctx_sync(ctx), "sync");
+    }
+};
+
+// ---- host residual functions (bit-identical to oracle/epoch.py; glibc exp, left-to-right sums) ---------------------
+static void fn_relu(SSGcnEngine::Impl&, int, const std::vector<std::vector<uint64_t>>& in, std::vector<std::vector<uint64_t>>& out) {
+    out.assign(1, in[0]);
+    for (auto& v : out[0])
+        if ((int64_t)v <= 0) v = 0;
+}
+static void fn_relu_grad(SSGcnEngine::Impl&, int, const std::vector<std::vector<uint64_t>>& in, std::vector<std::vector<uint64_t>>& out) {
+    out.assign(1, in[0]);  // in[0] = g, in[1] = z
+    for (size_t i = 0; i < out[0].size(); ++i)
+        if ((int64_t)in[1][i] <= 0) out[0][i] = 0;
+}
+static void fn_softmax(SSGcnEngine::Impl& im, int owner, const std::vector<std::vector<uint64_t>>& in, std::vector<std::vector<uint64_t>>& out) {
+    const uint32_t n = im.n_of[owner], C = im.C;
+    const double scale = (double)(1ull << im.f);
+    const auto& labels = im.party.at(owner).labels;
+    const uint64_t train = (uint64_t)(n * im.cfg.train_ratio);  // gcn.h:560
+    out.assign(2, std::vector<uint64_t>((size_t)n * C));
+    std::vector<double> e(C);
+    for (uint32_t i = 0; i < n; ++i) {
+        double m = -INFINITY;
+        for (uint32_t j = 0; j < C; ++j) {
+            e[j] = (double)(int64_t)in[0][(size_t)i * C + j] / scale;
+            if (e[j] > m) m = e[j];
+        }
+        double tot = 0.0;
+        for (uint32_t j = 0; j < C; ++j) {
+            e[j] = std::exp(e[j] - m);
+            tot += e[j];
+        }
+        for (uint32_t j = 0; j < C; ++j) {
+            const uint64_t pj = (uint64_t)(int64_t)((e[j] / tot) * scale);
+            out[0][(size_t)i * C + j] = pj;
+            uint64_t d = pj - ((uint32_t)labels[i] == j ? (1ull << im.f) : 0ull);
+            if (i >= train) d = 0;  // gcn.h:639-641
+            out[1][(size_t)i * C + j] = d;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+SSGcnEngine::SSGcnEngine(Comm* comm, const GNNConfig& cfg, int f, const uint32_t key[8]) {
+    impl_ = new Impl();
+    impl_->comm = comm;
+    impl_->ctx = comm->ctx();
+    impl_->cfg = cfg;
+    impl_->f = f;
+    memcpy(impl_->key, key, sizeof(impl_->key));
+    impl_->T = comm->world();
+    impl_->F = cfg.input_dim;
+    impl_->H = cfg.hidden_dim;
+    impl_->C = cfg.num_labels;
+    if (cfg.num_layers != 2) throw std::runtime_error("SSGcnEngine: the reference operators hard-code 2 layers (gcn.h:898-927)");
+    if (f <= 0 || f >= 31) throw std::runtime_error("SSGcnEngine: SCALER_BIT_LENGTH must be in (0, 31) (gcn.h:191)");
+}
+
+SSGcnEngine::~SSGcnEngine() {
+    if (!impl_) return;
+    cgb_ctx_sync(impl_->ctx);
+    for (auto& kv : impl_->party)
+        if (kv.second.csr) cgb_csr_destroy(impl_->ctx, kv.second.csr);
+    delete impl_;
+}
+
+void SSGcnEngine::add_party(const PartyGraph& g, const double* feats_local, const int32_t* labels_local) {
+    Impl& im = *impl_;
+    if (!im.comm->is_local(g.me)) throw std::runtime_error("add_party: party is not hosted by this process");
+    PartyData& pd = im.party[g.me];
+    pd.g = g;
+    const uint32_t n = (uint32_t)g.vids.size();
+    if (im.n_of.empty()) {
+        im.n_of.resize(im.T);
+        for (int t = 0; t < im.T; ++t) im.n_of[t] = g.offsets[t + 1] - g.offsets[t];
+    }
+    pd.labels.assign(labels_local, labels_local + n);
+    // gcn.h:819-835, 857-862: raw * (inDeg + 1)^-1/2 with the in-degree BEFORE the dummy increment (ssk.h:177 < 190)
+    pd.feats.resize((size_t)n * im.F);
+    for (uint32_t i = 0; i < n; ++i) {
+        const double sc = std::pow((double)g.in_deg_raw[i] + 1.0, -0.5);
+        for (uint32_t j = 0; j < im.F; ++j) pd.feats[(size_t)i * im.F + j] = feats_local[(size_t)i * im.F + j] * sc;
+    }
+    ck(im.ctx, cgb_csr_create(im.ctx, g.rowptr.data(), g.col.data(), g.offsets[im.T], g.col.size(), n, &pd.csr), "cgb_csr_create");
+    // normaliser (gcn.h:219-221): deg == 0 ? 0 : enc((deg+1)^-1/2); PreScatter is handed inDeg as well (ssk.h:739)
+    std::vector<uint64_t> nv(n);
+    for (uint32_t i = 0; i < n; ++i)
+        nv[i] = g.in_deg[i] == 0 ? 0 : (uint64_t)(int64_t)(std::pow((double)g.in_deg[i] + 1.0, -0.5) * (double)(1ull << im.f));
+    pd.norm.resize(im.ctx, 1, n);
+    ck(im.ctx, cgb_h2d(im.ctx, pd.norm.p, nv.data(), n * 8), "h2d");
+    ck(im.ctx, cgb_ctx_sync(im.ctx), "sync");
+}
+
+// gcn.h:838-852: std::srand(42) per call, then (double) rand() / RAND_MAX * 2 * limit - limit
+static std::vector<double> init_weight(int d0, int d1) {
+    std::vector<double> W((size_t)d0 * d1);
+    std::srand(42);
+    const double limit = std::sqrt(6.0 / (d0 + d1));
+    for (int i = 0; i < d0; ++i)
+        for (int j = 0; j < d1; ++j) W[(size_t)i * d1 + j] = (double)std::rand() / RAND_MAX * 2 * limit - limit;
+    return W;
+}
+
+void SSGcnEngine::setup() {
+    Impl& im = *impl_;
+    cgb_ctx* ctx = im.ctx;
+    const int T = im.T;
+    const uint32_t dims[3] = {im.F, im.H, im.C};
+    std::vector<double> Wp[2] = {init_weight(im.F, im.H), init_weight(im.H, im.C)};
+    im.lr_fixed = (uint64_t)(int64_t)(im.cfg.learning_rate * (double)(1ull << im.f));  // gcn.h:678
+    // Every party splits its own features / weight replica (ssk.h:205, gcn.h:880-882) and ships share 1 to its helper
+    // (ssk.h:209-232).  With dealer randomness both sides of the split are PRG-reproducible, so the owner computes
+    // share 0 and the helper receives share 1 as a message.
+    for (int o = 0; o < T; ++o) {
+        const int qo = im.q(o);
+        if (im.comm->is_local(o)) {
+            Side& s = im.own[o];
+            s.owner = o; s.share = 0; s.n = im.n_of[o];
+            PartyData& pd = im.party.at(o);
+            double* dptr = nullptr;
+            void* dv = nullptr;
+            ck(ctx, cgb_malloc(ctx, std::max<size_t>(pd.feats.size(), 1) * 8, &dv), "malloc");
+            dptr = (double*)dv;
+            ck(ctx, cgb_h2d(ctx, dptr, pd.feats.data(), pd.feats.size() * 8), "h2d");
+            s.X.resize(ctx, s.n, im.F);
+            s.tmp.resize(ctx, s.n, im.F);
+            ck(ctx, cgb_share_split(ctx, dptr, s.X.n(), im.f, im.key, stream_id(K_FEAT, 0, o, 0), 0, s.X.p, s.tmp.p), "share_split");
+            im.comm->post_send(o, qo, s.tmp.p, s.tmp.n(), Impl::tagf("setupX", -1, o));
+            ck(ctx, cgb_ctx_sync(ctx), "sync");
+            cgb_free(ctx, dv);
+        }
+        if (im.comm->is_local(qo)) {
+            Side& h = im.hlp[o];
+            h.owner = o; h.share = 1; h.n = im.n_of[o];
+            h.X.resize(ctx, h.n, im.F);
+            im.comm->post_recv(qo, o, h.X.p, h.X.n());
+        }
+    }
+    im.comm->exchange();
+    for (int l = 0; l < 2; ++l) {
+        std::map<int, DMat> w1;
+        for (int o = 0; o < T; ++o) {
+            const int qo = im.q(o);
+            if (im.comm->is_local(o)) {
+                Side& s = im.own.at(o);
+                void* dv = nullptr;
+                ck(ctx, cgb_malloc(ctx, Wp[l].size() * 8, &dv), "malloc");
+                ck(ctx, cgb_h2d(ctx, dv, Wp[l].data(), Wp[l].size() * 8), "h2d");
+                s.W[l].resize(ctx, dims[l], dims[l + 1]);
+                w1[o].resize(ctx, dims[l], dims[l + 1]);
+                ck(ctx, cgb_share_split(ctx, (const double*)dv, s.W[l].n(), im.f, im.key, stream_id(K_WEIGHT, 0, o, l), 0,
+                                        s.W[l].p, w1[o].p), "share_split");
+                im.comm->post_send(o, qo, w1[o].p, w1[o].n(), Impl::tagf("setupW", l, o));
+                ck(ctx, cgb_ctx_sync(ctx), "sync");
+                cgb_free(ctx, dv);
+            }
+            if (im.comm->is_local(qo)) {
+                Side& h = im.hlp.at(o);
+                h.W[l].resize(ctx, dims[l], dims[l + 1]);
+                im.comm->post_recv(qo, o, h.W[l].p, h.W[l].n());
+            }
+        }
+        im.comm->exchange();  // ssk.h:231-232
+    }
+    im.for_sides([&](Side& s) { s.X_backup.copy_from(s.X); });  // ssk.h:226-227
+    ck(ctx, cgb_ctx_sync(ctx), "sync");
+}
+
+static DMat* sel_V(Side& s, int) { return &s.V; }
+static DMat* sel_X(Side& s, int) { return &s.X; }
+static DMat* sel_XP(Side& s, int k) { return k == 0 ? &s.P : &s.X; }
+static DMat* sel_Xz0(Side& s, int k) { return k == 0 ? &s.X : &s.z[0]; }
+
+void SSGcnEngine::run(uint64_t n_iters) {
+    Impl& im = *impl_;
+    cgb_ctx* ctx = im.ctx;
+    const int T = im.T;
+    const uint32_t F = im.F, H = im.H, C = im.C;
+    for (uint64_t step = 0; step < n_iters; ++step, ++iter_) {
+        const uint64_t it = iter_;
+        const int ph = (int)(it % 6);
+        im.comm->cur_iter = it;
+        auto t0 = std::chrono::high_resolution_clock::now();
+        if (ph == 0) im.for_sides([&](Side& s) { s.X.copy_from(s.X_backup); });  // ssk.h:695, 938
+
+        if (ph == 0 || ph == 1) {
+            // ---------------- forward layer `ph` ----------------
+            const int layer = ph;
+            const uint32_t Din = layer == 0 ? F : H, Dout = layer == 0 ? H : C;
+            im.for_sides([&](Side& s) {  // PreScatterComp (gcn.h:198-255)
+                s.h_t[layer].resize(ctx, Din, s.n);
+                ck(ctx, cgb_transpose(ctx, s.X.p, s.h_t[layer].p, s.n, Din), "transpose");  // gcn.h:230-231
+                im.mm_prepare(s, it, 0, s.X, s.W[layer]);
+                im.mm_post(s, 0);
+            });
+            im.comm->exchange();
+            im.for_sides([&](Side& s) { im.mm_finish(s, s.n, Din, Dout, s.Xp); });
+            if (layer != 0)  // gcn.h:243-254
+                im.rowscale_all(it, 0, [](Side& s) -> DMat& { return s.Xp; }, [](Side& s) -> DMat& { return s.Xp; });
+            im.gas(it);
+            // gcn.h:470-484: in-degree scaling ((it + 1) % 6 != 0 for the forward layers)
+            im.rowscale_all(it, 1, [](Side& s) -> DMat& { return s.V; }, [](Side& s) -> DMat& { return s.V; });
+            im.for_sides([&](Side& s) { s.z[layer].copy_from(s.V); });
+            if (layer == 0) {  // gcn.h:546-558: ReLU -- 2PC-RESIDUAL
+                im.for_sides([&](Side& s) { s.X.resize(ctx, s.n, Dout); });
+                im.residual(it, fn_relu, 1, 1, sel_V, sel_X);
+            } else {  // gcn.h:559-642: softmax, p - y -- 2PC-RESIDUAL; then p is opened to the owner (gcn.h:604)
+                im.for_sides([&](Side& s) {
+                    s.X.resize(ctx, s.n, Dout);
+                    s.P.resize(ctx, s.n, Dout);
+                });
+                im.residual(it, fn_softmax, 1, 2, sel_V, sel_XP);
+                im.for_sides([&](Side& s) {
+                    if (s.share == 1) im.send(im.q(s.owner), s.owner, s.P, Impl::tagf("open_p", -1, s.owner));
+                    else {
+                        s.Ppeer.resize(ctx, s.n, Dout);
+                        im.recv(s.owner, im.q(s.owner), s.Ppeer);
+                    }
+                });
+                im.comm->exchange();
+                im.for_sides([&](Side& s) {
+                    if (s.share != 0) return;
+                    std::vector<double> prob(s.P.n());
+                    void* dv = nullptr;
+                    ck(ctx, cgb_malloc(ctx, std::max<size_t>(prob.size(), 1) * 8, &dv), "malloc");
+                    ck(ctx, cgb_open_decode(ctx, s.P.p, s.Ppeer.p, (double*)dv, s.P.n(), im.f), "open_decode");
+                    ck(ctx, cgb_d2h(ctx, prob.data(), dv, prob.size() * 8), "d2h");
+                    ck(ctx, cgb_ctx_sync(ctx), "sync");
+                    cgb_free(ctx, dv);
+                    const auto& labels = im.party.at(s.owner).labels;
+                    const uint32_t n = s.n;
+                    const uint64_t train = (uint64_t)(n * im.cfg.train_ratio), val = (uint64_t)(n * im.cfg.val_ratio);
+                    double loss = 0;
+                    uint64_t hit_full = 0, hit_train = 0, hit_test = 0;
+                    for (uint32_t i = 0; i < n; ++i) {
+                        uint32_t best = 0;
+                        for (uint32_t j = 0; j < C; ++j) {
+                            double& pj = prob[(size_t)i * C + j];
+                            if (pj == 0) pj = 0.001;  // gcn.h:615
+                            if (pj > prob[(size_t)i * C + best]) best = j;
+                        }
+                        loss -= std::log(std::max(prob[(size_t)i * C + labels[i]], 1e-30));
+                        const bool ok = best == (uint32_t)labels[i];
+                        hit_full += ok;
+                        if (i < train) hit_train += ok;
+                        if (i >= train + val) hit_test += ok;
+                    }
+                    Metrics m{it, s.owner, n ? loss / n : 0.0, n ? (double)hit_full / n : 0.0,
+                              train ? (double)hit_train / train : 0.0,
+                              n > train + val ? (double)hit_test / (n - train - val) : 0.0};
+                    metrics_.push_back(m);
+                    if (verbose) {  // the reference's log lines (gcn.h:620-632)
+                        printf("cross-entropy-loss = %lf\n", m.loss);
+                        printf("full set accuracy = %lf\n", m.acc_full);
+                        printf("training set accuracy = %lf\n", m.acc_train);
+                        printf("test set accuracy = %lf\n", m.acc_test);
+                    }
+                });
+            }
+        } else if (ph == 2) {
+            // ---------------- backward, first step of the last layer: apply only (ssk.h:709-732; gcn.h:664-669) -----
+            im.for_sides([&](Side& s) {
+                s.tmp2.resize(ctx, C, H);
+                ck(ctx, cgb_transpose(ctx, s.W[1].p, s.tmp2.p, H, C), "transpose");  // weightT (gcn.h:648)
+                im.mm_prepare(s, it, 0, s.X, s.tmp2);
+                im.mm_post(s, 0);
+            });
+            im.comm->exchange();
+            im.for_sides([&](Side& s) { im.mm_finish(s, s.n, C, H, s.g); });
+        } else if (ph == 3 || ph == 5) {
+            // ---------------- backward GAS + weight gradient (gcn.h:247-254, 470-484, 671-684 / 710-736) -------------
+            const int layer = ph == 3 ? 1 : 0;
+            const uint32_t Din = layer == 0 ? F : H, Dout = layer == 0 ? H : C;
+            im.rowscale_all(it, 0, [](Side& s) -> DMat& { return s.X; }, [](Side& s) -> DMat& { return s.Xp; });
+            im.gas(it);
+            if ((it + 1) % 6 != 0)  // gcn.h:470: no in-degree scaling on the last iteration of the epoch
+                im.rowscale_all(it, 1, [](Side& s) -> DMat& { return s.V; }, [](Side& s) -> DMat& { return s.V; });
+            im.for_sides([&](Side& s) {
+                im.mm_prepare(s, it, 1, s.h_t[layer], s.V);  // d = h_t * v
+                im.mm_post(s, 1);
+            });
+            im.comm->exchange();
+            im.for_sides([&](Side& s) {
+                DMat d;
+                im.mm_finish(s, Din, s.n, Dout, d);
+                const uint64_t train = (uint64_t)(s.n * im.cfg.train_ratio);
+                const uint64_t gs = train ? (uint64_t)(int64_t)((1.0 / (double)train) * (double)(1ull << im.f)) : 0;  // gcn.h:673-676
+                ck(ctx, cgb_scale_public(ctx, d.p, gs, d.p, d.n(), im.f, s.share), "scale");
+                ck(ctx, cgb_apply_gradient(ctx, s.W[layer].p, d.p, im.lr_fixed, s.W[layer].p, d.n(), im.f, s.share), "apply_gradient");
+                if (layer == 1) s.X.copy_from(s.g);  // dstVec.swap(g) (gcn.h:684)
+                else s.X.copy_from(s.V);             // first layer: g is empty in the reference; never used again
+                ck(ctx, cgb_ctx_sync(ctx), "sync");
+            });
+            im.weight_average(it, layer);
+        } else {
+            // ---------------- ph == 4: ReLU' mask, first layer so no further matmul (gcn.h:702-708) -- 2PC-RESIDUAL ---
+            im.residual(it, fn_relu_grad, 2, 1, sel_Xz0, sel_X);
+        }
+        ck(ctx, cgb_ctx_sync(ctx), "sync");
+        const double dt = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+        seconds_online += dt;
+        if (verbose) printf("::iteration took %lf seconds\n", dt);
+    }
+}
+
+std::vector<uint64_t> SSGcnEngine::download(int owner, int role, const std::string& name, uint32_t* rows, uint32_t* cols) {
+    Impl& im = *impl_;
+    Side* s = im.side(owner, role);
+    if (!s) throw std::runtime_error("download: side not hosted here");
+    DMat* m = nullptr;
+    if (name == "X") m = &s->X;
+    else if (name == "W0") m = &s->W[0];
+    else if (name == "W1") m = &s->W[1];
+    else if (name == "z0") m = &s->z[0];
+    else if (name == "z1") m = &s->z[1];
+    else if (name == "h_t0") m = &s->h_t[0];
+    else if (name == "h_t1") m = &s->h_t[1];
+    else if (name == "g") m = &s->g;
+    else if (name == "V") m = &s->V;
+    else if (name == "Xp") m = &s->Xp;
+    else throw std::runtime_error("download: unknown tensor " + name);
+    std::vector<uint64_t> out(m->n());
+    if (!out.empty()) ck(im.ctx, cgb_d2h(im.ctx, out.data(), m->p, out.size() * 8), "d2h");
+    ck(im.ctx, cgb_ctx_sync(im.ctx), "sync");
+    if (rows) *rows = m->rows;
+    if (cols) *cols = m->cols;
+    return out;
+}
+
+}  // namespace cognn

@@ -133,8 +133,8 @@ class EpochOracle:
         Z1 = po.sub(po.matmul(po.add(U0, U1), po.add(V0, V1)), Z0)  # dealer (offline)
         E0, F0 = po.sub(A0, U0), po.sub(B0, V0)
         E1, F1 = po.sub(A1, U1), po.sub(B1, V1)
-        self.send(it, p, q, f"mm{sub}", E0, F0)
-        self.send(it, q, p, f"mm{sub}", E1, F1)
+        self.send(it, p, q, f"mm{sub}.o{p}", E0, F0)
+        self.send(it, q, p, f"mm{sub}.o{p}", E1, F1)
         E, F = po.add(E0, E1), po.add(F0, F1)
         return (po.beaver_matmul_finish(E, F, U0, V0, Z0, 0, f), po.beaver_matmul_finish(E, F, U1, V1, Z1, 1, f))
 
@@ -148,8 +148,8 @@ class EpochOracle:
         c1 = (a0 + a1) * (b0 + b1)[:, None] - c0  # dealer (offline)
         e0, f0 = po.sub(x0, a0), po.sub(s, b0)
         e1, f1 = po.sub(x1, a1), po.sub(np.zeros(rows, dtype=U64), b1)
-        self.send(it, p, q, f"rm{sub}", e0, f0)
-        self.send(it, q, p, f"rm{sub}", e1, f1)
+        self.send(it, p, q, f"rm{sub}.o{p}", e0, f0)
+        self.send(it, q, p, f"rm{sub}.o{p}", e1, f1)
         e, fv = po.add(e0, e1), po.add(f0, f1)
         return (po.rowmul_beaver_finish(e, fv, a0, b0, c0, 0, f), po.rowmul_beaver_finish(e, fv, a1, b1, c1, 1, f))
 
@@ -157,7 +157,7 @@ class EpochOracle:
         """2PC-RESIDUAL stand-in (ideal functionality, NOT secure): helper sends its shares, owner evaluates in the
         clear on the host and re-shares; the helper's new share is a PRG stream both know from the dealer."""
         q = self.q(p)
-        self.send(it, q, p, f"res{sub}", *ins1)
+        self.send(it, q, p, f"res{sub}.o{p}", *ins1)
         outs = fn(*[po.add(a, b) for a, b in zip(ins0, ins1)])
         assert len(outs) == n_out
         o0, o1 = [], []
@@ -177,7 +177,7 @@ class EpochOracle:
             q = self.q(p)
             r = self.prg(K_OM_R, it, p, 0, (self.n[p], D))
             m = po.sub(X1s[p], r)
-            self.send(it, q, p, "om", m)
+            self.send(it, q, p, f"om.o{p}", m)
             S = np.concatenate([self.prg(K_OM_S, it, p, t, (self.n[t], D)) for t in range(T)])
             rowptr, col = self.csr[p]
             delta = po.sub(po.gather_sum_csr(rowptr, col, r), S)  # dealer (offline): A r - s
@@ -185,7 +185,7 @@ class EpochOracle:
         for p in range(T):  # round 2: mirror-update blocks to the primary helper of each destination owner
             for t in range(T):
                 if t != p and self.q(t) != p:
-                    self.send(it, p, self.q(t), "upd", Y[p][self.offsets[t]:self.offsets[t + 1]])
+                    self.send(it, p, self.q(t), f"upd.o{p}.t{t}", Y[p][self.offsets[t]:self.offsets[t + 1]])
         V0s, V1s = [], []
         for t in range(T):  # GatherComp additions (gcn.h:456-463): owner side and helper side
             lo, hi = self.offsets[t], self.offsets[t + 1]
@@ -212,9 +212,15 @@ class EpochOracle:
 
         def fn(z):
             zd = po.decode(z, f)
-            zd = zd - zd.max(axis=1, keepdims=True)
-            ez = np.exp(zd)
-            prob = ez / ez.sum(axis=1, keepdims=True)
+            prob = np.zeros_like(zd)
+            for i in range(n):  # glibc exp, left-to-right sums: the engine's host stand-in does exactly this
+                row = zd[i].tolist()
+                m = max(row)
+                e = [math.exp(v - m) for v in row]
+                tot = 0.0
+                for v in e:
+                    tot += v
+                prob[i] = [v / tot for v in e]
             P = po.encode(prob, f)
             onehot = np.zeros((n, C), dtype=U64)
             onehot[np.arange(n), labels] = U64(1 << f)
@@ -235,8 +241,8 @@ class EpochOracle:
         # party 0 accumulates A0 = W0_0 + sum_{i>=1} W1_i (W1_i is held by party q(i)); party 1 accumulates
         # A1 = W0_1 + sum_{i>=2} W0_i + W1_0 (gcn.h:753-765 + 773-775)
         for i in range(2, T):
-            self.send(it, i, 1, f"w{layer}", self.own[i]["W"][layer])        # clientTaskComm.send(weightRef, 1)
-            self.send(it, i, 0, f"w{layer}", self.hlp[i - 1]["W"][layer])    # serverTaskComm.send(coWeightRef, 0)
+            self.send(it, i, 1, f"w{layer}.own{i}", self.own[i]["W"][layer])        # clientTaskComm.send(weightRef, 1)
+            self.send(it, i, 0, f"w{layer}.hlp{i - 1}", self.hlp[i - 1]["W"][layer])    # serverTaskComm.send(coWeightRef, 0)
         A0 = self.own[0]["W"][layer].copy()
         for i in range(2, T):
             A0 = po.add(A0, self.hlp[i - 1]["W"][layer])
@@ -249,8 +255,8 @@ class EpochOracle:
         A0 = po.scale_public(A0, c, f, 0)
         A1 = po.scale_public(A1, c, f, 1)
         for i in range(2, T):
-            self.send(it, 1, i, f"wavg{layer}", A1)   # party i: weightRef <- party 1
-            self.send(it, 0, i, f"wavg{layer}", A0)   # party i: coWeightRef <- party 0
+            self.send(it, 1, i, f"wavg{layer}.A1", A1)   # party i: weightRef <- party 1
+            self.send(it, 0, i, f"wavg{layer}.A0", A0)   # party i: coWeightRef <- party 0
         # afterwards: party 0 holds (A0, A0), party 1 (A1, A1), party i >= 2 (local A1, remote A0)  (gcn.h:765-777)
         for p in range(T):
             self.own[p]["W"][layer] = (A0 if p == 0 else A1).copy()
@@ -299,7 +305,7 @@ class EpochOracle:
                 own["X"], hlp["X"] = h0, h1
             else:  # gcn.h:559-642
                 (P0, d0), (P1, d1) = self.residual(it, p, 0, self.make_f_softmax(p), [v0], [v1], 2)
-                self.send(it, self.q(p), p, "open_p", P1)  # getPlainShareVecVec (gcn.h:604): the owner learns p
+                self.send(it, self.q(p), p, f"open_p.o{p}", P1)  # getPlainShareVecVec (gcn.h:604): the owner learns p
                 prob = po.open_decode(P0, P1, self.f)
                 self.log.append(self.metrics(it, p, prob))
                 own["X"], hlp["X"] = d0, d1

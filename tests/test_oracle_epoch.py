@@ -56,9 +56,11 @@ def test_message_schedule_two_parties_has_no_update_blocks():
     cfg = dict(input_dim=6, hidden_dim=4, num_labels=3, learning_rate=0.5, train_ratio=0.4, val_ratio=0.2)
     o = ep.EpochOracle(g["edges"], g["tid"], 2, g["feats"], g["labels"], cfg)
     o.run(6)
-    tags = {m[3] for m in o.msgs}
+    tags = {m[3].split(".")[0] for m in o.msgs}
     assert "upd" not in tags and "w0" not in tags  # T = 2: the primary helper of the other party is the sender itself
     assert {"mm0", "mm1", "rm0", "rm1", "om", "res0", "open_p"} <= tags
+    keys = [m[:4] for m in o.msgs]
+    assert len(keys) == len(set(keys))  # (iteration, src, dst, tag) identifies a message
     # determinism: same seeds, same bytes
     o2 = ep.EpochOracle(g["edges"], g["tid"], 2, g["feats"], g["labels"], cfg)
     o2.run(6)
