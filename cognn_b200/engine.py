@@ -21,7 +21,7 @@ class CgeConfig(C.Structure):
 
 ENGINE_SYMBOLS = ["cge_last_error", "cge_nccl_unique_id", "cge_create_loopback", "cge_create_nccl", "cge_destroy",
                   "cge_add_party", "cge_setup", "cge_run", "cge_download", "cge_message_count", "cge_message_info",
-                  "cge_message_data", "cge_words_sent", "cge_rounds", "cge_launch_count", "cge_seconds_online",
+                  "cge_message_data", "cge_words_sent", "cge_rounds", "cge_launch_count", "cge_seconds_online", "cge_seconds_offline",
                   "cge_metrics_count", "cge_metrics_get", "cge_build_party_graph"]
 
 
@@ -41,8 +41,9 @@ def load_host():
     for n in ("cge_message_count", "cge_words_sent", "cge_rounds", "cge_launch_count", "cge_metrics_count"):
         getattr(h, n).restype = C.c_uint64
         getattr(h, n).argtypes = [C.c_void_p]
-    h.cge_seconds_online.restype = C.c_double
-    h.cge_seconds_online.argtypes = [C.c_void_p]
+    for n in ("cge_seconds_online", "cge_seconds_offline"):
+        getattr(h, n).restype = C.c_double
+        getattr(h, n).argtypes = [C.c_void_p]
     h.cge_create_loopback.argtypes = [C.c_int, C.c_void_p, C.c_int, C.POINTER(CgeConfig), C.POINTER(C.c_void_p)]
     h.cge_create_nccl.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(CgeConfig), C.POINTER(C.c_void_p)]
     h.cge_destroy.argtypes = [C.c_void_p]
@@ -170,6 +171,14 @@ class Engine:
     @property
     def rounds(self):
         return int(self.h.cge_rounds(self.e))
+
+    @property
+    def seconds_online(self):
+        return float(self.h.cge_seconds_online(self.e))
+
+    @property
+    def seconds_offline(self):
+        return float(self.h.cge_seconds_offline(self.e))
 
     @property
     def launches(self):

@@ -177,9 +177,10 @@ struct Side {
     DMat X, X_backup, W[2], h_t[2], z[2], g;
     // per-iteration temporaries
     DMat Xp, V, Y, m, tmp, tmp2;
-    DMat mmU, mmV, mmZ, mm_mine, mm_peer, mmE, mmF;
-    DMat rmA, rmB, rmC, rm_mine, rm_peer, rmE;
-    DMat res_in, res_out[2], P, Ppeer;
+    // dealer correlations of the current iteration (offline phase), indexed by `sub`
+    DMat mmU[2], mmV[2], mmZ[2], rmA[2], rmB[2], rmC[2];
+    DMat mm_mine, mm_peer, rm_mine, rm_peer;
+    DMat res_in, res_plain, P, Ppeer, grad;
     std::vector<DMat> upd_recv;  // helper side: masked sums received from the other owners
     DMat delta, S;
 };
@@ -229,32 +230,37 @@ struct SSGcnEngine::Impl {
     }
 
     // ---- Beaver matmul (sci::twoPartyGCNMatMul, gcn.h:233,665,671,710): prepare -> exchange -> finish --------------
-    void mm_prepare(Side& s, uint64_t it, int sub, const DMat& A, const DMat& B) {
-        const uint32_t M = A.rows, K = A.cols, N = B.cols;
+    // offline (dealer emulation): this side's share of the triple (U, V, Z = U V)
+    void mm_deal(Side& s, uint64_t it, int sub, uint32_t M, uint32_t K, uint32_t N) {
         if (s.share == 0) {
-            prg(K_MM_U0, it, s.owner, sub, s.mmU, M, K);
-            prg(K_MM_V0, it, s.owner, sub, s.mmV, K, N);
-            prg(K_MM_Z0, it, s.owner, sub, s.mmZ, M, N);
+            prg(K_MM_U0, it, s.owner, sub, s.mmU[sub], M, K);
+            prg(K_MM_V0, it, s.owner, sub, s.mmV[sub], K, N);
+            prg(K_MM_Z0, it, s.owner, sub, s.mmZ[sub], M, N);
         } else {
-            // dealer emulation (offline phase): Z1 = (U0+U1)(V0+V1) - Z0
+            // Z1 = (U0+U1)(V0+V1) - Z0
             DMat U0, V0, Z0;
             prg(K_MM_U0, it, s.owner, sub, U0, M, K);
             prg(K_MM_V0, it, s.owner, sub, V0, K, N);
             prg(K_MM_Z0, it, s.owner, sub, Z0, M, N);
-            prg(K_MM_U1, it, s.owner, sub, s.mmU, M, K);
-            prg(K_MM_V1, it, s.owner, sub, s.mmV, K, N);
-            vadd(U0.p, s.mmU.p, U0.p, U0.n());
-            vadd(V0.p, s.mmV.p, V0.p, V0.n());
-            s.mmZ.resize(ctx, M, N);
-            ck(ctx, cgb_matmul(ctx, U0.p, V0.p, s.mmZ.p, M, K, N, 0, 0), "cgb_matmul(dealer)");
-            vsub(s.mmZ.p, Z0.p, s.mmZ.p, s.mmZ.n());
+            prg(K_MM_U1, it, s.owner, sub, s.mmU[sub], M, K);
+            prg(K_MM_V1, it, s.owner, sub, s.mmV[sub], K, N);
+            vadd(U0.p, s.mmU[sub].p, U0.p, U0.n());
+            vadd(V0.p, s.mmV[sub].p, V0.p, V0.n());
+            s.mmZ[sub].resize(ctx, M, N);
+            ck(ctx, cgb_matmul(ctx, U0.p, V0.p, s.mmZ[sub].p, M, K, N, 0, 0), "cgb_matmul(dealer)");
+            vsub(s.mmZ[sub].p, Z0.p, s.mmZ[sub].p, s.mmZ[sub].n());
             ck(ctx, cgb_ctx_sync(ctx), "sync");  // U0/V0/Z0 are freed at scope exit
         }
-        // [E_i | F_i] in one message
+    }
+    // online: [E_i | F_i] = [A - U | B - V] in one message
+    void mm_prepare(Side& s, uint64_t, int sub, const DMat& A, const DMat& B) {
+        const uint32_t M = A.rows, K = A.cols, N = B.cols;
+        if (s.mmU[sub].rows != M || s.mmU[sub].cols != K || s.mmV[sub].cols != N)
+            throw std::runtime_error("mm_prepare: triple was dealt for another shape");
         s.mm_mine.resize(ctx, 1, M * K + K * N);
         s.mm_peer.resize(ctx, 1, M * K + K * N);
-        vsub(A.p, s.mmU.p, s.mm_mine.p, (size_t)M * K);
-        vsub(B.p, s.mmV.p, s.mm_mine.p + (size_t)M * K, (size_t)K * N);
+        vsub(A.p, s.mmU[sub].p, s.mm_mine.p, (size_t)M * K);
+        vsub(B.p, s.mmV[sub].p, s.mm_mine.p + (size_t)M * K, (size_t)K * N);
     }
     void mm_post(Side& s, int sub) {
         const int holder = s.share == 0 ? s.owner : q(s.owner);
@@ -262,31 +268,29 @@ struct SSGcnEngine::Impl {
         send(holder, other, s.mm_mine, tagf("mm", sub, s.owner));
         recv(holder, other, s.mm_peer);
     }
-    void mm_finish(Side& s, uint32_t M, uint32_t K, uint32_t N, DMat& C_out) {
+    void mm_finish(Side& s, int sub, uint32_t M, uint32_t K, uint32_t N, DMat& C_out) {
         vadd(s.mm_mine.p, s.mm_peer.p, s.mm_mine.p, s.mm_mine.n());  // E | F opened
         C_out.resize(ctx, M, N);
-        ck(ctx, cgb_beaver_matmul_finish(ctx, s.mm_mine.p, s.mm_mine.p + (size_t)M * K, s.mmU.p, s.mmV.p, s.mmZ.p,
+        ck(ctx, cgb_beaver_matmul_finish(ctx, s.mm_mine.p, s.mm_mine.p + (size_t)M * K, s.mmU[sub].p, s.mmV[sub].p, s.mmZ[sub].p,
                                          C_out.p, M, K, N, s.share, f), "cgb_beaver_matmul_finish");
     }
 
     // ---- Beaver row scaling (sci::twoPartyGCNVectorScale, gcn.h:247,476): scaler private to the owner -------------
-    void rm_prepare(Side& s, uint64_t it, int sub, const DMat& x, const DMat* scaler) {
-        const uint32_t rows = x.rows, D = x.cols;
+    void rm_deal(Side& s, uint64_t it, int sub, uint32_t rows, uint32_t D) {
         if (s.share == 0) {
-            prg(K_RM_A0, it, s.owner, sub, s.rmA, rows, D);
-            prg(K_RM_B0, it, s.owner, sub, s.rmB, 1, rows);
-            prg(K_RM_C0, it, s.owner, sub, s.rmC, rows, D);
+            prg(K_RM_A0, it, s.owner, sub, s.rmA[sub], rows, D);
+            prg(K_RM_B0, it, s.owner, sub, s.rmB[sub], 1, rows);
+            prg(K_RM_C0, it, s.owner, sub, s.rmC[sub], rows, D);
         } else {
-            DMat a0, b0, c0, ones;
+            DMat a0, b0, c0;
             prg(K_RM_A0, it, s.owner, sub, a0, rows, D);
             prg(K_RM_B0, it, s.owner, sub, b0, 1, rows);
             prg(K_RM_C0, it, s.owner, sub, c0, rows, D);
-            prg(K_RM_A1, it, s.owner, sub, s.rmA, rows, D);
-            prg(K_RM_B1, it, s.owner, sub, s.rmB, 1, rows);
-            vadd(a0.p, s.rmA.p, a0.p, a0.n());
-            vadd(b0.p, s.rmB.p, b0.p, b0.n());
-            // c1 = (a0+a1) * (b0+b1)[row] - c0  ==  rowmul_finish(e = a, fv = b, a' = 0, b' = 0, c = -c0) on share 0
-            // computed with the generic kernel: out = c + e*b' + fv*a' + e*fv with a' = b' = 0, c = 0 - c0
+            prg(K_RM_A1, it, s.owner, sub, s.rmA[sub], rows, D);
+            prg(K_RM_B1, it, s.owner, sub, s.rmB[sub], 1, rows);
+            vadd(a0.p, s.rmA[sub].p, a0.p, a0.n());
+            vadd(b0.p, s.rmB[sub].p, b0.p, b0.n());
+            // c1 = (a0+a1) * (b0+b1)[row] - c0, with the generic kernel: out = c + e*b' + fv*a' + e*fv, a' = b' = 0, c = -c0
             DMat zero_mat, zero_vec, negc;
             zero_mat.resize(ctx, rows, D);
             zero_vec.resize(ctx, 1, rows);
@@ -294,19 +298,23 @@ struct SSGcnEngine::Impl {
             ck(ctx, cgb_memset(ctx, zero_vec.p, 0, zero_vec.n() * 8), "memset");
             negc.resize(ctx, rows, D);
             vsub(zero_mat.p, c0.p, negc.p, negc.n());
-            s.rmC.resize(ctx, rows, D);
-            ck(ctx, cgb_rowmul_beaver_finish(ctx, a0.p, b0.p, zero_mat.p, zero_vec.p, negc.p, s.rmC.p, rows, D, 0, -1),
+            s.rmC[sub].resize(ctx, rows, D);
+            ck(ctx, cgb_rowmul_beaver_finish(ctx, a0.p, b0.p, zero_mat.p, zero_vec.p, negc.p, s.rmC[sub].p, rows, D, 0, -1),
                "rowmul(dealer)");
             ck(ctx, cgb_ctx_sync(ctx), "sync");
         }
+    }
+    void rm_prepare(Side& s, uint64_t, int sub, const DMat& x, const DMat* scaler) {
+        const uint32_t rows = x.rows, D = x.cols;
+        if (s.rmA[sub].rows != rows || s.rmA[sub].cols != D) throw std::runtime_error("rm_prepare: triple was dealt for another shape");
         s.rm_mine.resize(ctx, 1, rows * D + rows);
         s.rm_peer.resize(ctx, 1, rows * D + rows);
-        vsub(x.p, s.rmA.p, s.rm_mine.p, (size_t)rows * D);
+        vsub(x.p, s.rmA[sub].p, s.rm_mine.p, (size_t)rows * D);
         if (s.share == 0) {
-            vsub(scaler->p, s.rmB.p, s.rm_mine.p + (size_t)rows * D, rows);
+            vsub(scaler->p, s.rmB[sub].p, s.rm_mine.p + (size_t)rows * D, rows);
         } else {
             ck(ctx, cgb_memset(ctx, s.rm_mine.p + (size_t)rows * D, 0, (size_t)rows * 8), "memset");
-            vsub(s.rm_mine.p + (size_t)rows * D, s.rmB.p, s.rm_mine.p + (size_t)rows * D, rows);
+            vsub(s.rm_mine.p + (size_t)rows * D, s.rmB[sub].p, s.rm_mine.p + (size_t)rows * D, rows);
         }
     }
     void rm_post(Side& s, int sub) {
@@ -315,10 +323,10 @@ struct SSGcnEngine::Impl {
         send(holder, other, s.rm_mine, tagf("rm", sub, s.owner));
         recv(holder, other, s.rm_peer);
     }
-    void rm_finish(Side& s, uint32_t rows, uint32_t D, DMat& out) {
+    void rm_finish(Side& s, int sub, uint32_t rows, uint32_t D, DMat& out) {
         vadd(s.rm_mine.p, s.rm_peer.p, s.rm_mine.p, s.rm_mine.n());
         out.resize(ctx, rows, D);
-        ck(ctx, cgb_rowmul_beaver_finish(ctx, s.rm_mine.p, s.rm_mine.p + (size_t)rows * D, s.rmA.p, s.rmB.p, s.rmC.p,
+        ck(ctx, cgb_rowmul_beaver_finish(ctx, s.rm_mine.p, s.rm_mine.p + (size_t)rows * D, s.rmA[sub].p, s.rmB[sub].p, s.rmC[sub].p,
                                          out.p, rows, D, s.share, f), "cgb_rowmul_beaver_finish");
     }
 
@@ -343,10 +351,44 @@ struct SSGcnEngine::Impl {
             DMat& x = getx(s);
             DMat& o = getout(s);
             if (&o == &x) {
-                rm_finish(s, x.rows, x.cols, s.tmp);
+                rm_finish(s, sub, x.rows, x.cols, s.tmp);
                 std::swap(s.tmp, x);
             } else {
-                rm_finish(s, x.rows, x.cols, o);
+                rm_finish(s, sub, x.rows, x.cols, o);
+            }
+        });
+    }
+
+    // offline: the owner's OM correlation delta = A r - S (S = the mask shares s_{p->t} of all destination blocks)
+    void om_deal(Side& s, uint64_t it, uint32_t D) {
+        if (s.share != 0) return;
+        PartyData& pd = party[s.owner];
+        const uint32_t n_rows = pd.g.offsets[T];
+        DMat r;
+        prg(K_OM_R, it, s.owner, 0, r, s.n, D);
+        s.S.resize(ctx, n_rows, D);
+        for (int t = 0; t < T; ++t) {
+            const size_t off = (size_t)pd.g.offsets[t] * D, cnt = (size_t)n_of[t] * D;
+            ck(ctx, cgb_prg_fill(ctx, key, stream_id(K_OM_S, it, s.owner, t), 0, s.S.p + off, cnt), "prg S");
+        }
+        s.delta.resize(ctx, n_rows, D);
+        ck(ctx, cgb_gather_sum(ctx, pd.csr, r.p, nullptr, s.delta.p, D), "gather(dealer)");
+        vsub(s.delta.p, s.S.p, s.delta.p, s.delta.n());
+        ck(ctx, cgb_ctx_sync(ctx), "sync");  // r freed at scope exit
+    }
+
+    // everything the dealer hands out for iteration `it` (shapes per SURVEY 3.4)
+    void deal_iteration(uint64_t it) {
+        const int ph = (int)(it % 6);
+        for_sides([&](Side& s) {
+            const uint32_t n = s.n;
+            switch (ph) {
+                case 0: mm_deal(s, it, 0, n, F, H); om_deal(s, it, H); rm_deal(s, it, 1, n, H); break;
+                case 1: mm_deal(s, it, 0, n, H, C); rm_deal(s, it, 0, n, C); om_deal(s, it, C); rm_deal(s, it, 1, n, C); break;
+                case 2: mm_deal(s, it, 0, n, C, H); break;
+                case 3: rm_deal(s, it, 0, n, C); om_deal(s, it, C); rm_deal(s, it, 1, n, C); mm_deal(s, it, 1, H, n, C); break;
+                case 4: break;
+                case 5: rm_deal(s, it, 0, n, H); om_deal(s, it, H); mm_deal(s, it, 1, F, n, H); break;
             }
         });
     }
@@ -371,22 +413,11 @@ struct SSGcnEngine::Impl {
             if (s.share != 0) return;
             PartyData& pd = party[s.owner];
             const uint32_t D = s.Xp.cols, n_rows = pd.g.offsets[T];
-            // dealer emulation (offline): delta = A r - S
-            DMat r;
-            prg(K_OM_R, it, s.owner, 0, r, s.n, D);
-            s.S.resize(ctx, n_rows, D);
-            for (int t = 0; t < T; ++t) {
-                const size_t off = (size_t)pd.g.offsets[t] * D, cnt = (size_t)n_of[t] * D;
-                ck(ctx, cgb_prg_fill(ctx, key, stream_id(K_OM_S, it, s.owner, t), 0, s.S.p + off, cnt), "prg S");
-            }
-            s.delta.resize(ctx, n_rows, D);
-            ck(ctx, cgb_gather_sum(ctx, pd.csr, r.p, nullptr, s.delta.p, D), "gather(dealer)");
-            vsub(s.delta.p, s.S.p, s.delta.p, s.delta.n());
             // online: Y = A (Xp0 + m) + delta
             vadd(s.Xp.p, s.m.p, s.m.p, s.m.n());
             s.Y.resize(ctx, n_rows, D);
+            if (s.delta.cols != D) throw std::runtime_error("gas: OM correlation was dealt for another width");
             ck(ctx, cgb_gather_sum(ctx, pd.csr, s.m.p, s.delta.p, s.Y.p, D), "cgb_gather_sum");
-            ck(ctx, cgb_ctx_sync(ctx), "sync");  // r freed at scope exit
         });
         // round 2: mirror-update blocks to the primary helper of each destination owner (ssk.h:1090)
         for (int p = 0; p < T; ++p) {
@@ -477,11 +508,10 @@ struct SSGcnEngine::Impl {
                 fn(*this, s.owner, in, out);
                 for (int k = 0; k < n_out; ++k) {
                     DMat* o = out_sel(s, k);
-                    DMat plain;
-                    plain.resize(ctx, o->rows, o->cols);
-                    ck(ctx, cgb_h2d(ctx, plain.p, out[k].data(), out[k].size() * 8), "h2d");
-                    ck(ctx, cgb_prg_mask_sub(ctx, key, stream_id(K_RESHARE, it, s.owner, k), 0, plain.p, o->p, o->n()), "reshare");
-                    ck(ctx, cgb_ctx_sync(ctx), "sync");
+                    s.res_plain.resize(ctx, o->rows, o->cols);
+                    ck(ctx, cgb_h2d(ctx, s.res_plain.p, out[k].data(), out[k].size() * 8), "h2d");
+                    ck(ctx, cgb_prg_mask_sub(ctx, key, stream_id(K_RESHARE, it, s.owner, k), 0, s.res_plain.p, o->p, o->n()), "reshare");
+                    ck(ctx, cgb_ctx_sync(ctx), "sync");  // out[k] is a pageable host vector about to die
                 }
             } else {
                 for (int k = 0; k < n_out; ++k) {
@@ -738,7 +768,11 @@ void SSGcnEngine::run(uint64_t n_iters) {
         const uint64_t it = iter_;
         const int ph = (int)(it % 6);
         im.comm->cur_iter = it;
+        auto t_deal = std::chrono::high_resolution_clock::now();
+        im.deal_iteration(it);  // offline phase (dealer emulation), timed separately
+        ck(ctx, cgb_ctx_sync(ctx), "sync");
         auto t0 = std::chrono::high_resolution_clock::now();
+        seconds_offline += std::chrono::duration<double>(t0 - t_deal).count();
         if (ph == 0) im.for_sides([&](Side& s) { s.X.copy_from(s.X_backup); });  // ssk.h:695, 938
 
         if (ph == 0 || ph == 1) {
@@ -752,7 +786,7 @@ void SSGcnEngine::run(uint64_t n_iters) {
                 im.mm_post(s, 0);
             });
             im.comm->exchange();
-            im.for_sides([&](Side& s) { im.mm_finish(s, s.n, Din, Dout, s.Xp); });
+            im.for_sides([&](Side& s) { im.mm_finish(s, 0, s.n, Din, Dout, s.Xp); });
             if (layer != 0)  // gcn.h:243-254
                 im.rowscale_all(it, 0, [](Side& s) -> DMat& { return s.Xp; }, [](Side& s) -> DMat& { return s.Xp; });
             im.gas(it);
@@ -824,7 +858,7 @@ void SSGcnEngine::run(uint64_t n_iters) {
                 im.mm_post(s, 0);
             });
             im.comm->exchange();
-            im.for_sides([&](Side& s) { im.mm_finish(s, s.n, C, H, s.g); });
+            im.for_sides([&](Side& s) { im.mm_finish(s, 0, s.n, C, H, s.g); });
         } else if (ph == 3 || ph == 5) {
             // ---------------- backward GAS + weight gradient (gcn.h:247-254, 470-484, 671-684 / 710-736) -------------
             const int layer = ph == 3 ? 1 : 0;
@@ -839,15 +873,14 @@ void SSGcnEngine::run(uint64_t n_iters) {
             });
             im.comm->exchange();
             im.for_sides([&](Side& s) {
-                DMat d;
-                im.mm_finish(s, Din, s.n, Dout, d);
+                DMat& d = s.grad;
+                im.mm_finish(s, 1, Din, s.n, Dout, d);
                 const uint64_t train = (uint64_t)(s.n * im.cfg.train_ratio);
                 const uint64_t gs = train ? (uint64_t)(int64_t)((1.0 / (double)train) * (double)(1ull << im.f)) : 0;  // gcn.h:673-676
                 ck(ctx, cgb_scale_public(ctx, d.p, gs, d.p, d.n(), im.f, s.share), "scale");
                 ck(ctx, cgb_apply_gradient(ctx, s.W[layer].p, d.p, im.lr_fixed, s.W[layer].p, d.n(), im.f, s.share), "apply_gradient");
                 if (layer == 1) s.X.copy_from(s.g);  // dstVec.swap(g) (gcn.h:684)
                 else s.X.copy_from(s.V);             // first layer: g is empty in the reference; never used again
-                ck(ctx, cgb_ctx_sync(ctx), "sync");
             });
             im.weight_average(it, layer);
         } else {

@@ -1,0 +1,119 @@
+#!/usr/bin/env python
+"""Secure-GCN epoch / inference time of the engine on the named synthetic shapes (BASELINE.json configs 0-3).
+
+  python tools/epoch_bench.py --shape cora --parties 2 --mode train            all parties on ONE GPU (loopback plane)
+  torchrun --nproc-per-node T tools/epoch_bench.py --shape arxiv --parties T   one party per GPU (NCCL plane)
+
+Reports the online time per epoch (max over ranks), the offline (dealer emulation) time, messages, kernel launches,
+and -- with --cpu -- the CPU oracle restatement of the same epoch on the host (Python-orchestrated C kernels).
+The 2PC-residual steps (ReLU / softmax / ReLU') run as the host ideal-functionality stand-in on both sides; WAN cost
+is out of scope."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from tools import synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="cora")
+    ap.add_argument("--parties", type=int, default=2)
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--epochs", type=int, default=3)
+    ap.add_argument("--inter", type=float, default=None, help="fraction of inter-party edges (block partition)")
+    ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle epoch")
+    ap.add_argument("--check", action="store_true", help="compare the final weight shares with the CPU oracle")
+    args = ap.parse_args()
+
+    import torch
+
+    from cognn_b200 import engine as eng
+
+    T = args.parties
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    g = synth.make(args.shape, T, args.inter)
+    iters = 6 if args.mode == "train" else 2
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        assert world == T, "one rank per party"
+        import torch.distributed as dist
+
+        dist.init_process_group("gloo")  # only to hand out the NCCL unique id; the data plane is the engine's own NCCL comm
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            import ctypes
+
+            buf = (ctypes.c_char * 128)()
+            assert eng.load_host().cge_nccl_unique_id(buf) == 0
+            uid = torch.frombuffer(bytearray(bytes(buf)), dtype=torch.uint8).clone()
+        dist.broadcast(uid, 0)
+        e = eng.Engine(T, g["cfg"], device=local_rank, rank=rank, nccl_uid=bytes(uid.numpy().tobytes()))
+    else:
+        e = eng.Engine(T, g["cfg"], device=local_rank)
+    t0 = time.perf_counter()
+    e.load(g["edges"], g["tid"], g["feats"], g["labels"])
+    t_load = time.perf_counter() - t0
+    per_epoch = []
+
+    def measured(n):
+        on0, off0, l0, w0, r0 = e.seconds_online, e.seconds_offline, e.launches, e.words_sent, e.rounds
+        e.run(n)
+        return {"online_s": e.seconds_online - on0, "offline_s": e.seconds_offline - off0,
+                "launches": e.launches - l0, "words_sent": e.words_sent - w0, "rounds": e.rounds - r0}
+
+    for ep_i in range(args.epochs + 1):  # the first pass is a warm-up (allocations, NCCL connections)
+        per_epoch.append(measured(iters))
+        if args.mode == "infer":
+            e.run(4)  # inference = iterations 0 and 1 (-m 2 in the reference); finish the epoch untimed to get back to 0
+    warm = per_epoch[1:] or per_epoch
+    online = min(x["online_s"] for x in warm)
+    if world > 1:
+        t = torch.tensor([online], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        online = float(t.item())
+    rec = {"bench": "secure_gcn_" + ("epoch" if args.mode == "train" else "inference"), "shape": args.shape, "parties": T,
+           "plane": "nccl" if world > 1 else "loopback(1 GPU)", "N": g["N"], "E": g["E"],
+           "inter_party_edges": g["inter_party_edges"], "cfg": {k: g["cfg"][k] for k in ("input_dim", "hidden_dim", "num_labels")},
+           "iterations": iters, "online_s": online, "offline_dealer_s": min(x["offline_s"] for x in warm),
+           "launches": warm[-1]["launches"], "words_sent_local": warm[-1]["words_sent"], "rounds": warm[-1]["rounds"],
+           "load_s": t_load, "metrics_last": e.metrics()[-T:] if world == 1 else e.metrics()[-1:],
+           "gas_edges_per_s": g["E"] * (4 if args.mode == "train" else 2) / online,
+           "note": "2PC-residual steps = host ideal-functionality stand-in; WAN out of scope"}
+    if args.cpu and rank == 0:
+        from oracle import epoch as oep
+        from oracle import pyoracle as po
+
+        t0 = time.perf_counter()
+        o = oep.EpochOracle(g["edges"], g["tid"], T, g["feats"], g["labels"], g["cfg"])
+        t_setup = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        o.run(iters)
+        rec["cpu_oracle"] = {"epoch_s": time.perf_counter() - t0, "setup_s": t_setup, "cores": po.num_threads(),
+                             "kind": "port (python-orchestrated C kernels, includes dealer work)"}
+        if args.check and world == 1:
+            e2 = eng.Engine(T, g["cfg"], device=local_rank)
+            e2.load(g["edges"], g["tid"], g["feats"], g["labels"])
+            e2.run(iters)
+            ok = all(np.array_equal(e2.download(p, r, n), (o.own if r == 0 else o.hlp)[p]["W"][int(n[1])])
+                     for p in range(T) for r in (0, 1) for n in ("W0", "W1"))
+            rec["bit_exact_vs_oracle"] = bool(ok)
+            e2.close()
+    if rank == 0:
+        print(json.dumps(rec), flush=True)
+    e.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
