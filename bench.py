@@ -77,6 +77,17 @@ def build_party_csr(torch, n_local, n_edges, n_parties, rank, seed, device):
     return rowptr.int(), col
 
 
+def exchange_and_sum(dist, y, recv, v, n_parties, n_local, D, add):
+    """Mirror-update exchange of one GAS iteration (ssk.h:835 -> 1067/1090): block i of y goes to party i, then the
+    received blocks are summed share-locally (GatherComp add, gcn.h:456).  `add(a, b, out)` is the engine's add."""
+    dist.all_to_all_single(recv, y)
+    blocks = recv.view(n_parties, n_local, D)
+    add(blocks[0], blocks[1], v)
+    for j in range(2, n_parties):
+        add(v, blocks[j], v)
+    return v
+
+
 def algorithmic_bytes(n_rows, n_edges, D):
     # SURVEY.md 8d, fused SpMM form: every edge = one 8*D-byte row read + a 4-byte index, no cache-reuse credit
     return (8 * D + 4) * n_edges + 4 * (n_rows + 1) + 8 * D * n_rows
@@ -278,11 +289,7 @@ def main():
     def step():
         ctx.gather_sum(csr, x, None, out=y)
         if P > 1:
-            dist.all_to_all_single(recv, y)  # mirror-update blocks: block i of y -> party i
-            blocks = recv.view(P, n_local, D)
-            ctx.add(blocks[0], blocks[1], out=v)
-            for j in range(2, P):
-                ctx.add(v, blocks[j], out=v)
+            exchange_and_sum(dist, y, recv, v, P, n_local, D, lambda a, b, o: ctx.add(a, b, out=o))
 
     def barrier():
         if P > 1:
@@ -312,11 +319,7 @@ def main():
             kev[i][0].record()
             ctx.gather_sum(csr, x, None, out=y)
             kev[i][1].record()
-            dist.all_to_all_single(recv, y)
-            blocks = recv.view(P, n_local, D)
-            ctx.add(blocks[0], blocks[1], out=v)
-            for j in range(2, P):
-                ctx.add(v, blocks[j], out=v)
+            exchange_and_sum(dist, y, recv, v, P, n_local, D, lambda a, b, o: ctx.add(a, b, out=o))
     e1.record()
     barrier()
     torch.cuda.profiler.stop()
