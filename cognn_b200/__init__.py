@@ -216,6 +216,18 @@ class Context:
                                             s0.numel(), f))
         return out
 
+    # -- 2PC-residual stand-ins (ideal functionality, not secure) ------------------------------------------------
+    def ideal_relu(self, a0, a1):
+        out = self.torch.empty_like(a0)
+        self.check(self.lib.cgb_ideal_relu(self.handle, _ptr(self._u64(a0)), _ptr(self._u64(a1)), _ptr(out), a0.numel()))
+        return out
+
+    def ideal_relu_grad(self, g0, g1, z0, z1):
+        out = self.torch.empty_like(g0)
+        self.check(self.lib.cgb_ideal_relu_grad(self.handle, _ptr(self._u64(g0)), _ptr(self._u64(g1)), _ptr(self._u64(z0)),
+                                                _ptr(self._u64(z1)), _ptr(out), g0.numel()))
+        return out
+
     # -- (4) PRG -----------------------------------------------------------------------------------------------
     def prg_fill(self, key, stream, word_offset, n_words, out=None):
         if out is None:

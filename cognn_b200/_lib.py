@@ -67,6 +67,8 @@ SIGNATURES = {
     "cgb_open_decode": (C.c_int, [ctx_p, u64p, u64p, C.c_void_p, C.c_uint64, C.c_int]),
     "cgb_prg_fill": (C.c_int, [ctx_p, C.POINTER(C.c_uint32), C.c_uint64, C.c_uint64, u64p, C.c_uint64]),
     "cgb_prg_mask_sub": (C.c_int, [ctx_p, C.POINTER(C.c_uint32), C.c_uint64, C.c_uint64, u64p, u64p, C.c_uint64]),
+    "cgb_ideal_relu": (C.c_int, [ctx_p, u64p, u64p, u64p, C.c_uint64]),
+    "cgb_ideal_relu_grad": (C.c_int, [ctx_p, u64p, u64p, u64p, u64p, u64p, C.c_uint64]),
     "cgb_host_gather_sum": (C.c_int, [ctx_p, csr_p, u64p, u64p, u64p, C.c_uint32]),
 }
 

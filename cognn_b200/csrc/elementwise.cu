@@ -130,6 +130,17 @@ __global__ void __launch_bounds__(EW_THREADS) decode_kernel(const u64* __restric
         out[i] = decode_fixed(s0[i] + (s1 ? s1[i] : 0ull), f);
 }
 
+// 2PC-RESIDUAL stand-ins (ideal functionality on reconstructed values; NOT secure, see the header)
+__global__ void __launch_bounds__(EW_THREADS) ideal_relu_kernel(const u64* a0, const u64* a1, const u64* z0, const u64* z1,
+                                                               u64* out, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u64 v = a0[i] + a1[i];
+        const u64 gate = z0 ? z0[i] + z1[i] : v;
+        out[i] = (long long)gate > 0 ? v : 0ull;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -188,6 +199,23 @@ int cgb_transpose(cgb_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint32_t 
     CGB_REQUIRE(ctx, grid.y <= 65535, "cgb_transpose: too many rows (max 2097120)");
     transpose_kernel<<<grid, 256, 0, ctx->stream>>>((const u64*)d_in, (u64*)d_out, rows, cols);
     CGB_CHECK_LAUNCH(ctx, "transpose_kernel");
+    return CGB_OK;
+}
+int cgb_ideal_relu(cgb_ctx* ctx, const uint64_t* d_a0, const uint64_t* d_a1, uint64_t* d_out, uint64_t n) {
+    CGB_REQUIRE(ctx, (d_a0 && d_a1 && d_out) || n == 0, "cgb_ideal_relu: null argument");
+    if (n == 0) return CGB_OK;
+    ideal_relu_kernel<<<ew_blocks(ctx, n), EW_THREADS, 0, ctx->stream>>>((const u64*)d_a0, (const u64*)d_a1, nullptr, nullptr,
+                                                                        (u64*)d_out, n);
+    CGB_CHECK_LAUNCH(ctx, "ideal_relu_kernel");
+    return CGB_OK;
+}
+int cgb_ideal_relu_grad(cgb_ctx* ctx, const uint64_t* d_g0, const uint64_t* d_g1, const uint64_t* d_z0,
+                        const uint64_t* d_z1, uint64_t* d_out, uint64_t n) {
+    CGB_REQUIRE(ctx, (d_g0 && d_g1 && d_z0 && d_z1 && d_out) || n == 0, "cgb_ideal_relu_grad: null argument");
+    if (n == 0) return CGB_OK;
+    ideal_relu_kernel<<<ew_blocks(ctx, n), EW_THREADS, 0, ctx->stream>>>((const u64*)d_g0, (const u64*)d_g1, (const u64*)d_z0,
+                                                                        (const u64*)d_z1, (u64*)d_out, n);
+    CGB_CHECK_LAUNCH(ctx, "ideal_relu_kernel");
     return CGB_OK;
 }
 int cgb_encode(cgb_ctx* ctx, const double* d_x, uint64_t* d_out, uint64_t n, int f) {

@@ -206,6 +206,19 @@ struct SSGcnEngine::Impl {
     std::vector<uint32_t> n_of;  // vertices per party (global knowledge: the partition file is public)
     uint64_t lr_fixed = 0;
 
+    // per-phase wall time under the reference's print_duration tags (ssk.h:745,765,802,808,822,856,881,897); only when
+    // CGB_ENGINE_PROFILE is set, because it synchronises the stream at every tick
+    bool profile = getenv("CGB_ENGINE_PROFILE") != nullptr;
+    std::map<std::string, double> phase_s;
+    std::chrono::high_resolution_clock::time_point last_tick;
+    void tick(const char* tag) {
+        if (!profile) return;
+        cgb_ctx_sync(ctx);
+        auto now = std::chrono::high_resolution_clock::now();
+        if (tag) phase_s[tag] += std::chrono::duration<double>(now - last_tick).count();
+        last_tick = now;
+    }
+
     int q(int p) const { return (p + 1) % T; }
     Side* side(int owner, int share) {
         auto& m = share == 0 ? own : hlp;
@@ -470,7 +483,9 @@ struct SSGcnEngine::Impl {
     // helper's new share is a PRG stream both know from the dealer, the owner's is fn(x) - PRG.
     typedef void (*ResidualFn)(Impl&, int owner, const std::vector<std::vector<uint64_t>>& in,
                                std::vector<std::vector<uint64_t>>& out);
-    void residual(uint64_t it, ResidualFn fn, int n_in, int n_out, DMat* (*in_sel)(Side&, int), DMat* (*out_sel)(Side&, int)) {
+    double seconds_residual_host = 0;
+    void residual(uint64_t it, ResidualFn fn, int n_in, int n_out, DMat* (*in_sel)(Side&, int), DMat* (*out_sel)(Side&, int),
+                  int dev_kind = 0) {
         for_sides([&](Side& s) {
             size_t total = 0;
             for (int i = 0; i < n_in; ++i) total += in_sel(s, i)->n();
@@ -490,7 +505,20 @@ struct SSGcnEngine::Impl {
         comm->exchange();
         for_sides([&](Side& s) {
             std::vector<std::pair<uint32_t, uint32_t>> shapes;
-            if (s.share == 0) {
+            if (s.share == 0 && dev_kind != 0) {
+                // exact integer stand-ins evaluated on the device (cgb_ideal_relu*): no host round trip
+                DMat* o = out_sel(s, 0);
+                DMat* a = in_sel(s, 0);
+                s.res_plain.resize(ctx, a->rows, a->cols);
+                if (dev_kind == 1)
+                    ck(ctx, cgb_ideal_relu(ctx, a->p, s.res_in.p, s.res_plain.p, a->n()), "cgb_ideal_relu");
+                else
+                    ck(ctx, cgb_ideal_relu_grad(ctx, a->p, s.res_in.p, in_sel(s, 1)->p, s.res_in.p + a->n(), s.res_plain.p, a->n()),
+                       "cgb_ideal_relu_grad");
+                o->resize(ctx, a->rows, a->cols);
+                ck(ctx, cgb_prg_mask_sub(ctx, key, stream_id(K_RESHARE, it, s.owner, 0), 0, s.res_plain.p, o->p, o->n()), "reshare");
+            } else if (s.share == 0) {
+                auto th0 = std::chrono::high_resolution_clock::now();
                 std::vector<std::vector<uint64_t>> in(n_in), out;
                 size_t off = 0;
                 std::vector<uint64_t> peer(s.res_in.n());
@@ -513,6 +541,7 @@ struct SSGcnEngine::Impl {
                     ck(ctx, cgb_prg_mask_sub(ctx, key, stream_id(K_RESHARE, it, s.owner, k), 0, s.res_plain.p, o->p, o->n()), "reshare");
                     ck(ctx, cgb_ctx_sync(ctx), "sync");  // out[k] is a pageable host vector about to die
                 }
+                seconds_residual_host += std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - th0).count();
             } else {
                 for (int k = 0; k < n_out; ++k) {
                     DMat* o = out_sel(s, k);
@@ -647,6 +676,10 @@ SSGcnEngine::SSGcnEngine(Comm* comm, const GNNConfig& cfg, int f, const uint32_t
 SSGcnEngine::~SSGcnEngine() {
     if (!impl_) return;
     cgb_ctx_sync(impl_->ctx);
+    if (impl_->profile) {
+        for (auto& kv : impl_->phase_s) fprintf(stderr, "::%s took %lf seconds (all iterations)\n", kv.first.c_str(), kv.second);
+        fprintf(stderr, "::residual host stand-in took %lf seconds\n", impl_->seconds_residual_host);
+    }
     for (auto& kv : impl_->party)
         if (kv.second.csr) cgb_csr_destroy(impl_->ctx, kv.second.csr);
     delete impl_;
@@ -774,6 +807,7 @@ void SSGcnEngine::run(uint64_t n_iters) {
         auto t0 = std::chrono::high_resolution_clock::now();
         seconds_offline += std::chrono::duration<double>(t0 - t_deal).count();
         if (ph == 0) im.for_sides([&](Side& s) { s.X.copy_from(s.X_backup); });  // ssk.h:695, 938
+        im.tick(nullptr);
 
         if (ph == 0 || ph == 1) {
             // ---------------- forward layer `ph` ----------------
@@ -789,13 +823,16 @@ void SSGcnEngine::run(uint64_t n_iters) {
             im.for_sides([&](Side& s) { im.mm_finish(s, 0, s.n, Din, Dout, s.Xp); });
             if (layer != 0)  // gcn.h:243-254
                 im.rowscale_all(it, 0, [](Side& s) -> DMat& { return s.Xp; }, [](Side& s) -> DMat& { return s.Xp; });
+            im.tick("PreScatterComp");
             im.gas(it);
+            im.tick("Scatter+Gather (OM message, fused gather-sum, update exchange, adds)");
             // gcn.h:470-484: in-degree scaling ((it + 1) % 6 != 0 for the forward layers)
             im.rowscale_all(it, 1, [](Side& s) -> DMat& { return s.V; }, [](Side& s) -> DMat& { return s.V; });
+            im.tick("Gather_computation (in-degree scale)");
             im.for_sides([&](Side& s) { s.z[layer].copy_from(s.V); });
             if (layer == 0) {  // gcn.h:546-558: ReLU -- 2PC-RESIDUAL
                 im.for_sides([&](Side& s) { s.X.resize(ctx, s.n, Dout); });
-                im.residual(it, fn_relu, 1, 1, sel_V, sel_X);
+                im.residual(it, fn_relu, 1, 1, sel_V, sel_X, 1);
             } else {  // gcn.h:559-642: softmax, p - y -- 2PC-RESIDUAL; then p is opened to the owner (gcn.h:604)
                 im.for_sides([&](Side& s) {
                     s.X.resize(ctx, s.n, Dout);
@@ -864,9 +901,12 @@ void SSGcnEngine::run(uint64_t n_iters) {
             const int layer = ph == 3 ? 1 : 0;
             const uint32_t Din = layer == 0 ? F : H, Dout = layer == 0 ? H : C;
             im.rowscale_all(it, 0, [](Side& s) -> DMat& { return s.X; }, [](Side& s) -> DMat& { return s.Xp; });
+            im.tick("PreScatterComp");
             im.gas(it);
+            im.tick("Scatter+Gather (OM message, fused gather-sum, update exchange, adds)");
             if ((it + 1) % 6 != 0)  // gcn.h:470: no in-degree scaling on the last iteration of the epoch
                 im.rowscale_all(it, 1, [](Side& s) -> DMat& { return s.V; }, [](Side& s) -> DMat& { return s.V; });
+            im.tick("Gather_computation (in-degree scale)");
             im.for_sides([&](Side& s) {
                 im.mm_prepare(s, it, 1, s.h_t[layer], s.V);  // d = h_t * v
                 im.mm_post(s, 1);
@@ -882,11 +922,14 @@ void SSGcnEngine::run(uint64_t n_iters) {
                 if (layer == 1) s.X.copy_from(s.g);  // dstVec.swap(g) (gcn.h:684)
                 else s.X.copy_from(s.V);             // first layer: g is empty in the reference; never used again
             });
+            im.tick("Apply_computation");
             im.weight_average(it, layer);
+            im.tick("Apply_computation (weight averaging)");
         } else {
             // ---------------- ph == 4: ReLU' mask, first layer so no further matmul (gcn.h:702-708) -- 2PC-RESIDUAL ---
-            im.residual(it, fn_relu_grad, 2, 1, sel_Xz0, sel_X);
+            im.residual(it, fn_relu_grad, 2, 1, sel_Xz0, sel_X, 2);
         }
+        im.tick("Apply_computation");
         ck(ctx, cgb_ctx_sync(ctx), "sync");
         const double dt = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
         seconds_online += dt;

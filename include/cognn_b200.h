@@ -148,6 +148,16 @@ int cgb_prg_fill(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, uint64_t 
 int cgb_prg_mask_sub(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, uint64_t word_offset,
                      const uint64_t* d_in, uint64_t* d_out, uint64_t n_words);
 
+/* ---- 2PC-RESIDUAL stand-ins (IDEAL FUNCTIONALITY, NOT SECURE) ------------------------------------------------- */
+/* sci::twoPartyGCNRelu (gcn.h:549) and the ReLU' mask of sci::twoPartyGCNBackwardNNWithoutAH (gcn.h:705) stay on the
+ * reference's MPC backend.  So that an epoch can run end to end, the engine evaluates them on the RECONSTRUCTED value
+ * after the helper has sent its share to the owner -- a stand-in for the 2PC, exact integer arithmetic:
+ *   relu:      out = (int64)(a0+a1) > 0 ? a0+a1 : 0
+ *   relu_grad: out = (int64)(z0+z1) > 0 ? g0+g1 : 0                                                              */
+int cgb_ideal_relu(cgb_ctx* ctx, const uint64_t* d_a0, const uint64_t* d_a1, uint64_t* d_out, uint64_t n);
+int cgb_ideal_relu_grad(cgb_ctx* ctx, const uint64_t* d_g0, const uint64_t* d_g1, const uint64_t* d_z0,
+                        const uint64_t* d_z1, uint64_t* d_out, uint64_t n);
+
 /* ---- host-buffer entry point (what a CoGNN operator holding std::vector data calls) ------------------------ */
 /* One gather-sum step with HOST share rows: H2D of x (and delta if given), kernel, D2H of y,
  * synchronises.  h_x / h_y should be pinned (cgb_host_alloc) for full PCIe rate.  The CSR stays device resident.  bench.py's `e2e` times this. */

@@ -114,3 +114,18 @@ def test_prg_matches_openssl_golden_and_oracle(cgb, oracle):
         x = rand_u64(np.random.default_rng(n), n)
         assert np.array_equal(to_np(cgb.prg_mask_sub(key, 0x1234567890, off, to_dev(x))), x - want)
     assert cgb.prg_fill(key, 1, 0, 0).numel() == 0
+
+
+def test_ideal_functionality_standins(cgb):
+    """2PC-residual stand-ins (not secure): exact integer ReLU / ReLU' on reconstructed values, as oracle/epoch.py."""
+    rng = np.random.default_rng(5)
+    n = 5001
+    v = (rng.normal(size=n) * 1000).astype(np.int64).astype(np.uint64)
+    z = (rng.normal(size=n) * 1000).astype(np.int64).astype(np.uint64)
+    v[:3] = [0, 1, np.uint64(2**64 - 1)]
+    a1, z1 = rand_u64(rng, n), rand_u64(rng, n)
+    a0, z0 = v - a1, z - z1
+    got = to_np(cgb.ideal_relu(to_dev(a0), to_dev(a1)))
+    assert np.array_equal(got, np.where(v.astype(np.int64) > 0, v, np.uint64(0)))
+    got = to_np(cgb.ideal_relu_grad(to_dev(a0), to_dev(a1), to_dev(z0), to_dev(z1)))
+    assert np.array_equal(got, np.where(z.astype(np.int64) > 0, v, np.uint64(0)))
