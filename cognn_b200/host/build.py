@@ -32,5 +32,21 @@ def build(force=False):
     return LIB
 
 
+DEMO = os.path.join(PKG, "shim_demo")
+
+
+def build_shim_demo(force=False):
+    """tests/shim_demo.cpp against the header-only shim (cognn_b200/host/shim/cognn_shim.h) and libcognn_b200.so."""
+    src = os.path.join(PKG, "..", "tests", "shim_demo.cpp")
+    deps = [src, os.path.join(HERE, "shim", "cognn_shim.h"), os.path.join(PKG, "..", "include", "cognn_b200.h")]
+    if not force and os.path.exists(DEMO) and all(os.path.getmtime(DEMO) >= os.path.getmtime(d) for d in deps):
+        return DEMO
+    cmd = [_cxx(), "-O2", "-g", "-std=c++17", "-Wall", "-pthread", "-o", DEMO, src, "-L" + PKG, "-l:libcognn_b200.so",
+           "-Wl,-rpath,$ORIGIN", "-L/usr/local/cuda/lib64", "-lcudart"]
+    subprocess.check_call(cmd)
+    return DEMO
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(build_shim_demo(force="--force" in sys.argv))

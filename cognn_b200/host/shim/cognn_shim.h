@@ -1,0 +1,583 @@
+// cognn_shim.h -- header-only C++17 binding of the reference's "level B" primitive API onto the C ABI of
+// include/cognn_b200.h.  It re-creates the NAMES AND SIGNATURES the CoGNN operators call but /root/reference does
+// not define (they live in the absent Task-Worker tree: SCIHarness.h, ObliviousMapper.h, SecureAggregation.h,
+// TaskUtil.h), so that algo_kernels/vertex_centric/optimize-gcn/gcn.h-shaped operator code compiles against it:
+//
+//   typedefs ShareVec / ShareTensor / ShareVecVec / DoubleTensor / PosVec, transpose(), toShareVec()   task.h:237-272
+//   GNNParam::getGNNParam().readConfig()                                                               task.h:78-170
+//   sci::ALICE / sci::BOB, sci::twoPartyGCNMatMul            gcn.h:233,665,671,710
+//   sci::twoPartyGCNVectorScale                              gcn.h:247,476
+//   sci::twoPartyGCNMatrixScale / twoPartyGCNApplyGradient   gcn.h:676,678,723,730,764
+//   sci::twoPartyGCNCondVectorAddition                       gcn.h:456
+//   sci::getPlainShareVecVec                                 gcn.h:604
+//   prefix_network_aggregate(..., AggregationOp::ADD_AGG, ...)          gcn.h:328
+//   client_oblivious_mapper_online / server_oblivious_mapper_online     ssk.h:752,760,818,848 / 1011,1016,1057,1075
+//   CryptoUtil::intoShares / encodeDoubleAsFixedPoint / mergeShareAsDouble   gcn.h:70,80,96,220
+//
+// Calling convention kept from the reference: caller-owned STL containers by reference, the callee resizes outputs,
+// in/out aliasing is allowed (results are computed out of place), errors are fatal (printf + exit(-1), ssk.h:794-797).
+// The two parties of a call run the same sequence of primitives (as ALICE and BOB threads do in ssk.h:702-704 /
+// 926-928); a per-owner operation counter keeps their dealer PRG streams aligned.
+//
+// NOT provided (2PC-RESIDUAL, stays on the reference's SCI/OT backend): sci::twoPartyGCNRelu,
+// sci::twoPartyGCNForwardNNPredictionWithoutWeight, sci::twoPartyGCNBackwardNNWithoutAH.
+// This is the API-faithful path: every call moves host vectors to the GPU and back.  The device-resident fast path is
+// the engine (engine.h); both produce the same reconstructed values.
+#pragma once
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <deque>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../../include/cognn_b200.h"
+
+#ifndef SCALER_BIT_LENGTH
+#define SCALER_BIT_LENGTH CGB_SCALER_BITS
+#endif
+
+typedef std::vector<uint64_t> ShareVec;
+typedef std::vector<std::vector<double>> DoubleTensor;
+typedef std::vector<std::vector<uint64_t>> ShareTensor;
+typedef std::vector<ShareTensor> ShareTensorVec;
+typedef std::vector<ShareVec> ShareVecVec;
+struct PosVec {
+    std::vector<uint64_t> pos;
+};
+
+inline ShareTensor transpose(const ShareTensor& st) {
+    if (st.empty()) return ShareTensor();
+    ShareTensor out(st[0].size(), ShareVec(st.size()));
+    for (size_t i = 0; i < st.size(); ++i)
+        for (size_t j = 0; j < st[i].size(); ++j) out[j][i] = st[i][j];
+    return out;
+}
+inline ShareVec toShareVec(int hotIndex, int vecSize) {  // one-hot label in fixed point (gcn.h:575)
+    ShareVec v(vecSize, 0);
+    if (hotIndex >= 0 && hotIndex < vecSize) v[hotIndex] = 1ull << SCALER_BIT_LENGTH;
+    return v;
+}
+
+class GNNParam {  // task.h:78-170
+    GNNParam() {}
+
+public:
+    int num_layers = 2, num_labels = 0, input_dim = 0, hidden_dim = 0, num_samples = 0, num_edges = 0;
+    double learning_rate = 0, train_ratio = 0, val_ratio = 0, test_ratio = 0;
+    static GNNParam& getGNNParam() {
+        static GNNParam instance;
+        return instance;
+    }
+    void readConfig(const std::string& file_name) {
+        std::ifstream fin(file_name);
+        if (!fin.is_open()) {
+            std::cerr << "Failed to open the file: " << file_name << std::endl;
+            return;
+        }
+        std::string param;
+        char colon;
+        while (fin >> param >> colon) {
+            if (colon != ':') {
+                std::cerr << "Invalid format: expected a colon after " << param << std::endl;
+                break;
+            }
+            if (param == "num_layers") fin >> num_layers;
+            else if (param == "num_labels") fin >> num_labels;
+            else if (param == "input_dim") fin >> input_dim;
+            else if (param == "hidden_dim") fin >> hidden_dim;
+            else if (param == "num_samples") fin >> num_samples;
+            else if (param == "num_edges") fin >> num_edges;
+            else if (param == "learning_rate") fin >> learning_rate;
+            else if (param == "train_ratio") fin >> train_ratio;
+            else if (param == "val_ratio") fin >> val_ratio;
+            else if (param == "test_ratio") fin >> test_ratio;
+            else {
+                std::cerr << "Unknown parameter: " << param << std::endl;
+                break;
+            }
+        }
+    }
+};
+
+enum class AggregationOp { ADD_AGG, MIN_AGG, MAX_AGG };
+
+namespace cognn_shim {
+
+[[noreturn]] inline void fatal(const char* what, const char* detail) {
+    printf("%s: %s\n", what, detail ? detail : "");  // the reference's error behaviour (ssk.h:794-797)
+    exit(-1);
+}
+
+// message plane between the two threads / processes of one (owner, helper) pair
+struct Channel {
+    virtual ~Channel() {}
+    virtual void send(const std::vector<uint64_t>& v) = 0;
+    virtual void recv(std::vector<uint64_t>& v) = 0;  // whole message
+};
+
+// both ends in one process (ALICE and BOB threads, like the reference's single-host runs with -c 0)
+class InProcPipe {
+public:
+    struct End : Channel {
+        InProcPipe* p;
+        int side;
+        void send(const std::vector<uint64_t>& v) override {
+            std::lock_guard<std::mutex> l(p->m);
+            p->q[side].push_back(v);
+            p->cv.notify_all();
+        }
+        void recv(std::vector<uint64_t>& v) override {
+            std::unique_lock<std::mutex> l(p->m);
+            p->cv.wait(l, [&] { return !p->q[1 - side].empty(); });
+            v = std::move(p->q[1 - side].front());
+            p->q[1 - side].pop_front();
+        }
+    };
+    InProcPipe() {
+        a.p = b.p = this;
+        a.side = 0;
+        b.side = 1;
+    }
+    End a, b;
+
+private:
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<std::vector<uint64_t>> q[2];
+};
+
+// dealer PRG stream ids: same layout as the engine (DESIGN.md "Randomness"); `op` plays the role of the iteration
+enum Kind : uint64_t { K_MM_U0 = 5, K_MM_U1, K_MM_V0, K_MM_V1, K_MM_Z0, K_RM_A0, K_RM_A1, K_RM_B0, K_RM_B1, K_RM_C0,
+                       K_OM_R = 32, K_OM_S = 33, K_SPLIT = 34 };
+inline uint64_t stream_id(uint64_t kind, uint64_t op, uint64_t owner, uint64_t sub) {
+    return (kind << 48) | (op << 16) | (owner << 8) | sub;
+}
+
+class Runtime {
+public:
+    Runtime(int tileIndex, int tileNum, int device, const uint32_t key_[8]) : tileIndex(tileIndex), tileNum(tileNum), device(device) {
+        for (int i = 0; i < 8; ++i) key[i] = key_[i];
+    }
+    ~Runtime() {
+        for (auto& kv : ctxs) cgb_ctx_destroy(kv.second);
+    }
+    // the thread that will issue primitives for (coTid, party) registers its channel to the matching thread of coTid
+    void connect(uint64_t coTid, int party, Channel* ch) { chans[{coTid, party}] = ch; }
+    static Runtime*& current_ptr() {
+        static thread_local Runtime* rt = nullptr;
+        return rt;
+    }
+    static void bind_thread(Runtime* rt) { current_ptr() = rt; }
+    static Runtime& current() {
+        if (!current_ptr()) fatal("cognn_shim", "no Runtime bound to this thread (Runtime::bind_thread)");
+        return *current_ptr();
+    }
+    cgb_ctx* ctx(uint64_t coTid, int party) {
+        std::lock_guard<std::mutex> l(mu);
+        auto key_ = std::make_pair(coTid, party);
+        auto it = ctxs.find(key_);
+        if (it != ctxs.end()) return it->second;
+        cgb_ctx* c = nullptr;
+        if (cgb_ctx_create(device, &c) != CGB_OK) fatal("cgb_ctx_create", cgb_last_error(nullptr));
+        ctxs[key_] = c;
+        return c;
+    }
+    Channel& chan(uint64_t coTid, int party) {
+        auto it = chans.find({coTid, party});
+        if (it == chans.end()) fatal("cognn_shim", "no channel connected for this (coTid, party)");
+        return *it->second;
+    }
+    uint64_t next_op(uint64_t owner, int share) {
+        std::lock_guard<std::mutex> l(mu);
+        return ops[{owner, share}]++;
+    }
+    int tileIndex, tileNum, device;
+    uint32_t key[8];
+
+private:
+    std::mutex mu;
+    std::map<std::pair<uint64_t, int>, cgb_ctx*> ctxs;
+    std::map<std::pair<uint64_t, int>, Channel*> chans;
+    std::map<std::pair<uint64_t, int>, uint64_t> ops;
+};
+
+// ---- small RAII device buffer + host <-> device helpers -------------------------------------------------------------
+struct Dev {
+    cgb_ctx* c;
+    uint64_t* p = nullptr;
+    size_t n = 0;
+    Dev(cgb_ctx* c, size_t n) : c(c), n(n) {
+        void* q = nullptr;
+        if (cgb_malloc(c, (n ? n : 1) * 8, &q) != CGB_OK) fatal("cgb_malloc", cgb_last_error(c));
+        p = (uint64_t*)q;
+    }
+    Dev(const Dev&) = delete;
+    ~Dev() { cgb_free(c, p); }
+    void up(const std::vector<uint64_t>& h) {
+        if (h.size() != n) fatal("cognn_shim", "upload size mismatch");
+        if (n && cgb_h2d(c, p, h.data(), n * 8) != CGB_OK) fatal("cgb_h2d", cgb_last_error(c));
+        cgb_ctx_sync(c);
+    }
+    std::vector<uint64_t> down() const {
+        std::vector<uint64_t> h(n);
+        if (n && cgb_d2h(c, h.data(), p, n * 8) != CGB_OK) fatal("cgb_d2h", cgb_last_error(c));
+        cgb_ctx_sync(c);
+        return h;
+    }
+};
+inline void ok(cgb_ctx* c, int rc, const char* what) {
+    if (rc != CGB_OK) fatal(what, cgb_last_error(c));
+}
+inline std::vector<uint64_t> flatten(const ShareVecVec& m, size_t* rows, size_t* cols) {
+    *rows = m.size();
+    *cols = m.empty() ? 0 : m[0].size();
+    std::vector<uint64_t> f(*rows * *cols);
+    for (size_t i = 0; i < *rows; ++i) {
+        if (m[i].size() != *cols) fatal("cognn_shim", "ragged share matrix");
+        for (size_t j = 0; j < *cols; ++j) f[i * *cols + j] = m[i][j];
+    }
+    return f;
+}
+inline void unflatten(const std::vector<uint64_t>& f, size_t rows, size_t cols, ShareVecVec& out) {
+    ShareVecVec r(rows, ShareVec(cols));
+    for (size_t i = 0; i < rows; ++i)
+        for (size_t j = 0; j < cols; ++j) r[i][j] = f[i * cols + j];
+    out.swap(r);  // out may alias an input: assign only at the end
+}
+inline void prg(cgb_ctx* c, const uint32_t key[8], uint64_t sid, Dev& d) { ok(c, cgb_prg_fill(c, key, sid, 0, d.p, d.n), "cgb_prg_fill"); }
+// exchange: send mine, receive the peer's message of the same size, return it on the device
+inline void swap_msgs(Channel& ch, const Dev& mine, Dev& peer) {
+    ch.send(mine.down());
+    std::vector<uint64_t> v;
+    ch.recv(v);
+    peer.up(v);
+}
+struct Call {  // common prologue of every two-party primitive
+    Runtime& rt;
+    int share;
+    uint64_t owner, op;
+    cgb_ctx* c;
+    Channel& ch;
+    Call(uint64_t coTid, int party)
+        : rt(Runtime::current()), share(party == 1 ? 0 : 1), owner(party == 1 ? (uint64_t)rt.tileIndex : coTid),
+          op(rt.next_op(owner, share)), c(rt.ctx(coTid, party)), ch(rt.chan(coTid, party)) {
+        if (party != 1 && party != 2) fatal("cognn_shim", "party must be sci::ALICE (1) or sci::BOB (2)");
+    }
+};
+
+}  // namespace cognn_shim
+
+// ---------------------------------------------------------------------------------------------------------------------
+class CryptoUtil {
+public:
+    static uint64_t encodeDoubleAsFixedPoint(double x) { return (uint64_t)(int64_t)(x * (double)(1ull << SCALER_BIT_LENGTH)); }
+    static double decodeFixedPointAsDouble(uint64_t v) { return (double)(int64_t)v / (double)(1ull << SCALER_BIT_LENGTH); }
+    // s1 = next word of this thread's split stream, s0 = enc(x) - s1 (DESIGN.md "Frozen semantics")
+    static void intoShares(double x, uint64_t& s0, uint64_t& s1) {
+        static thread_local std::vector<uint64_t> pool;
+        static thread_local size_t pos = 0;
+        static thread_local uint64_t refill = 0;
+        if (pos == pool.size()) {
+            auto& rt = cognn_shim::Runtime::current();
+            cgb_ctx* c = rt.ctx((uint64_t)-1, 1);
+            cognn_shim::Dev d(c, 1 << 16);
+            cognn_shim::ok(c, cgb_prg_fill(c, rt.key, cognn_shim::stream_id(cognn_shim::K_SPLIT, refill, rt.tileIndex, 0),
+                                           0, d.p, d.n), "cgb_prg_fill");
+            pool = d.down();
+            pos = 0;
+            ++refill;
+        }
+        s1 = pool[pos++];
+        s0 = encodeDoubleAsFixedPoint(x) - s1;
+    }
+    static double mergeShareAsDouble(uint64_t s0, uint64_t s1) { return decodeFixedPointAsDouble(s0 + s1); }
+};
+
+namespace sci {
+
+const int ALICE = 1;
+const int BOB = 2;
+
+// C = trunc(A * B) on shares (Beaver triple from the dealer PRG; one message each way)
+inline void twoPartyGCNMatMul(const ShareVecVec& A, const ShareTensor& B, ShareVecVec& C, uint64_t coTid, int party) {
+    using namespace cognn_shim;
+    Call k(coTid, party);
+    size_t M, K, K2, N;
+    std::vector<uint64_t> a = flatten(A, &M, &K), b = flatten(B, &K2, &N);
+    if (K != K2) fatal("twoPartyGCNMatMul", "inner dimensions differ");
+    cgb_ctx* c = k.c;
+    Dev dA(c, M * K), dB(c, K * N), U(c, M * K), V(c, K * N), Z(c, M * N), mine(c, M * K + K * N), peer(c, M * K + K * N), out(c, M * N);
+    dA.up(a);
+    dB.up(b);
+    if (k.share == 0) {
+        prg(c, k.rt.key, stream_id(K_MM_U0, k.op, k.owner, 0), U);
+        prg(c, k.rt.key, stream_id(K_MM_V0, k.op, k.owner, 0), V);
+        prg(c, k.rt.key, stream_id(K_MM_Z0, k.op, k.owner, 0), Z);
+    } else {  // dealer emulation: Z1 = (U0+U1)(V0+V1) - Z0
+        Dev U0(c, M * K), V0(c, K * N), Z0(c, M * N);
+        prg(c, k.rt.key, stream_id(K_MM_U0, k.op, k.owner, 0), U0);
+        prg(c, k.rt.key, stream_id(K_MM_V0, k.op, k.owner, 0), V0);
+        prg(c, k.rt.key, stream_id(K_MM_Z0, k.op, k.owner, 0), Z0);
+        prg(c, k.rt.key, stream_id(K_MM_U1, k.op, k.owner, 0), U);
+        prg(c, k.rt.key, stream_id(K_MM_V1, k.op, k.owner, 0), V);
+        ok(c, cgb_add(c, U0.p, U.p, U0.p, U0.n), "cgb_add");
+        ok(c, cgb_add(c, V0.p, V.p, V0.p, V0.n), "cgb_add");
+        ok(c, cgb_matmul(c, U0.p, V0.p, Z.p, M, K, N, 0, 0), "cgb_matmul");
+        ok(c, cgb_sub(c, Z.p, Z0.p, Z.p, Z.n), "cgb_sub");
+        cgb_ctx_sync(c);
+    }
+    ok(c, cgb_sub(c, dA.p, U.p, mine.p, M * K), "cgb_sub");
+    ok(c, cgb_sub(c, dB.p, V.p, mine.p + M * K, K * N), "cgb_sub");
+    swap_msgs(k.ch, mine, peer);
+    ok(c, cgb_add(c, mine.p, peer.p, mine.p, mine.n), "cgb_add");
+    ok(c, cgb_beaver_matmul_finish(c, mine.p, mine.p + M * K, U.p, V.p, Z.p, out.p, M, K, N, k.share, SCALER_BIT_LENGTH),
+       "cgb_beaver_matmul_finish");
+    unflatten(out.down(), M, N, C);
+}
+
+namespace detail {
+// out = [trunc](x * s[row]) with s private to ALICE (BOB's scaler argument is ignored, it passes zeros: ssk.h:985-994)
+inline void rowmul(const ShareVecVec& in, const std::vector<uint64_t>& scaler, ShareVecVec& out, uint64_t coTid, int party, int f) {
+    using namespace cognn_shim;
+    Call k(coTid, party);
+    size_t rows, D;
+    std::vector<uint64_t> x = flatten(in, &rows, &D);
+    if (scaler.size() != rows) fatal("twoPartyGCNVectorScale", "one scaler per row expected");
+    cgb_ctx* c = k.c;
+    Dev dx(c, rows * D), a(c, rows * D), b(c, rows), cc(c, rows * D), mine(c, rows * D + rows), peer(c, rows * D + rows), res(c, rows * D);
+    dx.up(x);
+    if (k.share == 0) {
+        prg(c, k.rt.key, stream_id(K_RM_A0, k.op, k.owner, 0), a);
+        prg(c, k.rt.key, stream_id(K_RM_B0, k.op, k.owner, 0), b);
+        prg(c, k.rt.key, stream_id(K_RM_C0, k.op, k.owner, 0), cc);
+    } else {
+        Dev a0(c, rows * D), b0(c, rows), c0(c, rows * D), zm(c, rows * D), zv(c, rows);
+        prg(c, k.rt.key, stream_id(K_RM_A0, k.op, k.owner, 0), a0);
+        prg(c, k.rt.key, stream_id(K_RM_B0, k.op, k.owner, 0), b0);
+        prg(c, k.rt.key, stream_id(K_RM_C0, k.op, k.owner, 0), c0);
+        prg(c, k.rt.key, stream_id(K_RM_A1, k.op, k.owner, 0), a);
+        prg(c, k.rt.key, stream_id(K_RM_B1, k.op, k.owner, 0), b);
+        ok(c, cgb_add(c, a0.p, a.p, a0.p, a0.n), "cgb_add");
+        ok(c, cgb_add(c, b0.p, b.p, b0.p, b0.n), "cgb_add");
+        ok(c, cgb_memset(c, zm.p, 0, zm.n * 8), "memset");
+        ok(c, cgb_memset(c, zv.p, 0, zv.n * 8), "memset");
+        ok(c, cgb_sub(c, zm.p, c0.p, c0.p, c0.n), "cgb_sub");  // -c0
+        ok(c, cgb_rowmul_beaver_finish(c, a0.p, b0.p, zm.p, zv.p, c0.p, cc.p, rows, D, 0, -1), "rowmul(dealer)");
+        cgb_ctx_sync(c);
+    }
+    ok(c, cgb_sub(c, dx.p, a.p, mine.p, rows * D), "cgb_sub");
+    if (k.share == 0) {
+        Dev s(c, rows);
+        s.up(scaler);
+        ok(c, cgb_sub(c, s.p, b.p, mine.p + rows * D, rows), "cgb_sub");
+        cgb_ctx_sync(c);
+    } else {
+        ok(c, cgb_memset(c, mine.p + rows * D, 0, rows * 8), "memset");
+        ok(c, cgb_sub(c, mine.p + rows * D, b.p, mine.p + rows * D, rows), "cgb_sub");
+    }
+    swap_msgs(k.ch, mine, peer);
+    ok(c, cgb_add(c, mine.p, peer.p, mine.p, mine.n), "cgb_add");
+    ok(c, cgb_rowmul_beaver_finish(c, mine.p, mine.p + rows * D, a.p, b.p, cc.p, res.p, rows, D, k.share, f), "cgb_rowmul_beaver_finish");
+    unflatten(res.down(), rows, D, out);
+}
+}  // namespace detail
+
+inline void twoPartyGCNVectorScale(const ShareVecVec& in, const std::vector<uint64_t>& scaler, ShareVecVec& out, bool /*isSigned*/,
+                                   uint64_t coTid, int party) {
+    detail::rowmul(in, scaler, out, coTid, party, SCALER_BIT_LENGTH);
+}
+
+// out = v + (cond ? u : 0); cond is private to ALICE (BOB passes all-true, ssk.h:1124-1126): MUX via a Beaver product
+inline void twoPartyGCNCondVectorAddition(const ShareVecVec& v, const ShareVecVec& u, const std::vector<bool>& cond, ShareVecVec& out,
+                                          uint64_t coTid, int party) {
+    std::vector<uint64_t> sel(cond.size());
+    for (size_t i = 0; i < cond.size(); ++i) sel[i] = cond[i] ? 1 : 0;
+    ShareVecVec gated;
+    detail::rowmul(u, sel, gated, coTid, party, -1);
+    ShareVecVec r(v.size());
+    for (size_t i = 0; i < v.size(); ++i) {
+        r[i].resize(v[i].size());
+        for (size_t j = 0; j < v[i].size(); ++j) r[i][j] = v[i][j] + gated[i][j];
+    }
+    out.swap(r);
+}
+
+// public scalar: share-local (both parties pass the same value; gcn.h:676,764)
+inline void twoPartyGCNMatrixScale(const ShareTensor& in, uint64_t scaler, ShareTensor& out, uint64_t coTid, int party) {
+    using namespace cognn_shim;
+    auto& rt = Runtime::current();
+    cgb_ctx* c = rt.ctx(coTid, party);
+    size_t rows, cols;
+    std::vector<uint64_t> x = flatten(in, &rows, &cols);
+    Dev d(c, x.size());
+    d.up(x);
+    ok(c, cgb_scale_public(c, d.p, scaler, d.p, d.n, SCALER_BIT_LENGTH, party == ALICE ? 0 : 1), "cgb_scale_public");
+    unflatten(d.down(), rows, cols, out);
+}
+inline void twoPartyGCNApplyGradient(const ShareTensor& W, const ShareTensor& dW, uint64_t lr, ShareTensor& out, uint64_t coTid, int party) {
+    using namespace cognn_shim;
+    auto& rt = Runtime::current();
+    cgb_ctx* c = rt.ctx(coTid, party);
+    size_t rows, cols, r2, c2;
+    std::vector<uint64_t> w = flatten(W, &rows, &cols), g = flatten(dW, &r2, &c2);
+    if (rows != r2 || cols != c2) fatal("twoPartyGCNApplyGradient", "shape mismatch");
+    Dev dw(c, w.size()), dg(c, g.size());
+    dw.up(w);
+    dg.up(g);
+    ok(c, cgb_apply_gradient(c, dw.p, dg.p, lr, dw.p, dw.n, SCALER_BIT_LENGTH, party == ALICE ? 0 : 1), "cgb_apply_gradient");
+    unflatten(dw.down(), rows, cols, out);
+}
+// opening towards ALICE (gcn.h:604: the owner learns the predictions); BOB gets an empty tensor
+inline void getPlainShareVecVec(const ShareTensor& st, DoubleTensor& plain, uint64_t coTid, int party) {
+    using namespace cognn_shim;
+    auto& rt = Runtime::current();
+    Channel& ch = rt.chan(coTid, party);
+    size_t rows, cols;
+    std::vector<uint64_t> x = flatten(st, &rows, &cols);
+    if (party == BOB) {
+        ch.send(x);
+        plain.clear();
+        return;
+    }
+    std::vector<uint64_t> other;
+    ch.recv(other);
+    if (other.size() != x.size()) fatal("getPlainShareVecVec", "share size mismatch");
+    cgb_ctx* c = rt.ctx(coTid, party);
+    Dev a(c, x.size()), b(c, x.size());
+    a.up(x);
+    b.up(other);
+    void* dv = nullptr;
+    ok(c, cgb_malloc(c, (x.size() ? x.size() : 1) * 8, &dv), "cgb_malloc");
+    ok(c, cgb_open_decode(c, a.p, b.p, (double*)dv, x.size(), SCALER_BIT_LENGTH), "cgb_open_decode");
+    std::vector<double> h(x.size());
+    if (!h.empty()) ok(c, cgb_d2h(c, h.data(), dv, h.size() * 8), "cgb_d2h");
+    cgb_ctx_sync(c);
+    cgb_free(c, dv);
+    plain.assign(rows, std::vector<double>(cols));
+    for (size_t i = 0; i < rows; ++i)
+        for (size_t j = 0; j < cols; ++j) plain[i][j] = h[i * cols + j];
+}
+
+}  // namespace sci
+
+// ---------------------------------------------------------------------------------------------------------------------
+// OGA: group-by-destination sum over dst-sorted rows, result in the same "duplicated" layout (gcn.h:328-335).
+// ALICE passes the real dstPos, BOB passes zeros (ssk.h:1047-1048) and never learns the groups: the map is linear, so
+// BOB sends x1 - r, ALICE computes G(x0 + x1 - r) + (G r - s), BOB keeps s.
+inline ShareVecVec prefix_network_aggregate(const std::vector<uint64_t>& dstPos, const ShareVecVec& svv, AggregationOp op, uint64_t coTid,
+                                            int party, bool /*duplicate*/) {
+    using namespace cognn_shim;
+    if (op != AggregationOp::ADD_AGG) fatal("prefix_network_aggregate", "only ADD_AGG is on the GCN path");
+    Call k(coTid, party);
+    size_t E, D;
+    std::vector<uint64_t> x = flatten(svv, &E, &D);
+    cgb_ctx* c = k.c;
+    ShareVecVec result;
+    if (party == sci::BOB) {
+        Dev dx(c, E * D), m(c, E * D), s(c, E * D);
+        dx.up(x);
+        ok(c, cgb_prg_mask_sub(c, k.rt.key, stream_id(K_OM_R, k.op, k.owner, 0), 0, dx.p, m.p, m.n), "cgb_prg_mask_sub");
+        k.ch.send(m.down());
+        prg(c, k.rt.key, stream_id(K_OM_S, k.op, k.owner, 0), s);
+        unflatten(s.down(), E, D, result);
+        return result;
+    }
+    if (dstPos.size() != E) fatal("prefix_network_aggregate", "one destination per row expected");
+    std::vector<uint32_t> segptr(1, 0);
+    for (size_t e = 1; e <= E; ++e)
+        if (e == E || dstPos[e] != dstPos[e - 1]) segptr.push_back((uint32_t)e);
+    if (E == 0) segptr.assign(1, 0);
+    std::vector<uint64_t> msg;
+    k.ch.recv(msg);
+    if (msg.size() != E * D) fatal("prefix_network_aggregate", "message size mismatch");
+    Dev dx(c, E * D), m(c, E * D), r(c, E * D), s(c, E * D), gr(c, E * D), y(c, E * D);
+    void* dseg = nullptr;
+    ok(c, cgb_malloc(c, segptr.size() * 4, &dseg), "cgb_malloc");
+    ok(c, cgb_h2d(c, dseg, segptr.data(), segptr.size() * 4), "cgb_h2d");
+    dx.up(x);
+    m.up(msg);
+    prg(c, k.rt.key, stream_id(K_OM_R, k.op, k.owner, 0), r);
+    prg(c, k.rt.key, stream_id(K_OM_S, k.op, k.owner, 0), s);
+    const uint32_t n_seg = (uint32_t)segptr.size() - 1;
+    ok(c, cgb_segsum(c, (const uint32_t*)dseg, n_seg, E, r.p, gr.p, (uint32_t)D, 1), "cgb_segsum");  // dealer: G r
+    ok(c, cgb_sub(c, gr.p, s.p, gr.p, gr.n), "cgb_sub");                                              //         - s
+    ok(c, cgb_add(c, dx.p, m.p, dx.p, dx.n), "cgb_add");
+    ok(c, cgb_segsum(c, (const uint32_t*)dseg, n_seg, E, dx.p, y.p, (uint32_t)D, 1), "cgb_segsum");
+    ok(c, cgb_add(c, y.p, gr.p, y.p, y.n), "cgb_add");
+    unflatten(y.down(), E, D, result);
+    cgb_free(c, dseg);
+    return result;
+}
+
+// OM online, client side (the party that knows the positions): dst[j] = src[index of dstPos[j] in srcPos] on shares
+inline void client_oblivious_mapper_online(const std::vector<uint64_t>& srcPos, const std::vector<uint64_t>& dstPos, const ShareVecVec& srcSvv,
+                                           ShareVecVec& dstSvv, uint32_t plainNumPerOperand, uint64_t iter, uint32_t preprocessId,
+                                           uint64_t coTid, bool allowMissing = false) {
+    using namespace cognn_shim;
+    (void)iter;
+    (void)preprocessId;  // the reference keys its offline correlation by (iter, preprocessId); here by the call counter
+    Call k(coTid, sci::ALICE);
+    const size_t n_src = srcPos.size(), n_dst = dstPos.size(), D = plainNumPerOperand;
+    size_t r_, c_;
+    std::vector<uint64_t> x = flatten(srcSvv, &r_, &c_);
+    if (r_ != n_src || (n_src && c_ != D)) fatal("client_oblivious_mapper_online", "source shape mismatch");
+    std::unordered_map<uint64_t, uint32_t> first;
+    for (size_t i = 0; i < n_src; ++i) first.emplace(srcPos[i], (uint32_t)i);  // duplicated sources: first occurrence
+    std::vector<uint32_t> idx(n_dst);
+    for (size_t j = 0; j < n_dst; ++j) {
+        auto it = first.find(dstPos[j]);
+        if (it == first.end()) {
+            if (!allowMissing) fatal("client_oblivious_mapper_online", "destination position missing in source positions");
+            idx[j] = CGB_NO_ROW;
+        } else idx[j] = it->second;
+    }
+    k.ch.send(std::vector<uint64_t>{(uint64_t)n_dst});  // the server learns the output size (as in the reference's preprocessing)
+    std::vector<uint64_t> msg;
+    k.ch.recv(msg);
+    if (msg.size() != n_src * D) fatal("client_oblivious_mapper_online", "message size mismatch");
+    cgb_ctx* c = k.c;
+    Dev dx(c, n_src * D), m(c, n_src * D), r(c, n_src * D), s(c, n_dst * D), delta(c, n_dst * D), y(c, n_dst * D);
+    void* didx = nullptr;
+    ok(c, cgb_malloc(c, (n_dst ? n_dst : 1) * 4, &didx), "cgb_malloc");
+    if (n_dst) ok(c, cgb_h2d(c, didx, idx.data(), n_dst * 4), "cgb_h2d");
+    dx.up(x);
+    m.up(msg);
+    prg(c, k.rt.key, stream_id(K_OM_R, k.op, k.owner, 0), r);
+    prg(c, k.rt.key, stream_id(K_OM_S, k.op, k.owner, 0), s);
+    if (D) {
+        ok(c, cgb_expand_rows(c, (const uint32_t*)didx, n_dst, r.p, nullptr, delta.p, (uint32_t)D), "cgb_expand_rows");  // dealer: pi(r)
+        ok(c, cgb_sub(c, delta.p, s.p, delta.p, delta.n), "cgb_sub");                                                   //         - s
+        ok(c, cgb_add(c, dx.p, m.p, dx.p, dx.n), "cgb_add");
+        ok(c, cgb_expand_rows(c, (const uint32_t*)didx, n_dst, dx.p, delta.p, y.p, (uint32_t)D), "cgb_expand_rows");
+    }
+    unflatten(y.down(), n_dst, D, dstSvv);
+    cgb_free(c, didx);
+}
+
+// OM online, server side: sends its masked share, keeps the fresh mask as its share of the result
+inline void server_oblivious_mapper_online(const ShareVecVec& srcSvv, ShareVecVec& dstSvv, uint64_t iter, uint32_t preprocessId, uint64_t coTid) {
+    using namespace cognn_shim;
+    (void)iter;
+    (void)preprocessId;
+    Call k(coTid, sci::BOB);
+    size_t n_src, D;
+    std::vector<uint64_t> x = flatten(srcSvv, &n_src, &D);
+    std::vector<uint64_t> hdr;
+    k.ch.recv(hdr);
+    const size_t n_dst = hdr.empty() ? 0 : (size_t)hdr[0];
+    cgb_ctx* c = k.c;
+    Dev dx(c, n_src * D), m(c, n_src * D), s(c, n_dst * D);
+    dx.up(x);
+    ok(c, cgb_prg_mask_sub(c, k.rt.key, stream_id(K_OM_R, k.op, k.owner, 0), 0, dx.p, m.p, m.n), "cgb_prg_mask_sub");
+    k.ch.send(m.down());
+    prg(c, k.rt.key, stream_id(K_OM_S, k.op, k.owner, 0), s);
+    unflatten(s.down(), n_dst, D, dstSvv);
+}
