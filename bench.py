@@ -88,6 +88,47 @@ def exchange_and_sum(dist, y, recv, v, n_parties, n_local, D, add):
     return v
 
 
+class RawCuda:
+    """A cgb_malloc allocation viewed as a torch int64 tensor (cudaMalloc memory is IPC-exportable, torch's is not)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+
+def setup_peer_windows(torch, dist, ctx, rank, P, n_local, D, dev):
+    """Double-buffered receive windows, mapped into every peer with CUDA IPC.  Window k of party t holds one n_local x D
+    block per source party; the gather kernel of party `rank` stores its block for t straight into it over NVLink."""
+    nbytes = P * n_local * D * 8
+    bufs = [ctx.malloc(nbytes) for _ in range(2)]
+    mine = [ctx.ipc_export(b) for b in bufs]
+    everyone = [None] * P
+    dist.all_gather_object(everyone, mine)
+    block_ptrs = []
+    for k in range(2):
+        row = []
+        for t in range(P):
+            base = bufs[k] if t == rank else ctx.ipc_open(everyone[t][k])
+            row.append(base + rank * n_local * D * 8)
+        block_ptrs.append(row)
+    views = [torch.as_tensor(RawCuda(b, (P, n_local, D)), device=dev) for b in bufs]
+    offsets = [t * n_local for t in range(P + 1)]
+    return {"bufs": bufs, "block_ptrs": block_ptrs, "views": views, "offsets": offsets,
+            "flag": torch.zeros(1, dtype=torch.int32, device=dev)}
+
+
+def fused_step(dist, ctx, csr, x, win, step_idx, v, P, add):
+    """One GAS gather step with the exchange fused into the kernel: every output row is written once, directly into the
+    window of the party that owns it (peer memory over NVLink); a 4-byte all-reduce is the cross-rank barrier."""
+    k = step_idx & 1
+    ctx.gather_sum_blocks(csr, x, win["block_ptrs"][k], win["offsets"])
+    dist.all_reduce(win["flag"])  # stream-ordered barrier: all peers have finished writing window k
+    blocks = win["views"][k]
+    add(blocks[0], blocks[1], v)
+    for j in range(2, P):
+        add(v, blocks[j], v)
+    return v
+
+
 def algorithmic_bytes(n_rows, n_edges, D):
     # SURVEY.md 8d, fused SpMM form: every edge = one 8*D-byte row read + a 4-byte index, no cache-reuse credit
     return (8 * D + 4) * n_edges + 4 * (n_rows + 1) + 8 * D * n_rows
@@ -201,6 +242,8 @@ def main():
     ap.add_argument("--cpu-frac", type=float, default=0.25, help="fraction of rows in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: fused = gather kernel stores into peer windows over NVLink; nccl = gather then all_to_all")
     args = ap.parse_args()
 
     import torch
@@ -220,6 +263,9 @@ def main():
         "edges_per_party": E, "vertices_per_party": n_local, "D": D, "parties": P,
         "l2": "inputs larger than L2 (share rows + indices >> 126 MB); no flush needed",
         "seed": 42,
+        "exchange": ("fused: gather kernel stores each block into the consumer's window over NVLink (CUDA IPC peer "
+                     "memory), 4-byte all-reduce as barrier" if (P > 1 and args.exchange == "fused") else
+                     ("gather, then NCCL all_to_all_single of the blocks" if P > 1 else "none (single party)")),
     }
 
     # -------------------------------------------------------------------------------------------------------
@@ -286,10 +332,27 @@ def main():
     recv = torch.empty_like(y) if P > 1 else None
     v = torch.empty((n_local, D), dtype=torch.int64, device=dev) if P > 1 else None
 
+    add = lambda a, b, o: ctx.add(a, b, out=o)  # noqa: E731
+    fused = P > 1 and args.exchange == "fused"
+    win = setup_peer_windows(torch, dist, ctx, rank, P, n_local, D, dev) if fused else None
+    step_no = [0]
+    if fused:
+        # self-check outside the timed region: the fused path must equal gather + NCCL all-to-all + sum
+        ctx.gather_sum(csr, x, None, out=y)
+        ref = exchange_and_sum(dist, y, recv, torch.empty_like(v), P, n_local, D, add).clone()
+        for k in range(2):
+            got = fused_step(dist, ctx, csr, x, win, k, v, P, add)
+            assert torch.equal(got, ref), "fused peer-store exchange differs from the NCCL all-to-all path"
+        dist.barrier()
+
     def step():
+        if fused:
+            fused_step(dist, ctx, csr, x, win, step_no[0], v, P, add)
+            step_no[0] += 1
+            return
         ctx.gather_sum(csr, x, None, out=y)
         if P > 1:
-            exchange_and_sum(dist, y, recv, v, P, n_local, D, lambda a, b, o: ctx.add(a, b, out=o))
+            exchange_and_sum(dist, y, recv, v, P, n_local, D, add)
 
     def barrier():
         if P > 1:
@@ -315,11 +378,22 @@ def main():
             kev[i][0].record()
             step()
             kev[i][1].record()
+        elif fused:
+            k = step_no[0] & 1
+            kev[i][0].record()
+            ctx.gather_sum_blocks(csr, x, win["block_ptrs"][k], win["offsets"])
+            kev[i][1].record()
+            dist.all_reduce(win["flag"])
+            blocks = win["views"][k]
+            add(blocks[0], blocks[1], v)
+            for j in range(2, P):
+                add(v, blocks[j], v)
+            step_no[0] += 1
         else:
             kev[i][0].record()
             ctx.gather_sum(csr, x, None, out=y)
             kev[i][1].record()
-            exchange_and_sum(dist, y, recv, v, P, n_local, D, lambda a, b, o: ctx.add(a, b, out=o))
+            exchange_and_sum(dist, y, recv, v, P, n_local, D, add)
     e1.record()
     barrier()
     torch.cuda.profiler.stop()

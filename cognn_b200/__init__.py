@@ -98,6 +98,36 @@ class Context:
                                            _ptr(delta), _ptr(self._u64(out)), D))
         return out
 
+    def gather_sum_blocks(self, csr, x, block_ptrs, block_offsets, delta=None):
+        """block_ptrs: list of raw device addresses (ints; may be peer memory), block_offsets: row offsets (len + 1)."""
+        D = x.shape[1]
+        n = len(block_ptrs)
+        bases = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in block_ptrs])
+        offs = (C.c_uint32 * (n + 1))(*[int(o) for o in block_offsets])
+        self.check(self.lib.cgb_gather_sum_blocks(self.handle, csr.handle, _ptr(self._u64(x)), _ptr(delta), D, n, bases, offs))
+
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(self.lib.cgb_malloc(self.handle, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, ptr):
+        self.check(self.lib.cgb_free(self.handle, C.c_void_p(ptr)))
+
+    def ipc_export(self, ptr):
+        h = (C.c_char * 64)()
+        self.check(self.lib.cgb_ipc_export(self.handle, C.c_void_p(ptr), h))
+        return bytes(h)
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        buf = (C.c_char * 64).from_buffer_copy(handle)
+        self.check(self.lib.cgb_ipc_open(self.handle, buf, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        self.check(self.lib.cgb_ipc_close(self.handle, C.c_void_p(ptr)))
+
     def expand_rows(self, idx, x, delta=None, out=None):
         D = x.shape[1]
         n_out = idx.numel()

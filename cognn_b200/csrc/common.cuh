@@ -50,6 +50,7 @@ struct cgb_csr {
     size_t piece_words = 0;
 };
 #define CGB_CHUNK_EDGES 64u
+#define CGB_MAX_BLOCKS 16
 #define CGB_END_FLAG 0x80000000u
 
 #define CGB_LONG_ROW 256u

@@ -12,6 +12,7 @@
 // every schedule yields the same bits.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -187,7 +188,21 @@ struct ChunkArgs {
     uint32_t* counters;
     u64* piece_head;  // n_chunks x D: sum of the chunk's leading edges when they continue a row from an earlier chunk
     u64* piece_tail;  // n_chunks x D: sum of the chunk's trailing edges when their row continues in a later chunk
+    // optional: the output rows are split into n_blk contiguous blocks, block t stored at blk_base[t] -- the base may
+    // be PEER memory (another GPU's receive buffer mapped over NVLink), which fuses the mirror-update exchange of
+    // ssk.h:835 -> 1067/1090 into the gather: every 8*D-byte row is written exactly once, straight to its consumer
+    int n_blk;
+    u64* blk_base[CGB_MAX_BLOCKS];
+    uint32_t blk_off[CGB_MAX_BLOCKS + 1];
 };
+
+__device__ __forceinline__ u64* out_row(const ChunkArgs& a, uint32_t row) {
+    if (a.n_blk == 0) return a.y + (size_t)row * a.D;
+    int t = 0;
+#pragma unroll 1
+    while (t + 1 < a.n_blk && row >= a.blk_off[t + 1]) ++t;
+    return a.blk_base[t] + (size_t)(row - a.blk_off[t]) * a.D;
+}
 
 // A row segment cut by a chunk boundary has been stored as a "piece"; count the arrival and, if this was the last
 // piece of the row, fold them.  Rare relative to the edge loop, so kept out of line.
@@ -216,7 +231,7 @@ __device__ __noinline__ void piece_arrive(const ChunkArgs& a, uint32_t row, uint
                 p.load_cg(a.piece_head + (size_t)cc * a.D + col0);
                 sum.add(p);
             }
-            sum.store_cs(a.y + o);
+            sum.store_cs(out_row(a, row) + col0);
         }
         if (lane == 0) *ctr = 0;  // ready for the next launch
     }
@@ -243,7 +258,7 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
             Acc<VEC> v;
             v.zero();
             if (a.delta) v.load_nc(a.delta + o);
-            v.store_cs(a.y + o);
+            v.store_cs(out_row(a, row) + col0);
         }
         return;
     }
@@ -293,7 +308,7 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
                                         d.load_nc(a.delta + o);
                                         acc.add(d);
                                     }
-                                    acc.store_cs(a.y + o);
+                                    acc.store_cs(out_row(a, row) + col0);
                                 }
                             } else {  // end of a row that began in an earlier chunk: leave a head piece
                                 if (active) acc.store(a.piece_head + (size_t)c * a.D + col0);
@@ -374,7 +389,7 @@ __global__ void __launch_bounds__(BLOCK) gather_chunk_async_kernel(const __grid_
             Acc<VEC> v;
             v.zero();
             if (a.delta) v.load_nc(a.delta + o);
-            v.store_cs(a.y + o);
+            v.store_cs(out_row(a, row) + col0);
         }
         return;
     }
@@ -410,7 +425,7 @@ __global__ void __launch_bounds__(BLOCK) gather_chunk_async_kernel(const __grid_
                                 d.load_nc(a.delta + o);
                                 acc.add(d);
                             }
-                            acc.store_cs(a.y + o);
+                            acc.store_cs(out_row(a, row) + col0);
                         }
                     } else {
                         if (active) acc.store(a.piece_head + (size_t)c * a.D + col0);
@@ -726,13 +741,16 @@ uint32_t cgb_csr_num_rows(const cgb_csr* c) { return c ? c->n_rows : 0; }
 const uint32_t* cgb_csr_rowptr(const cgb_csr* c) { return c ? c->d_rowptr : nullptr; }
 const uint32_t* cgb_csr_col(const cgb_csr* c) { return c ? c->d_col : nullptr; }
 
-int cgb_gather_sum(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, const uint64_t* d_delta, uint64_t* d_y,
-                   uint32_t D) {
+static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, const uint64_t* d_delta, uint64_t* d_y,
+                       uint32_t D, int n_blk, uint64_t* const* blk_base, const uint32_t* blk_off) {
     cgb_csr* csr = const_cast<cgb_csr*>(csr_c);
-    CGB_REQUIRE(ctx, csr && d_x && d_y && D > 0, "cgb_gather_sum: null argument");
+    CGB_REQUIRE(ctx, csr && d_x && (d_y || n_blk > 0) && D > 0, "cgb_gather_sum: null argument");
     CGB_REQUIRE(ctx, (const void*)d_x != (const void*)d_y, "cgb_gather_sum: y must not alias x");
     if (csr->n_rows == 0) return CGB_OK;
-    const Shape s = pick_shape(D, is_aligned16(d_x) && is_aligned16(d_delta) && is_aligned16(d_y));
+    bool al = is_aligned16(d_x) && is_aligned16(d_delta) && is_aligned16(d_y);
+    for (int t = 0; t < n_blk; ++t) al = al && is_aligned16(blk_base[t]);
+    const Shape s = pick_shape(D, al);
+    CGB_REQUIRE(ctx, n_blk == 0 || !use_row_schedule(), "cgb_gather_sum_blocks: needs the edge-balanced schedule");
     if (!use_row_schedule()) {
         CGB_REQUIRE(ctx, csr->n_src_rows < CGB_END_FLAG, "cgb_gather_sum: source rows must fit 31 bits");
         if (csr->n_chunks) {
@@ -765,6 +783,12 @@ int cgb_gather_sum(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, cons
         a.counters = csr->d_chunk_ctr;
         a.piece_head = (u64*)csr->d_piece;
         a.piece_tail = (u64*)csr->d_piece + (size_t)csr->n_chunks * D;
+        a.n_blk = n_blk;
+        for (int t = 0; t < n_blk; ++t) {
+            a.blk_base[t] = (u64*)blk_base[t];
+            a.blk_off[t] = blk_off[t];
+        }
+        if (n_blk) a.blk_off[n_blk] = blk_off[n_blk];
         const uint64_t total = ((uint64_t)csr->n_chunks + csr->n_empty) * s.n_ct;
         // tuning knobs (round 1 experiments): CGB_GATHER_IMPL=async -> cp.async staged variant (CGB_GATHER_NBUF=2|3);
         // CGB_GATHER_U8=1 -> 8 register loads in flight per lane at 32 warps/SM;
@@ -846,6 +870,42 @@ int cgb_gather_sum(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, cons
     });
     CGB_REQUIRE(ctx, rc == 0, "cgb_gather_sum: no kernel for this shape");
     CGB_CHECK_LAUNCH(ctx, "gather_sum_kernel");
+    return CGB_OK;
+}
+
+int cgb_gather_sum(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x, const uint64_t* d_delta, uint64_t* d_y,
+                   uint32_t D) {
+    return gather_impl(ctx, csr, d_x, d_delta, d_y, D, 0, nullptr, nullptr);
+}
+
+int cgb_gather_sum_blocks(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x, const uint64_t* d_delta, uint32_t D,
+                          uint32_t n_blocks, uint64_t* const* d_block_base, const uint32_t* block_row_offsets) {
+    CGB_REQUIRE(ctx, csr && d_block_base && block_row_offsets, "cgb_gather_sum_blocks: null argument");
+    CGB_REQUIRE(ctx, n_blocks >= 1 && n_blocks <= CGB_MAX_BLOCKS, "cgb_gather_sum_blocks: 1..16 blocks");
+    CGB_REQUIRE(ctx, block_row_offsets[0] == 0 && block_row_offsets[n_blocks] == csr->n_rows,
+                "cgb_gather_sum_blocks: offsets must span the rows");
+    return gather_impl(ctx, csr, d_x, d_delta, nullptr, D, (int)n_blocks, d_block_base, block_row_offsets);
+}
+
+int cgb_ipc_export(cgb_ctx* ctx, void* d_ptr, void* out_handle64) {
+    CGB_REQUIRE(ctx, d_ptr && out_handle64, "cgb_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CGB_CHECK_CUDA(ctx, cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(out_handle64, &h, sizeof(h));
+    return CGB_OK;
+}
+int cgb_ipc_open(cgb_ctx* ctx, const void* handle64, void** d_peer_out) {
+    CGB_REQUIRE(ctx, handle64 && d_peer_out, "cgb_ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    CGB_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    CGB_CHECK_CUDA(ctx, cudaIpcOpenMemHandle(d_peer_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return CGB_OK;
+}
+int cgb_ipc_close(cgb_ctx* ctx, void* d_peer) {
+    if (!d_peer) return CGB_OK;
+    CGB_CHECK_CUDA(ctx, cudaIpcCloseMemHandle(d_peer));
     return CGB_OK;
 }
 

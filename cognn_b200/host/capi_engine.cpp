@@ -150,6 +150,7 @@ uint64_t cge_rounds(cge_engine* h) { return h->comm->rounds; }
 uint64_t cge_launch_count(cge_engine* h) { return cgb_ctx_launch_count(h->ctx); }
 double cge_seconds_online(cge_engine* h) { return h->eng->seconds_online; }
 double cge_seconds_offline(cge_engine* h) { return h->eng->seconds_offline; }
+double cge_seconds_residual_host(cge_engine* h) { return h->eng->seconds_residual_host(); }
 
 uint64_t cge_metrics_count(cge_engine* h) { return h->eng->metrics().size(); }
 int cge_metrics_get(cge_engine* h, uint64_t i, uint64_t* iter, int* party, double* loss, double* acc_full, double* acc_train,

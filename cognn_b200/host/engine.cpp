@@ -937,6 +937,8 @@ void SSGcnEngine::run(uint64_t n_iters) {
     }
 }
 
+double SSGcnEngine::seconds_residual_host() const { return impl_->seconds_residual_host; }
+
 std::vector<uint64_t> SSGcnEngine::download(int owner, int role, const std::string& name, uint32_t* rows, uint32_t* cols) {
     Impl& im = *impl_;
     Side* s = im.side(owner, role);

@@ -88,6 +88,7 @@ public:
     const std::vector<Metrics>& metrics() const { return metrics_; }
     bool verbose = false;          // print the reference's log lines ("::iteration took", accuracy)
     double seconds_online = 0, seconds_offline = 0;
+    double seconds_residual_host() const;
 
     struct Impl;
 

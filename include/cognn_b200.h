@@ -101,6 +101,17 @@ const uint32_t* cgb_csr_col(const cgb_csr* csr);
  * expand -> ScatterComp -> prefix_network_aggregate -> extract in one pass over the edges.  d_y must not alias d_x. */
 int cgb_gather_sum(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x, const uint64_t* d_delta, uint64_t* d_y,
                    uint32_t D);
+/* Same gather, but the output rows are split into n_blocks contiguous blocks (block t = rows [offsets[t], offsets[t+1]),
+ * one per destination party) and block t is stored at d_block_base[t].  A base may be PEER memory -- another GPU's
+ * receive buffer mapped with cgb_ipc_open -- so the mirror-update exchange (ssk.h:835 -> 1067/1090) is fused into the
+ * gather: each row is written once, over NVLink, straight to the party that consumes it.  d_block_base and
+ * block_row_offsets are HOST arrays (n_blocks <= 16).  Completion on the peer needs a cross-rank barrier afterwards. */
+int cgb_gather_sum_blocks(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x, const uint64_t* d_delta, uint32_t D,
+                          uint32_t n_blocks, uint64_t* const* d_block_base, const uint32_t* block_row_offsets);
+/* CUDA IPC plumbing for the peer buffers (one process per GPU): d_ptr must come from cgb_malloc; handle is 64 bytes */
+int cgb_ipc_export(cgb_ctx* ctx, void* d_ptr, void* out_handle64);
+int cgb_ipc_open(cgb_ctx* ctx, const void* handle64, void** d_peer_out);
+int cgb_ipc_close(cgb_ctx* ctx, void* d_peer);
 /* OM online, client side: y[j,:] = (idx[j]==CGB_NO_ROW ? 0 : x[idx[j],:]) + (delta ? delta[j,:] : 0) */
 int cgb_expand_rows(cgb_ctx* ctx, const uint32_t* d_idx, uint64_t n_out, const uint64_t* d_x,
                     const uint64_t* d_delta, uint64_t* d_y, uint32_t D);

@@ -48,7 +48,8 @@ uint64_t cge_words_sent(cge_engine* h);
 uint64_t cge_rounds(cge_engine* h);
 uint64_t cge_launch_count(cge_engine* h);
 double cge_seconds_online(cge_engine* h);   /* host wall time of the online phases, stream-synchronised */
-double cge_seconds_offline(cge_engine* h);  /* dealer emulation (correlation generation), excluded from online */
+double cge_seconds_offline(cge_engine* h);
+double cge_seconds_residual_host(cge_engine* h); /* part of online spent in the host 2PC-residual stand-in (softmax) */  /* dealer emulation (correlation generation), excluded from online */
 uint64_t cge_metrics_count(cge_engine* h);
 int cge_metrics_get(cge_engine* h, uint64_t i, uint64_t* iter, int* party, double* loss, double* acc_full, double* acc_train,
                     double* acc_test);

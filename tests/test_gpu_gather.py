@@ -123,3 +123,26 @@ def test_large_graph_properties(cgb):
     assert torch.equal(ya + yb, yab)  # int64 wraps like Z_2^64
     assert torch.equal(ya.sum(0), a[col.long()].sum(0))
     csr.destroy()
+
+
+@pytest.mark.parametrize("D", [7, 16, 64])
+def test_gather_sum_blocks_matches_oracle(cgb, oracle, D):
+    """Block outputs (one buffer per destination party; in deployment the buffers are peer memory over NVLink)."""
+    import torch
+
+    rng = np.random.default_rng(300 + D)
+    n_dst, n_src = 2100, 1500
+    rowptr, col = power_law_csr(rng, n_dst, n_src, 30000)
+    x, delta = rand_u64(rng, n_src, D), rand_u64(rng, n_dst, D)
+    csr = cgb.csr_create(to_dev(rowptr), to_dev(col), n_src)
+    offsets = [0, 700, 700, 1500, 2100]  # includes an empty block
+    bufs = [torch.empty((offsets[t + 1] - offsets[t], D), dtype=torch.int64, device="cuda") for t in range(4)]
+    # empty tensors have a null data_ptr on some torch versions: point them at a dummy allocation
+    dummy = torch.empty(2, dtype=torch.int64, device="cuda")
+    ptrs = [b.data_ptr() if b.numel() else dummy.data_ptr() for b in bufs]
+    for dl in (None, delta):
+        want = oracle.gather_sum_csr(rowptr, col, x, dl)
+        cgb.gather_sum_blocks(csr, to_dev(x), ptrs, offsets, None if dl is None else to_dev(dl))
+        for t in range(4):
+            assert np.array_equal(to_np(bufs[t]).reshape(-1, D), want[offsets[t]:offsets[t + 1]])
+    csr.destroy()
