@@ -123,9 +123,7 @@ def fused_step(dist, ctx, csr, x, win, step_idx, v, P, add):
     ctx.gather_sum_blocks(csr, x, win["block_ptrs"][k], win["offsets"])
     dist.all_reduce(win["flag"])  # stream-ordered barrier: all peers have finished writing window k
     blocks = win["views"][k]
-    add(blocks[0], blocks[1], v)
-    for j in range(2, P):
-        add(v, blocks[j], v)
+    ctx.sum_n([blocks[j] for j in range(P)], out=v)  # GatherComp additions over all source parties, one pass
     return v
 
 
@@ -387,9 +385,7 @@ def main():
             kev[i][1].record()
             dist.all_reduce(win["flag"])
             blocks = win["views"][k]
-            add(blocks[0], blocks[1], v)
-            for j in range(2, P):
-                add(v, blocks[j], v)
+            ctx.sum_n([blocks[j] for j in range(P)], out=v)
             step_no[0] += 1
         else:
             kev[i][0].record()

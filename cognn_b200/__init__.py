@@ -182,6 +182,13 @@ class Context:
         self.check(self.lib.cgb_sub(self.handle, _ptr(self._u64(a)), _ptr(self._u64(b)), _ptr(out), a.numel()))
         return out
 
+    def sum_n(self, tensors, out=None):
+        n = len(tensors)
+        out = self.torch.empty_like(tensors[0]) if out is None else out
+        ptrs = (C.c_void_p * n)(*[C.c_void_p(self._u64(t).data_ptr()) for t in tensors])
+        self.check(self.lib.cgb_sum_n(self.handle, ptrs, n, _ptr(out), tensors[0].numel()))
+        return out
+
     def trunc(self, x, share, f=SCALER_BITS, out=None):
         out = self.torch.empty_like(x) if out is None else out
         self.check(self.lib.cgb_trunc(self.handle, _ptr(self._u64(x)), _ptr(out), x.numel(), f, share))

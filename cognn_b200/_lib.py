@@ -57,6 +57,7 @@ SIGNATURES = {
                                            C.c_uint32, C.c_int, C.c_int]),
     "cgb_add": (C.c_int, [ctx_p, u64p, u64p, u64p, C.c_uint64]),
     "cgb_sub": (C.c_int, [ctx_p, u64p, u64p, u64p, C.c_uint64]),
+    "cgb_sum_n": (C.c_int, [ctx_p, C.c_void_p, C.c_uint32, u64p, C.c_uint64]),
     "cgb_trunc": (C.c_int, [ctx_p, u64p, u64p, C.c_uint64, C.c_int, C.c_int]),
     "cgb_scale_public": (C.c_int, [ctx_p, u64p, C.c_uint64, u64p, C.c_uint64, C.c_int, C.c_int]),
     "cgb_apply_gradient": (C.c_int, [ctx_p, u64p, u64p, C.c_uint64, u64p, C.c_uint64, C.c_int, C.c_int]),

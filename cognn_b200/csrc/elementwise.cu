@@ -130,6 +130,38 @@ __global__ void __launch_bounds__(EW_THREADS) decode_kernel(const u64* __restric
         out[i] = decode_fixed(s0[i] + (s1 ? s1[i] : 0ull), f);
 }
 
+struct SumArgs {
+    const u64* in[16];
+    int n_in;
+};
+__global__ void __launch_bounds__(EW_THREADS) sum_n_kernel(const SumArgs a, u64* out, uint64_t n, bool vec) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        const uint64_t n2 = n >> 1;
+        for (uint64_t k = i0; k < n2; k += stride) {
+            ulonglong2 acc = reinterpret_cast<const ulonglong2*>(a.in[0])[k];
+            for (int j = 1; j < a.n_in; ++j) {
+                const ulonglong2 v = reinterpret_cast<const ulonglong2*>(a.in[j])[k];
+                acc.x += v.x;
+                acc.y += v.y;
+            }
+            reinterpret_cast<ulonglong2*>(out)[k] = acc;
+        }
+        if (i0 == 0 && (n & 1)) {
+            u64 acc = a.in[0][n - 1];
+            for (int j = 1; j < a.n_in; ++j) acc += a.in[j][n - 1];
+            out[n - 1] = acc;
+        }
+    } else {
+        for (uint64_t k = i0; k < n; k += stride) {
+            u64 acc = a.in[0][k];
+            for (int j = 1; j < a.n_in; ++j) acc += a.in[j][k];
+            out[k] = acc;
+        }
+    }
+}
+
 // 2PC-RESIDUAL stand-ins (ideal functionality on reconstructed values; NOT secure, see the header)
 __global__ void __launch_bounds__(EW_THREADS) ideal_relu_kernel(const u64* a0, const u64* a1, const u64* z0, const u64* z1,
                                                                u64* out, uint64_t n) {
@@ -152,6 +184,21 @@ int cgb_add(cgb_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_
 int cgb_sub(cgb_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint64_t n) {
     CGB_REQUIRE(ctx, (d_a && d_b && d_out) || n == 0, "cgb_sub: null argument");
     return launch_ew2(ctx, d_a, d_b, d_out, n, OpSub(), "ew_sub");
+}
+int cgb_sum_n(cgb_ctx* ctx, const uint64_t* const* d_in, uint32_t n_in, uint64_t* d_out, uint64_t n) {
+    CGB_REQUIRE(ctx, d_in && d_out && n_in >= 1 && n_in <= 16, "cgb_sum_n: 1..16 inputs");
+    if (n == 0) return CGB_OK;
+    SumArgs a;
+    bool vec = aligned16(d_out) && n >= 2;
+    for (uint32_t j = 0; j < n_in; ++j) {
+        CGB_REQUIRE(ctx, d_in[j], "cgb_sum_n: null input");
+        a.in[j] = (const u64*)d_in[j];
+        vec = vec && aligned16(d_in[j]);
+    }
+    a.n_in = (int)n_in;
+    sum_n_kernel<<<ew_blocks(ctx, vec ? n / 2 : n), EW_THREADS, 0, ctx->stream>>>(a, (u64*)d_out, n, vec);
+    CGB_CHECK_LAUNCH(ctx, "sum_n_kernel");
+    return CGB_OK;
 }
 int cgb_trunc(cgb_ctx* ctx, const uint64_t* d_x, uint64_t* d_out, uint64_t n, int f, int share) {
     CGB_REQUIRE(ctx, (d_x && d_out) || n == 0, "cgb_trunc: null argument");

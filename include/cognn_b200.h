@@ -134,6 +134,9 @@ int cgb_beaver_matmul_finish(cgb_ctx* ctx, const uint64_t* d_E, const uint64_t* 
 /* ---- (3) fused elementwise: truncation, masking / opening, scaling ---------------------------------------- */
 int cgb_add(cgb_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint64_t n);
 int cgb_sub(cgb_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint64_t n);
+/* out = sum of n_in (<= 16) share vectors: the GatherComp additions over all source parties (gcn.h:456-463, called T
+ * times per iteration in the reference) in one pass.  d_in is a HOST array of device pointers; out may alias d_in[0]. */
+int cgb_sum_n(cgb_ctx* ctx, const uint64_t* const* d_in, uint32_t n_in, uint64_t* d_out, uint64_t n);
 int cgb_trunc(cgb_ctx* ctx, const uint64_t* d_x, uint64_t* d_out, uint64_t n, int f, int share);
 int cgb_scale_public(cgb_ctx* ctx, const uint64_t* d_x, uint64_t c, uint64_t* d_out, uint64_t n, int f, int share);
 int cgb_apply_gradient(cgb_ctx* ctx, const uint64_t* d_W, const uint64_t* d_d, uint64_t lr, uint64_t* d_out,

@@ -129,3 +129,17 @@ def test_ideal_functionality_standins(cgb):
     assert np.array_equal(got, np.where(v.astype(np.int64) > 0, v, np.uint64(0)))
     got = to_np(cgb.ideal_relu_grad(to_dev(a0), to_dev(a1), to_dev(z0), to_dev(z1)))
     assert np.array_equal(got, np.where(z.astype(np.int64) > 0, v, np.uint64(0)))
+
+
+def test_sum_n_matches_oracle(cgb, oracle):
+    rng = np.random.default_rng(8)
+    for n in (1, 7, 4096, 100_001):
+        xs = [rand_u64(rng, n) for _ in range(5)]
+        want = xs[0].copy()
+        for x in xs[1:]:
+            want = oracle.add(want, x)
+        devs = [to_dev(x) for x in xs]
+        assert np.array_equal(to_np(cgb.sum_n(devs)), want)
+        assert np.array_equal(to_np(cgb.sum_n(devs[:1])), xs[0])
+        cgb.sum_n(devs, out=devs[0])  # in place on the first input
+        assert np.array_equal(to_np(devs[0]), want)
