@@ -75,6 +75,8 @@ SIGNATURES = {
     "cgb_ideal_relu": (C.c_int, [ctx_p, u64p, u64p, u64p, C.c_uint64]),
     "cgb_ideal_relu_grad": (C.c_int, [ctx_p, u64p, u64p, u64p, u64p, u64p, C.c_uint64]),
     "cgb_host_gather_sum": (C.c_int, [ctx_p, csr_p, u64p, u64p, u64p, C.c_uint32]),
+    "cgb_host_gather_sum_async": (C.c_int, [ctx_p, csr_p, u64p, u64p, u64p, C.c_uint32]),
+    "cgb_host_sync": (C.c_int, [ctx_p]),
 }
 
 _lib = None

@@ -82,6 +82,18 @@ int cgb_ctx_destroy(cgb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->pipe.ready) {
+        cudaStreamSynchronize(ctx->pipe.h2d);
+        cudaStreamSynchronize(ctx->pipe.d2h);
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->pipe.buf[i]) cudaFree(ctx->pipe.buf[i]);
+            cudaEventDestroy(ctx->pipe.ev_x[i]);
+            cudaEventDestroy(ctx->pipe.ev_y[i]);
+            cudaEventDestroy(ctx->pipe.ev_out[i]);
+        }
+        cudaStreamDestroy(ctx->pipe.h2d);
+        cudaStreamDestroy(ctx->pipe.d2h);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return CGB_OK;

@@ -17,6 +17,15 @@ struct cgb_ctx {
     // grow-only device scratch (split-K accumulators, Beaver temporaries)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // double-buffered staging for the pipelined host entry point (cgb_host_gather_sum_async)
+    struct HostPipe {
+        cudaStream_t h2d = nullptr, d2h = nullptr;
+        cudaEvent_t ev_x[2] = {nullptr, nullptr}, ev_y[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+        void* buf[2] = {nullptr, nullptr};
+        size_t bytes[2] = {0, 0};
+        uint64_t steps = 0;
+        bool ready = false;
+    } pipe;
 };
 
 struct cgb_csr {

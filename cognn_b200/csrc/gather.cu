@@ -887,6 +887,69 @@ int cgb_gather_sum_blocks(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x,
     return gather_impl(ctx, csr, d_x, d_delta, nullptr, D, (int)n_blocks, d_block_base, block_row_offsets);
 }
 
+// Pipelined host entry point: slot s = step & 1 owns a device staging area; the H2D of step i+1 runs on its own stream
+// while step i computes and step i-1... copies back (PCIe is full duplex), so host-buffer throughput approaches
+// max(H2D, D2H, kernel) per step instead of their sum.
+int cgb_host_gather_sum_async(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* h_x, const uint64_t* h_delta,
+                              uint64_t* h_y, uint32_t D) {
+    CGB_REQUIRE(ctx, csr && h_x && h_y && D > 0, "cgb_host_gather_sum_async: null argument");
+    auto& P = ctx->pipe;
+    CGB_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!P.ready) {
+        CGB_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&P.h2d, cudaStreamNonBlocking));
+        CGB_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&P.d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CGB_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&P.ev_x[i], cudaEventDisableTiming));
+            CGB_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&P.ev_y[i], cudaEventDisableTiming));
+            CGB_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&P.ev_out[i], cudaEventDisableTiming));
+        }
+        P.ready = true;
+    }
+    auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t xb = (size_t)csr->n_src_rows * D * sizeof(u64);
+    const size_t yb = (size_t)csr->n_rows * D * sizeof(u64);
+    const size_t need = align(xb) + align(yb) + (h_delta ? align(yb) : 0);
+    const int s = (int)(P.steps & 1);
+    if (need > P.bytes[s]) {
+        CGB_CHECK_CUDA(ctx, cudaDeviceSynchronize());
+        if (P.buf[s]) cudaFree(P.buf[s]);
+        P.buf[s] = nullptr;
+        P.bytes[s] = 0;
+        CGB_CHECK_CUDA(ctx, cudaMalloc(&P.buf[s], need));
+        P.bytes[s] = need;
+    }
+    char* base = (char*)P.buf[s];
+    u64* d_x = (u64*)base;
+    u64* d_y = (u64*)(base + align(xb));
+    u64* d_delta = h_delta ? (u64*)(base + align(xb) + align(yb)) : nullptr;
+    // the slot is free once its previous result has left the device
+    if (P.steps >= 2) CGB_CHECK_CUDA(ctx, cudaStreamWaitEvent(P.h2d, P.ev_out[s], 0));
+    CGB_CHECK_CUDA(ctx, cudaMemcpyAsync(d_x, h_x, xb, cudaMemcpyHostToDevice, P.h2d));
+    if (h_delta) CGB_CHECK_CUDA(ctx, cudaMemcpyAsync(d_delta, h_delta, yb, cudaMemcpyHostToDevice, P.h2d));
+    CGB_CHECK_CUDA(ctx, cudaEventRecord(P.ev_x[s], P.h2d));
+    CGB_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, P.ev_x[s], 0));
+    int rc = cgb_gather_sum(ctx, csr, (const uint64_t*)d_x, (const uint64_t*)d_delta, (uint64_t*)d_y, D);
+    if (rc) return rc;
+    CGB_CHECK_CUDA(ctx, cudaEventRecord(P.ev_y[s], ctx->stream));
+    CGB_CHECK_CUDA(ctx, cudaStreamWaitEvent(P.d2h, P.ev_y[s], 0));
+    CGB_CHECK_CUDA(ctx, cudaMemcpyAsync(h_y, d_y, yb, cudaMemcpyDeviceToHost, P.d2h));
+    CGB_CHECK_CUDA(ctx, cudaEventRecord(P.ev_out[s], P.d2h));
+    ++P.steps;
+    return CGB_OK;
+}
+
+int cgb_host_sync(cgb_ctx* ctx) {
+    auto& P = ctx->pipe;
+    if (P.ready) {
+        CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(P.h2d));
+        CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(P.d2h));
+    } else {
+        CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return CGB_OK;
+}
+
 int cgb_ipc_export(cgb_ctx* ctx, void* d_ptr, void* out_handle64) {
     CGB_REQUIRE(ctx, d_ptr && out_handle64, "cgb_ipc_export: null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");

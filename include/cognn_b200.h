@@ -178,6 +178,13 @@ int cgb_ideal_relu_grad(cgb_ctx* ctx, const uint64_t* d_g0, const uint64_t* d_g1
 int cgb_host_gather_sum(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* h_x, const uint64_t* h_delta,
                         uint64_t* h_y, uint32_t D);
 
+/* Pipelined variant for back-to-back steps: returns after enqueueing; H2D of step i+1 overlaps the kernel of step i and
+ * the D2H of step i-1 (two staging slots, three streams).  Host buffers must be pinned and stay valid until
+ * cgb_host_sync() returns.  Results are identical to cgb_host_gather_sum. */
+int cgb_host_gather_sum_async(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* h_x, const uint64_t* h_delta,
+                              uint64_t* h_y, uint32_t D);
+int cgb_host_sync(cgb_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,3 +146,35 @@ def test_gather_sum_blocks_matches_oracle(cgb, oracle, D):
         for t in range(4):
             assert np.array_equal(to_np(bufs[t]).reshape(-1, D), want[offsets[t]:offsets[t + 1]])
     csr.destroy()
+
+
+def test_host_entry_points_sync_and_pipelined(cgb, oracle):
+    """cgb_host_gather_sum and the pipelined cgb_host_gather_sum_async + cgb_host_sync with a different input per step
+    (a slot-reuse or ordering bug would mix the steps)."""
+    import ctypes as C
+
+    import torch
+
+    rng = np.random.default_rng(17)
+    n_dst, n_src, D = 900, 800, 16
+    rowptr, col = power_law_csr(rng, n_dst, n_src, 12000)
+    csr = cgb.csr_create(to_dev(rowptr), to_dev(col), n_src)
+    steps = 7
+    xs = [rand_u64(rng, n_src, D) for _ in range(steps)]
+    delta = rand_u64(rng, n_dst, D)
+    hx = [torch.from_numpy(x.view(np.int64)).pin_memory() for x in xs]
+    hy = [torch.zeros((n_dst, D), dtype=torch.int64).pin_memory() for _ in range(steps)]
+    hd = torch.from_numpy(delta.view(np.int64)).pin_memory()
+    lib = cgb.lib
+    for i in range(steps):
+        dl = C.c_void_p(hd.data_ptr()) if i % 2 else None
+        cgb.check(lib.cgb_host_gather_sum_async(cgb.handle, csr.handle, C.c_void_p(hx[i].data_ptr()), dl,
+                                                C.c_void_p(hy[i].data_ptr()), D))
+    cgb.check(lib.cgb_host_sync(cgb.handle))
+    for i in range(steps):
+        want = oracle.gather_sum_csr(rowptr, col, xs[i], delta if i % 2 else None)
+        assert np.array_equal(hy[i].numpy().view(np.uint64), want), i
+    out = torch.zeros((n_dst, D), dtype=torch.int64).pin_memory()
+    cgb.check(lib.cgb_host_gather_sum(cgb.handle, csr.handle, C.c_void_p(hx[0].data_ptr()), None, C.c_void_p(out.data_ptr()), D))
+    assert np.array_equal(out.numpy().view(np.uint64), oracle.gather_sum_csr(rowptr, col, xs[0]))
+    csr.destroy()
