@@ -364,6 +364,8 @@ def main():
     barrier()
     # kernel-only duration of the dominant kernel (gather_sum) for the roofline, CUDA events on the launch stream
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    bev = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sev = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
@@ -384,8 +386,10 @@ def main():
             ctx.gather_sum_blocks(csr, x, win["block_ptrs"][k], win["offsets"])
             kev[i][1].record()
             dist.all_reduce(win["flag"])
+            bev[i].record()
             blocks = win["views"][k]
             ctx.sum_n([blocks[j] for j in range(P)], out=v)
+            sev[i].record()
             step_no[0] += 1
         else:
             kev[i][0].record()
@@ -406,6 +410,15 @@ def main():
         ms_total = float(t.item())
     ms_per_step = ms_total / K
     value = E * P / (ms_per_step * 1e-3)
+    phases = None
+    if fused:
+        mine = torch.tensor([kernel_ms, sum(kev[i][1].elapsed_time(bev[i]) for i in range(K)) / K,
+                             sum(bev[i].elapsed_time(sev[i]) for i in range(K)) / K], dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(P)]
+        dist.all_gather(allr, mine)
+        phases = {"per_rank_ms": {"gather_kernel_with_peer_stores": [round(float(t[0]), 3) for t in allr],
+                                  "barrier_wait": [round(float(t[1]), 3) for t in allr],
+                                  "sum_of_received_blocks": [round(float(t[2]), 3) for t in allr]}}
 
     peak, peak_src = measured_peak_hbm()
     n_rows = n_local * P
@@ -485,6 +498,8 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline}
+        if phases:
+            line["multi_gpu_phases"] = phases
         print(json.dumps(line))
     if P > 1:
         dist.destroy_process_group()
