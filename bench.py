@@ -127,6 +127,45 @@ def fused_step(dist, ctx, csr, x, win, step_idx, v, P, add):
     return v
 
 
+def setup_pipelined(torch, ctx, win, rowptr, col, rank, P, n_local, D, dev):
+    """One CSR per destination party, a local staging block per remote party and views of the peers' windows: the
+    gather of block t+1 overlaps the NVLink copy (DMA) of block t."""
+    csrs = []
+    for t in range(P):
+        lo, hi = t * n_local, (t + 1) * n_local
+        e0, e1 = int(rowptr[lo]), int(rowptr[hi])
+        csrs.append(ctx.csr_create((rowptr[lo:hi + 1] - rowptr[lo]).int().contiguous(), col[e0:e1].contiguous(), n_local))
+    stage = torch.empty((P, n_local, D), dtype=torch.int64, device=dev)
+    slot_bytes = n_local * D * 8
+    peer = [[torch.as_tensor(RawCuda(win["block_ptrs"][k][t], (n_local, D)), device=dev) for t in range(P)] for k in range(2)]
+    return {"csrs": csrs, "stage": stage, "peer": peer, "copy_stream": torch.cuda.Stream(device=dev),
+            "ev": [torch.cuda.Event() for _ in range(P)], "done": torch.cuda.Event(), "slot_bytes": slot_bytes}
+
+
+def pipelined_step(torch, dist, ctx, x, win, pipe, step_idx, v, rank, P):
+    """Gather per destination block (remote blocks first), push each finished block to its owner with an async peer copy
+    on a second stream while the next block is gathered; 4-byte all-reduce as barrier; one-pass sum of the received blocks."""
+    k = step_idx & 1
+    main = torch.cuda.current_stream()
+    cs = pipe["copy_stream"]
+    for j in range(1, P + 1):
+        t = (rank + j) % P
+        if t != rank:
+            ctx.gather_sum(pipe["csrs"][t], x, None, out=pipe["stage"][t])
+            pipe["ev"][t].record(main)
+            cs.wait_event(pipe["ev"][t])
+            with torch.cuda.stream(cs):
+                pipe["peer"][k][t].copy_(pipe["stage"][t], non_blocking=True)
+        else:
+            ctx.gather_sum(pipe["csrs"][t], x, None, out=pipe["peer"][k][t])  # own window, own slot
+    pipe["done"].record(cs)
+    main.wait_event(pipe["done"])
+    dist.all_reduce(win["flag"])
+    blocks = win["views"][k]
+    ctx.sum_n([blocks[j] for j in range(P)], out=v)
+    return v
+
+
 def algorithmic_bytes(n_rows, n_edges, D):
     # SURVEY.md 8d, fused SpMM form: every edge = one 8*D-byte row read + a 4-byte index, no cache-reuse credit
     return (8 * D + 4) * n_edges + 4 * (n_rows + 1) + 8 * D * n_rows
@@ -242,8 +281,9 @@ def main():
     ap.add_argument("--cpu-frac", type=float, default=1.0, help="fraction of rows in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
-                    help="N > 1: fused = gather kernel stores into peer windows over NVLink; nccl = gather then all_to_all")
+    ap.add_argument("--exchange", default="pipelined", choices=["pipelined", "fused", "nccl"],
+                    help="N > 1: pipelined = per-destination gathers overlapped with async peer copies over NVLink (default); "
+                         "fused = one gather kernel storing straight into peer windows; nccl = gather then all_to_all")
     args = ap.parse_args()
 
     import torch
@@ -263,9 +303,13 @@ def main():
         "edges_per_party": E, "vertices_per_party": n_local, "D": D, "parties": P,
         "l2": "inputs larger than L2 (share rows + indices >> 126 MB); no flush needed",
         "seed": 42,
-        "exchange": ("fused: gather kernel stores each block into the consumer's window over NVLink (CUDA IPC peer "
-                     "memory), 4-byte all-reduce as barrier" if (P > 1 and args.exchange == "fused") else
-                     ("gather, then NCCL all_to_all_single of the blocks" if P > 1 else "none (single party)")),
+        "exchange": {"pipelined": "one gather per destination party; each finished block is pushed into its owner's window "
+                                  "(CUDA IPC peer memory over NVLink) by an async copy that overlaps the next gather; "
+                                  "4-byte all-reduce as barrier; one-pass sum",
+                     "fused": "one gather kernel stores each block straight into the consumer's window over NVLink; "
+                              "4-byte all-reduce as barrier",
+                     "nccl": "gather, then NCCL all_to_all_single of the blocks"}[args.exchange] if P > 1
+        else "none (single party)",
     }
 
     # -------------------------------------------------------------------------------------------------------
@@ -334,7 +378,9 @@ def main():
 
     add = lambda a, b, o: ctx.add(a, b, out=o)  # noqa: E731
     fused = P > 1 and args.exchange == "fused"
-    win = setup_peer_windows(torch, dist, ctx, rank, P, n_local, D, dev) if fused else None
+    piped = P > 1 and args.exchange == "pipelined"
+    win = setup_peer_windows(torch, dist, ctx, rank, P, n_local, D, dev) if (fused or piped) else None
+    pipe = setup_pipelined(torch, ctx, win, rowptr, col, rank, P, n_local, D, dev) if piped else None
     step_no = [0]
     if fused:
         # self-check outside the timed region: the fused path must equal gather + NCCL all-to-all + sum
@@ -344,8 +390,19 @@ def main():
             got = fused_step(dist, ctx, csr, x, win, k, v, P, add)
             assert torch.equal(got, ref), "fused peer-store exchange differs from the NCCL all-to-all path"
         dist.barrier()
+    if piped:
+        ctx.gather_sum(csr, x, None, out=y)
+        ref = exchange_and_sum(dist, y, recv, torch.empty_like(v), P, n_local, D, add).clone()
+        for k in range(2):
+            got = pipelined_step(torch, dist, ctx, x, win, pipe, k, v, rank, P)
+            assert torch.equal(got, ref), "pipelined peer-copy exchange differs from the NCCL all-to-all path"
+        dist.barrier()
 
     def step():
+        if piped:
+            pipelined_step(torch, dist, ctx, x, win, pipe, step_no[0], v, rank, P)
+            step_no[0] += 1
+            return
         if fused:
             fused_step(dist, ctx, csr, x, win, step_no[0], v, P, add)
             step_no[0] += 1
@@ -380,6 +437,10 @@ def main():
             kev[i][0].record()
             step()
             kev[i][1].record()
+        elif piped:
+            kev[i][0].record()
+            step()
+            kev[i][1].record()
         elif fused:
             k = step_no[0] & 1
             kev[i][0].record()
@@ -404,6 +465,17 @@ def main():
     clocks = sampler.stop(t_wall0, t_wall1)
     ms_total = e0.elapsed_time(e1)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / K
+    if piped:
+        # the P per-destination gather launches of one step, timed on their own (no copies) for the roofline
+        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        ka.record()
+        for _ in range(reps):
+            for t in range(P):
+                ctx.gather_sum(pipe["csrs"][t], x, None, out=pipe["stage"][t])
+        kb.record()
+        torch.cuda.synchronize()
+        kernel_ms = ka.elapsed_time(kb) / reps
     if P > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

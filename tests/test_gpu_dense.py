@@ -143,3 +143,40 @@ def test_sum_n_matches_oracle(cgb, oracle):
         assert np.array_equal(to_np(cgb.sum_n(devs[:1])), xs[0])
         cgb.sum_n(devs, out=devs[0])  # in place on the first input
         assert np.array_equal(to_np(devs[0]), want)
+
+
+def test_matmul_properties_at_sweep_size(cgb):
+    """configs[4] size (2^18 x 512 x 256), too slow for the oracle: linearity in A and the transposed-storage identity."""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M, K, N = 1 << 18, 512, 256
+    A = torch.randint(-2**63, 2**63 - 1, (M, K), device="cuda", dtype=torch.int64, generator=g)
+    B = torch.randint(-2**63, 2**63 - 1, (M, K), device="cuda", dtype=torch.int64, generator=g)
+    W = torch.randint(-2**63, 2**63 - 1, (K, N), device="cuda", dtype=torch.int64, generator=g)
+    ya, yb, yab = cgb.matmul(A, W), cgb.matmul(B, W), cgb.matmul(A + B, W)
+    assert torch.equal(ya + yb, yab)
+    # a few rows against exact integer arithmetic on the host
+    rows = [0, 12345, M - 1]
+    Wl = [[int(v) for v in r] for r in W.cpu().tolist()]
+    for r in rows:
+        a = [int(v) for v in A[r].cpu().tolist()]
+        want = [sum(a[k] * Wl[k][j] for k in range(K)) % (1 << 64) for j in (0, 7, N - 1)]
+        got = [int(ya[r, j].item()) % (1 << 64) for j in (0, 7, N - 1)]
+        assert got == want
+    # weight-gradient form: X^T G with X stored n x F (transA) equals the explicit transpose
+    X = A[: 1 << 16, :128].contiguous()
+    G = B[: 1 << 16, :16].contiguous()
+    assert torch.equal(cgb.matmul(X, G, transA=True), cgb.matmul(cgb.transpose(X), G))
+
+
+def test_prg_stream_is_position_addressable_at_scale(cgb):
+    key = [1, 2, 3, 4, 5, 6, 7, 8]
+    n = 40_000_003
+    whole = cgb.prg_fill(key, 99, 5, n)
+    cut = 17_000_001
+    a, b = cgb.prg_fill(key, 99, 5, cut), cgb.prg_fill(key, 99, 5 + cut, n - cut)
+    import torch
+
+    assert torch.equal(whole[:cut], a) and torch.equal(whole[cut:], b)
+    assert not torch.equal(cgb.prg_fill(key, 100, 5, 1000), whole[:1000])

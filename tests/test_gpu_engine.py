@@ -83,3 +83,26 @@ def test_engine_cora_shaped_epoch_tracks_float64():
         w = po.open_decode(e.download(0, 0, f"W{layer}"), e.download(0, 1, f"W{layer}"), 16)
         assert np.allclose(w, ref.W[0][layer], atol=2e-2)
     e.close()
+
+
+def test_engine_multi_edges_isolated_vertices_and_block_partition():
+    """Repeated edges (accepted by graph.h:621), vertices without any edge (normaliser 0 / dummy rule) and a
+    contiguous-block partition: every share and message still equals the oracle's."""
+    from cognn_b200 import engine as eng
+
+    T = 3
+    g = small_graph(n=64, n_edges=200, F=9, C=3, T=T, seed=99, partition="block", multi_edges=25, isolated=5)
+    cfg = dict(input_dim=9, hidden_dim=6, num_labels=3, learning_rate=0.25, train_ratio=0.5, val_ratio=0.25)
+    o = ep.EpochOracle(g["edges"], g["tid"], T, g["feats"], g["labels"], cfg)
+    o.run(6)
+    e = eng.Engine(T, cfg, record=True)
+    e.load(g["edges"], g["tid"], g["feats"], g["labels"])
+    e.run(6)
+    for owner in range(T):
+        for role in (0, 1):
+            for name in NAMES:
+                assert np.array_equal(e.download(owner, role, name), oracle_tensor(o, owner, role, name)), (owner, role, name)
+    got = {(m[0], m[1], m[2], m[3]): m[4] for m in e.messages() if not m[3].startswith("setup")}
+    for m in o.msgs:
+        assert np.array_equal(got[(m[0], m[1], m[2], m[3])], m[4])
+    e.close()
