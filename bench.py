@@ -138,8 +138,9 @@ def setup_pipelined(torch, ctx, win, rowptr, col, rank, P, n_local, D, dev):
     stage = torch.empty((P, n_local, D), dtype=torch.int64, device=dev)
     slot_bytes = n_local * D * 8
     peer = [[torch.as_tensor(RawCuda(win["block_ptrs"][k][t], (n_local, D)), device=dev) for t in range(P)] for k in range(2)]
-    return {"csrs": csrs, "stage": stage, "peer": peer, "copy_stream": torch.cuda.Stream(device=dev),
-            "ev": [torch.cuda.Event() for _ in range(P)], "done": torch.cuda.Event(), "slot_bytes": slot_bytes}
+    return {"csrs": csrs, "stage": stage, "peer": peer, "copy_streams": [torch.cuda.Stream(device=dev) for _ in range(P)],
+            "ev": [torch.cuda.Event() for _ in range(P)], "done": [torch.cuda.Event() for _ in range(P)],
+            "slot_bytes": slot_bytes}
 
 
 def pipelined_step(torch, dist, ctx, x, win, pipe, step_idx, v, rank, P):
@@ -147,19 +148,21 @@ def pipelined_step(torch, dist, ctx, x, win, pipe, step_idx, v, rank, P):
     on a second stream while the next block is gathered; 4-byte all-reduce as barrier; one-pass sum of the received blocks."""
     k = step_idx & 1
     main = torch.cuda.current_stream()
-    cs = pipe["copy_stream"]
     for j in range(1, P + 1):
         t = (rank + j) % P
         if t != rank:
             ctx.gather_sum(pipe["csrs"][t], x, None, out=pipe["stage"][t])
             pipe["ev"][t].record(main)
+            cs = pipe["copy_streams"][t]  # one copy stream per destination: copies to different peers run concurrently
             cs.wait_event(pipe["ev"][t])
             with torch.cuda.stream(cs):
                 pipe["peer"][k][t].copy_(pipe["stage"][t], non_blocking=True)
+            pipe["done"][t].record(cs)
         else:
             ctx.gather_sum(pipe["csrs"][t], x, None, out=pipe["peer"][k][t])  # own window, own slot
-    pipe["done"].record(cs)
-    main.wait_event(pipe["done"])
+    for t in range(P):
+        if t != rank:
+            main.wait_event(pipe["done"][t])
     dist.all_reduce(win["flag"])
     blocks = win["views"][k]
     ctx.sum_n([blocks[j] for j in range(P)], out=v)
