@@ -9,8 +9,17 @@
 // Small output tiles with a long K (the weight-gradient h_t * v, K = N_p) are split along K and combined with
 // 64-bit atomics (addition mod 2^64 is order-independent, so this stays bit exact).
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
+
+// tensor-core (tcgen05 kind::i8 limb) path, matmul_tc.cu
+int cgb_matmul_tc_run(cgb_ctx* ctx, const u64* const A[2], const u64* const B[2], int n_pairs, const u64* Z, u64* C, uint32_t M,
+                      uint32_t K, uint32_t N, int transA, int accumulate, int f, int share);
+#ifndef CGB_MATMUL_AUTO_TC
+#define CGB_MATMUL_AUTO_TC 0  // flipped to 1 once the tensor-core path is the measured winner for N >= 32
+#endif
 
 namespace {
 
@@ -151,6 +160,15 @@ void launch_cfg(cgb_ctx* ctx, MatmulArgs& a) {
 // Runs the (up to two pair) product with optional Z / truncation epilogue.
 int run_matmul(cgb_ctx* ctx, MatmulArgs a) {
     if (a.M == 0 || a.N == 0) return CGB_OK;
+    // pipe selection (DESIGN.md "Matmul design"): CGB_MATMUL_IMPL = imad | tc | auto
+    {
+        const char* impl = getenv("CGB_MATMUL_IMPL");
+        bool tc = false;
+        if (impl && !strcmp(impl, "tc")) tc = a.K >= 1;
+        else if (impl && !strcmp(impl, "imad")) tc = false;
+        else tc = CGB_MATMUL_AUTO_TC && a.N >= 32 && a.M >= 128 && a.K >= 32;
+        if (tc) return cgb_matmul_tc_run(ctx, a.A, a.B, a.n_pairs, a.Z, a.C, a.M, a.K, a.N, a.transA, a.accumulate, a.f, a.share);
+    }
     constexpr uint32_t BK = 16;
     uint32_t BM, BN;
     if (a.N > 32) { BM = 128; BN = 64; }

@@ -1,0 +1,339 @@
+// matmul_tc.cu -- op (2) on the 5th-generation tensor cores: u64 x u64 -> low 64 bits through int8 limbs.
+//
+// Serves sci::twoPartyGCNMatMul (optimize-gcn/gcn.h:233,665,671,710) for shapes where the tensor pipe beats the
+// integer pipe (N >= 64).  Every u64 is cut into 8 unsigned byte limbs; C mod 2^64 only needs the 36 limb products
+// A_i * B_j with i + j <= 7, and all products of one anti-diagonal d = i + j carry the same weight 2^(8d):
+//     C = sum_{d=0..7} 2^(8d) * sum_{i+j=d} A_i B_j        (mod 2^64)
+// Each A_i B_j is a u8 x u8 -> s32 GEMM: tcgen05.mma kind::i8 with the accumulator of diagonal d in tensor memory
+// (8 accumulators x 64 columns = all 512 TMEM columns of the SM).  Only the low 64 - 8d bits of accumulator d matter,
+// so 32-bit wrap-around of the high diagonals is harmless; the low diagonals stay exact for K_total <= 4096.
+//
+// Data path: a pre-pass writes the limb planes to global memory already in the UMMA canonical (no-swizzle, K-major)
+// shared-memory layout, one contiguous 32 KB (A: 128 rows) / 16 KB (B: 64 columns) block per (tile, 32-wide k-step),
+// so the main kernel moves operands with plain 1-D bulk TMA copies (cp.async.bulk, SASS UBLKCP) -- no tensor maps.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane, 36 tcgen05.mma per k-step), warps 2-5 =
+// epilogue (tcgen05.ld, recombination of the 8 diagonals into u64, optional + Z and fixed-point truncation, store).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_BM = 128;      // rows of A per CTA tile (= UMMA M, one TMEM lane per row)
+constexpr int TC_BN = 64;       // columns of B per CTA tile (= UMMA N); 8 diagonals x 64 = 512 TMEM columns
+constexpr int TC_BK = 32;       // k-step: 32 bytes per limb plane row = UMMA K for 8-bit operands
+constexpr int TC_STAGES = 4;
+constexpr uint32_t A_STAGE_BYTES = 8 * TC_BM * TC_BK;  // 8 limb planes
+constexpr uint32_t B_STAGE_BYTES = 8 * TC_BN * TC_BK;
+constexpr uint32_t A_PLANE_BYTES = TC_BM * TC_BK;
+constexpr uint32_t B_PLANE_BYTES = TC_BN * TC_BK;
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024;
+
+// ---- limb planes in the UMMA canonical layout ------------------------------------------------------------------
+// K-major, SWIZZLE_NONE ("interleave"): in 16-byte units the operand tile is ((8,n),2):((1,SBO),LBO): a core matrix is
+// 8 rows x 16 bytes stored contiguously (128 B), row groups follow at SBO = 128 B, the second 16-byte k-chunk of the
+// 32-byte k-step at LBO = rows * 16 B.  Byte (row r, k-byte kb) of a plane therefore sits at (kb/16 * rows + r) * 16 + kb%16.
+// Global layout: [row block][k-step][limb plane][that plane's tile], so one (row block, k-step) is one contiguous block.
+template <int ROWS>
+__device__ __forceinline__ size_t plane_offset(uint32_t rb, uint32_t ks, uint32_t n_ksteps, uint32_t plane, uint32_t r, uint32_t kb) {
+    return (((size_t)rb * n_ksteps + ks) * 8 + plane) * (size_t)(ROWS * TC_BK) + (size_t)(kb >> 4) * ROWS * 16 + (size_t)r * 16 + (kb & 15);
+}
+
+// A operand: rows = output rows.  src is M x K row-major (or K x M if transA); one thread handles 16 consecutive k of one row
+// and writes 8 x 16 bytes (one per limb plane).  Padding rows / columns are written as zeros.
+__global__ void __launch_bounds__(256) limb_split_rows_kernel(const u64* __restrict__ src, uint8_t* __restrict__ dst, uint32_t M, uint32_t K,
+                                                              uint32_t lda, uint32_t Mpad, uint32_t ks0, uint32_t n_ksteps_total,
+                                                              uint32_t n_ksteps_this, int transA) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t chunks_per_row = n_ksteps_this * 2;  // 16-element chunks
+    if (idx >= (uint64_t)Mpad * chunks_per_row) return;
+    // consecutive threads walk rows (so that 8 threads complete a 128-byte core matrix and stores coalesce)
+    const uint32_t m = (uint32_t)(idx % Mpad), ch = (uint32_t)(idx / Mpad);
+    const uint32_t k0 = ch * 16;
+    uint32_t w[8][4];
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[p][q] = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t k = k0 + j;
+        u64 v = 0;
+        if (m < M && k < K) v = transA ? __ldg(src + (size_t)k * lda + m) : __ldg(src + (size_t)m * lda + k);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) w[p][j >> 2] |= (uint32_t)((v >> (8 * p)) & 0xFF) << (8 * (j & 3));
+    }
+    const uint32_t rb = m / TC_BM, r = m % TC_BM;
+    const uint32_t ks = ks0 + ch / 2, kb = (ch & 1) * 16;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        uint4* out = reinterpret_cast<uint4*>(dst + plane_offset<TC_BM>(rb, ks, n_ksteps_total, p, r, kb));
+        *out = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+    }
+}
+
+// B operand: src is K x N row-major; the UMMA B operand is N x K, K-major.  One thread = one column n, 16 consecutive k.
+__global__ void __launch_bounds__(256) limb_split_cols_kernel(const u64* __restrict__ src, uint8_t* __restrict__ dst, uint32_t K, uint32_t N,
+                                                              uint32_t Npad, uint32_t ks0, uint32_t n_ksteps_total, uint32_t n_ksteps_this) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t chunks = n_ksteps_this * 2;
+    if (idx >= (uint64_t)Npad * chunks) return;
+    const uint32_t n = (uint32_t)(idx % Npad), ch = (uint32_t)(idx / Npad);  // consecutive threads walk n: coalesced reads of B rows
+    const uint32_t k0 = ch * 16;
+    uint32_t w[8][4];
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[p][q] = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t k = k0 + j;
+        u64 v = 0;
+        if (n < N && k < K) v = __ldg(src + (size_t)k * N + n);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) w[p][j >> 2] |= (uint32_t)((v >> (8 * p)) & 0xFF) << (8 * (j & 3));
+    }
+    const uint32_t nb = n / TC_BN, r = n % TC_BN;
+    const uint32_t ks = ks0 + ch / 2, kb = (ch & 1) * 16;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        uint4* out = reinterpret_cast<uint4*>(dst + plane_offset<TC_BN>(nb, ks, n_ksteps_total, p, r, kb));
+        *out = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+    }
+}
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // cute::UMMA::SmemDescriptor: start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46), version = 1 [46,48), layout SWIZZLE_NONE
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           (1ull << 46);
+}
+
+struct TcArgs {
+    const uint8_t* A;  // limb planes, [row block][k-step][plane][tile]
+    const uint8_t* B;
+    const u64* Z;
+    u64* C;
+    uint32_t M, N, n_ksteps;
+    int f, share, accumulate;
+};
+
+__global__ void __launch_bounds__(192, 1) matmul_tc_kernel(const __grid_constant__ TcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], acc_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t mb = blockIdx.y, nb = blockIdx.x;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + TC_STAGES * A_STAGE_BYTES;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(&acc_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {  // TMEM allocation is a warp-wide operation; the same warp frees it at the end
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_smem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint8_t* gA = a.A + (size_t)mb * a.n_ksteps * A_STAGE_BYTES;
+            const uint8_t* gB = a.B + (size_t)nb * a.n_ksteps * B_STAGE_BYTES;
+            for (uint32_t ks = 0; ks < a.n_ksteps; ++ks) {
+                const uint32_t s = ks % TC_STAGES, ph = (ks / TC_STAGES) & 1;
+                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);  // slot free (first round passes immediately)
+                mbar_expect_tx(smem_u32(&full_bar[s]), A_STAGE_BYTES + B_STAGE_BYTES);
+                bulk_g2s(smem_u32(sA + s * A_STAGE_BYTES), gA + (size_t)ks * A_STAGE_BYTES, A_STAGE_BYTES, smem_u32(&full_bar[s]));
+                bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), gB + (size_t)ks * B_STAGE_BYTES, B_STAGE_BYTES, smem_u32(&full_bar[s]));
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one lane issues every tcgen05.mma of the tile =====
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): c = S32 (2) [4,6), a = b = UINT8 (0), K-major both, N>>3 [17,23), M>>4 [24,29)
+            const uint32_t idesc = (2u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            for (uint32_t ks = 0; ks < a.n_ksteps; ++ks) {
+                const uint32_t s = ks % TC_STAGES, ph = (ks / TC_STAGES) & 1;
+                mbar_wait(smem_u32(&full_bar[s]), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = smem_u32(sA + s * A_STAGE_BYTES), b0 = smem_u32(sB + s * B_STAGE_BYTES);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint64_t da = smem_desc(a0 + i * A_PLANE_BYTES, TC_BM * 16, 128);
+#pragma unroll
+                    for (int j = 0; j + i < 8; ++j) {
+                        const uint64_t db = smem_desc(b0 + j * B_PLANE_BYTES, TC_BN * 16, 128);
+                        // the first product landing on a diagonal initialises its accumulator (i == 0 covers every d once)
+                        tc_mma_i8(tmem_base + (uint32_t)(i + j) * TC_BN, da, db, idesc, (ks > 0 || i > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(smem_u32(&empty_bar[s]));  // frees the smem stage once these MMAs have read it
+            }
+            tc_commit(smem_u32(&acc_bar));  // all accumulators final
+        }
+    } else {
+        // ===== epilogue: warps 2..5, one output row per thread (TMEM lane = 32 * (warp % 4) + lane) =====
+        mbar_wait(smem_u32(&acc_bar), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t q = warp & 3;
+        const uint32_t row_in_tile = q * 32 + lane;
+        const uint32_t gm = mb * TC_BM + row_in_tile;
+        const uint32_t lane_addr = tmem_base + ((q * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < TC_BN / 16; ++c) {
+            u64 acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                uint32_t r[16];
+                const uint32_t taddr = lane_addr + (uint32_t)(d * TC_BN + c * 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                      "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] += (u64)r[j] << (8 * d);  // 32-bit wrap of the high diagonals only touches bits >= 64
+            }
+            if (gm < a.M) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t gn = nb * TC_BN + c * 16 + j;
+                    if (gn < a.N) {
+                        const size_t o = (size_t)gm * a.N + gn;
+                        u64 v = acc[j];
+                        if (a.Z) v += a.Z[o];
+                        if (a.accumulate) v += a.C[o];
+                        a.C[o] = trunc_share(v, a.f, a.share);
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+}  // namespace
+
+// One tensor-core launch over a K range that fits the 32-bit diagonal accumulators (n_pairs * K <= 4096).
+static int tc_chunk(cgb_ctx* ctx, const u64* const A[2], const u64* const B[2], int n_pairs, const u64* Z, u64* C, uint32_t M, uint32_t K,
+                    uint32_t lda, uint32_t N, int transA, int accumulate, int f, int share) {
+    const uint32_t ks_pair = (K + TC_BK - 1) / TC_BK;
+    const uint32_t n_ksteps = ks_pair * (uint32_t)n_pairs;
+    CGB_REQUIRE(ctx, (uint64_t)n_ksteps * TC_BK <= 4096, "cgb_matmul_tc: K chunk too long for the 32-bit diagonal accumulators");
+    const uint32_t Mpad = (M + TC_BM - 1) / TC_BM * TC_BM, Npad = (N + TC_BN - 1) / TC_BN * TC_BN;
+    const size_t a_bytes = (size_t)(Mpad / TC_BM) * n_ksteps * A_STAGE_BYTES;
+    const size_t b_bytes = (size_t)(Npad / TC_BN) * n_ksteps * B_STAGE_BYTES;
+    // planes live in their own grow-only buffer (ctx->scratch may hold V + F of the caller)
+    static thread_local struct { void* p; size_t n; int dev; } planes = {nullptr, 0, -1};
+    const size_t need = ((a_bytes + 255) & ~(size_t)255) + b_bytes;
+    if (need > planes.n || planes.dev != ctx->device) {
+        CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (planes.p) cudaFree(planes.p);
+        planes.p = nullptr;
+        planes.n = 0;
+        CGB_CHECK_CUDA(ctx, cudaMalloc(&planes.p, need));
+        planes.n = need;
+        planes.dev = ctx->device;
+    }
+    uint8_t* dA = (uint8_t*)planes.p;
+    uint8_t* dB = dA + ((a_bytes + 255) & ~(size_t)255);
+    for (int p = 0; p < n_pairs; ++p) {
+        const uint64_t ta = (uint64_t)Mpad * ks_pair * 2, tb = (uint64_t)Npad * ks_pair * 2;
+        limb_split_rows_kernel<<<(unsigned)((ta + 255) / 256), 256, 0, ctx->stream>>>(A[p], dA, M, K, lda, Mpad, p * ks_pair, n_ksteps, ks_pair,
+                                                                                     transA);
+        CGB_CHECK_LAUNCH(ctx, "limb_split_rows_kernel");
+        limb_split_cols_kernel<<<(unsigned)((tb + 255) / 256), 256, 0, ctx->stream>>>(B[p], dB, K, N, Npad, p * ks_pair, n_ksteps, ks_pair);
+        CGB_CHECK_LAUNCH(ctx, "limb_split_cols_kernel");
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        CGB_CHECK_CUDA(ctx, cudaFuncSetAttribute(matmul_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+        attr_set = true;
+    }
+    TcArgs a;
+    a.A = dA; a.B = dB; a.Z = Z; a.C = C; a.M = M; a.N = N; a.n_ksteps = n_ksteps;
+    a.f = f; a.share = share; a.accumulate = accumulate;
+    dim3 grid(Npad / TC_BN, Mpad / TC_BM);
+    matmul_tc_kernel<<<grid, 192, TC_SMEM_BYTES, ctx->stream>>>(a);
+    CGB_CHECK_LAUNCH(ctx, "matmul_tc_kernel");
+    return CGB_OK;
+}
+
+// Tensor-core product of up to two (A, B) pairs accumulated into one result (the Beaver finish E*(V[+F]) + U*F), with the
+// same epilogue options as the integer-pipe kernel.  K is processed in chunks that keep the diagonal accumulators exact;
+// the partial results are carried in C (u64), Z is added with the first chunk and the truncation applied with the last.
+int cgb_matmul_tc_run(cgb_ctx* ctx, const u64* const A[2], const u64* const B[2], int n_pairs, const u64* Z, u64* C, uint32_t M,
+                      uint32_t K, uint32_t N, int transA, int accumulate, int f, int share) {
+    const uint32_t kmax = (4096u / (uint32_t)n_pairs) / TC_BK * TC_BK;
+    const uint32_t lda = transA ? M : K;
+    for (uint32_t k0 = 0; k0 < K || k0 == 0; k0 += kmax) {
+        const uint32_t kc = std::min(kmax, K - k0);
+        const bool first = k0 == 0, last = k0 + kc >= K;
+        const u64* Ac[2] = {nullptr, nullptr};
+        const u64* Bc[2] = {nullptr, nullptr};
+        for (int p = 0; p < n_pairs; ++p) {
+            Ac[p] = transA ? A[p] + (size_t)k0 * M : A[p] + k0;
+            Bc[p] = B[p] + (size_t)k0 * N;
+        }
+        int rc = tc_chunk(ctx, Ac, Bc, n_pairs, first ? Z : nullptr, C, M, kc, lda, N, transA, first ? accumulate : 1, last ? f : 0, share);
+        if (rc) return rc;
+        if (last) break;
+    }
+    return CGB_OK;
+}

@@ -180,3 +180,31 @@ def test_prg_stream_is_position_addressable_at_scale(cgb):
 
     assert torch.equal(whole[:cut], a) and torch.equal(whole[cut:], b)
     assert not torch.equal(cgb.prg_fill(key, 100, 5, 1000), whole[:1000])
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 32, 64), (128, 64, 64), (256, 128, 128), (300, 100, 70), (1000, 512, 256),
+                                    (129, 1433, 16), (2048, 4096, 64), (500, 5000, 40)])
+def test_tensor_core_matmul_matches_oracle(cgb, oracle, M, K, N, monkeypatch):
+    """tcgen05 kind::i8 limb path (CGB_MATMUL_IMPL=tc) bit-exact against the oracle, incl. padding in every dimension,
+    K > 4096 (chunked accumulation), transposed storage, accumulate, and the fused Beaver finish."""
+    monkeypatch.setenv("CGB_MATMUL_IMPL", "tc")
+    rng = np.random.default_rng(M + 3 * K + 7 * N)
+    A, B = rand_u64(rng, M, K), rand_u64(rng, K, N)
+    # extreme limbs: all-ones words stress the diagonal accumulators
+    A[0, :] = np.uint64(2**64 - 1)
+    B[:, 0] = np.uint64(2**64 - 1)
+    want = oracle.matmul(A, B)
+    assert np.array_equal(to_np(cgb.matmul(to_dev(A), to_dev(B))), want)
+    At = np.ascontiguousarray(A.T)
+    assert np.array_equal(to_np(cgb.matmul(to_dev(At), to_dev(B), transA=True)), want)
+    C0 = rand_u64(rng, M, N)
+    out = to_dev(C0)
+    cgb.matmul(to_dev(A), to_dev(B), out=out, accumulate=True)
+    assert np.array_equal(to_np(out), oracle.matmul(A, B, C_in=C0))
+    if K <= 2048:
+        E, F, U, V, Z = A, B, rand_u64(rng, M, K), rand_u64(rng, K, N), rand_u64(rng, M, N)
+        for share in (0, 1):
+            for f in (-1, 16):
+                want = oracle.beaver_matmul_finish(E, F, U, V, Z, share, f)
+                got = cgb.beaver_matmul_finish(to_dev(E), to_dev(F), to_dev(U), to_dev(V), to_dev(Z), share, f)
+                assert np.array_equal(to_np(got), want), (share, f)

@@ -95,7 +95,7 @@ def main():
                     ctx.matmul(A, B, out=C)
                 med, best = timed(lambda: ctx.matmul(A, B, out=C), 5, None)
                 macs = M * F * H
-                emit({"kernel": "matmul_u64", "M": M, "K": F, "N": H, "ms_median": med, "ms_best": best,
+                emit({"kernel": "matmul_u64", "impl": os.environ.get("CGB_MATMUL_IMPL", "auto"), "M": M, "K": F, "N": H, "ms_median": med, "ms_best": best,
                       "u64_mac_per_s": macs / (med * 1e-3), "bytes_GBps": 8 * (M * F + F * H + M * H) / (med * 1e-3) / 1e9})
                 del B, C
             del A
