@@ -18,7 +18,7 @@
 int cgb_matmul_tc_run(cgb_ctx* ctx, const u64* const A[2], const u64* const B[2], int n_pairs, const u64* Z, u64* C, uint32_t M,
                       uint32_t K, uint32_t N, int transA, int accumulate, int f, int share);
 #ifndef CGB_MATMUL_AUTO_TC
-#define CGB_MATMUL_AUTO_TC 0  // flipped to 1 once the tensor-core path is the measured winner for N >= 32
+#define CGB_MATMUL_AUTO_TC 1  // the tensor-core path is the measured winner for wide outputs (see run_matmul)
 #endif
 
 namespace {
@@ -166,7 +166,13 @@ int run_matmul(cgb_ctx* ctx, MatmulArgs a) {
         bool tc = false;
         if (impl && !strcmp(impl, "tc")) tc = a.K >= 1;
         else if (impl && !strcmp(impl, "imad")) tc = false;
-        else tc = CGB_MATMUL_AUTO_TC && a.N >= 32 && a.M >= 128 && a.K >= 32;
+        else {
+            // auto (measured, profiles/r1_sweep_matmul_{tc,imad}.jsonl): the tensor pipe wins 3.4-7.4x once the 64-wide
+            // tile is mostly used and there are enough 128 x 64 tiles to fill the machine; small-N outputs (H = 16, C = 7)
+            // and long-K / few-tile weight gradients stay on the integer pipe (split-K)
+            const uint64_t tiles = (uint64_t)((a.M + 127) / 128) * ((a.N + 63) / 64);
+            tc = CGB_MATMUL_AUTO_TC && a.N >= 48 && a.K >= 32 && tiles >= (uint64_t)ctx->num_sms / 2;
+        }
         if (tc) return cgb_matmul_tc_run(ctx, a.A, a.B, a.n_pairs, a.Z, a.C, a.M, a.K, a.N, a.transA, a.accumulate, a.f, a.share);
     }
     constexpr uint32_t BK = 16;
