@@ -47,6 +47,22 @@ def build_shim_demo(force=False):
     return DEMO
 
 
+HARNESS = os.path.join(PKG, "gcn-optimize-b200")
+
+
+def build_harness(force=False):
+    """cognn_b200/host/harness.cpp: the reference's CLI (harness.cpp / harness.h) on top of the engine."""
+    src = os.path.join(HERE, "harness.cpp")
+    deps = [src, os.path.join(HERE, "engine.h"), LIB]
+    if not force and os.path.exists(HARNESS) and all(os.path.getmtime(HARNESS) >= os.path.getmtime(d) for d in deps):
+        return HARNESS
+    cmd = [_cxx(), "-O2", "-g", "-std=c++17", "-Wall", "-Wno-implicit-fallthrough", "-pthread", "-o", HARNESS, src, "-L" + PKG,
+           "-l:libcognn_b200_host.so", "-l:libcognn_b200.so", "-Wl,-rpath,$ORIGIN", "-L/usr/local/cuda/lib64", "-lcudart", "-lnccl"]
+    subprocess.check_call(cmd)
+    return HARNESS
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
     print(build_shim_demo(force="--force" in sys.argv))
+    print(build_harness(force="--force" in sys.argv))
