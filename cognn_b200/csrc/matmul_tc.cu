@@ -11,7 +11,7 @@
 // Data path: a pre-pass writes the limb planes to global memory already in the UMMA canonical (no-swizzle, K-major)
 // shared-memory layout, one contiguous 32 KB (A: 128 rows) / 16 KB (B: 64 columns) block per (tile, 32-wide k-step),
 // so the main kernel moves operands with plain 1-D bulk TMA copies (cp.async.bulk, SASS UBLKCP) -- no tensor maps.
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane, 36 tcgen05.mma per k-step), warps 2-5 =
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane; the 36 limb products of a k-step are issued as 12 tcgen05.mma of N = 64..256), warps 2-5 =
 // epilogue (tcgen05.ld, recombination of the 8 diagonals into u64, optional + Z and fixed-point truncation, store).
 #include <algorithm>
 #include <cstdlib>
@@ -75,6 +75,10 @@ __global__ void __launch_bounds__(256) limb_split_rows_kernel(const u64* __restr
 }
 
 // B operand: src is K x N row-major; the UMMA B operand is N x K, K-major.  One thread = one column n, 16 consecutive k.
+// Inside a (column block, k-step) block the order is [k-chunk][limb plane][column][16 B]: the 8 planes form one 512-row
+// K-major operand, so ONE tcgen05.mma can multiply an A plane with several consecutive B planes (N up to 256) and write
+// the consecutive diagonals' accumulators -- 12 MMAs per k-step instead of 36, each A plane read from smem 1-2 times
+// instead of up to 8.
 __global__ void __launch_bounds__(256) limb_split_cols_kernel(const u64* __restrict__ src, uint8_t* __restrict__ dst, uint32_t K, uint32_t N,
                                                               uint32_t Npad, uint32_t ks0, uint32_t n_ksteps_total, uint32_t n_ksteps_this) {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -99,7 +103,9 @@ __global__ void __launch_bounds__(256) limb_split_cols_kernel(const u64* __restr
     const uint32_t ks = ks0 + ch / 2, kb = (ch & 1) * 16;
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
-        uint4* out = reinterpret_cast<uint4*>(dst + plane_offset<TC_BN>(nb, ks, n_ksteps_total, p, r, kb));
+        const size_t off = ((size_t)nb * n_ksteps_total + ks) * (size_t)(8 * TC_BN * TC_BK) + (size_t)(kb >> 4) * (8 * TC_BN * 16) +
+                           ((size_t)p * TC_BN + r) * 16;
+        uint4* out = reinterpret_cast<uint4*>(dst + off);
         *out = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
     }
 }
@@ -199,7 +205,7 @@ __global__ void __launch_bounds__(192, 1) matmul_tc_kernel(const __grid_constant
         // ===== MMA issuer: one lane issues every tcgen05.mma of the tile =====
         if (lane == 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): c = S32 (2) [4,6), a = b = UINT8 (0), K-major both, N>>3 [17,23), M>>4 [24,29)
-            const uint32_t idesc = (2u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            const uint32_t idesc0 = (2u << 4) | ((uint32_t)(TC_BM >> 4) << 24);
             for (uint32_t ks = 0; ks < a.n_ksteps; ++ks) {
                 const uint32_t s = ks % TC_STAGES, ph = (ks / TC_STAGES) & 1;
                 mbar_wait(smem_u32(&full_bar[s]), ph);
@@ -208,11 +214,15 @@ __global__ void __launch_bounds__(192, 1) matmul_tc_kernel(const __grid_constant
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const uint64_t da = smem_desc(a0 + i * A_PLANE_BYTES, TC_BM * 16, 128);
+                    // A_i times the B planes j = 0 .. 7-i lands on the diagonals i .. 7: consecutive TMEM columns.  One MMA
+                    // covers up to 4 planes (N = 256); plane j of B starts at row j * 64 of the 512-row operand.
 #pragma unroll
-                    for (int j = 0; j + i < 8; ++j) {
-                        const uint64_t db = smem_desc(b0 + j * B_PLANE_BYTES, TC_BN * 16, 128);
-                        // the first product landing on a diagonal initialises its accumulator (i == 0 covers every d once)
-                        tc_mma_i8(tmem_base + (uint32_t)(i + j) * TC_BN, da, db, idesc, (ks > 0 || i > 0) ? 1u : 0u);
+                    for (int j0 = 0; j0 + i < 8; j0 += 4) {
+                        const int planes = (8 - i - j0) < 4 ? (8 - i - j0) : 4;
+                        const uint32_t n = (uint32_t)planes * TC_BN;
+                        const uint64_t db = smem_desc(b0 + (uint32_t)j0 * TC_BN * 16, 8 * TC_BN * 16, 128);
+                        // the products with A_0 touch every diagonal first: they initialise the accumulators at the first k-step
+                        tc_mma_i8(tmem_base + (uint32_t)(i + j0) * TC_BN, da, db, idesc0 | ((n >> 3) << 17), (ks > 0 || i > 0) ? 1u : 0u);
                     }
                 }
                 tc_commit(smem_u32(&empty_bar[s]));  // frees the smem stage once these MMAs have read it
