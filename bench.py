@@ -382,8 +382,23 @@ def main():
     add = lambda a, b, o: ctx.add(a, b, out=o)  # noqa: E731
     fused = P > 1 and args.exchange == "fused"
     piped = P > 1 and args.exchange == "pipelined"
-    win = setup_peer_windows(torch, dist, ctx, rank, P, n_local, D, dev) if (fused or piped) else None
-    pipe = setup_pipelined(torch, ctx, win, rowptr, col, rank, P, n_local, D, dev) if piped else None
+    win = pipe = None
+    if fused or piped:
+        # peer windows need CUDA IPC between the ranks' processes; if the platform refuses it, say so and use the NCCL
+        # all-to-all exchange (same kernels, same result) instead of failing the whole run
+        try:
+            win = setup_peer_windows(torch, dist, ctx, rank, P, n_local, D, dev)
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+        except Exception as ex:  # noqa: BLE001
+            sys.stderr.write(f"[bench] rank {rank}: peer windows unavailable ({ex}); falling back to --exchange nccl\n")
+            ok = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            fused = piped = False
+            win = None
+            config["exchange"] = "gather, then NCCL all_to_all_single of the blocks (peer windows unavailable on this platform)"
+    if piped:
+        pipe = setup_pipelined(torch, ctx, win, rowptr, col, rank, P, n_local, D, dev)
     step_no = [0]
     if fused:
         # self-check outside the timed region: the fused path must equal gather + NCCL all-to-all + sum

@@ -178,3 +178,44 @@ def test_host_entry_points_sync_and_pipelined(cgb, oracle):
     cgb.check(lib.cgb_host_gather_sum(cgb.handle, csr.handle, C.c_void_p(hx[0].data_ptr()), None, C.c_void_p(out.data_ptr()), D))
     assert np.array_equal(out.numpy().view(np.uint64), oracle.gather_sum_csr(rowptr, col, xs[0]))
     csr.destroy()
+
+
+@pytest.mark.parametrize("D", [2, 16, 33])
+def test_gather_sum_chunk_boundaries(cgb, oracle, D):
+    """Rows that start / end exactly on the 64-edge chunk boundaries of the edge-balanced schedule, rows spanning several
+    chunks, runs of empty rows between them, an empty first and last row, and the whole thing repeated with delta."""
+    rng = np.random.default_rng(D)
+    degs = [0, 64, 64, 1, 63, 65, 0, 0, 128, 1, 1, 62, 200, 0, 64, 3, 61, 129, 0, 500, 64, 0]
+    rowptr = np.zeros(len(degs) + 1, dtype=np.uint32)
+    rowptr[1:] = np.cumsum(degs)
+    n_src = 97
+    col = rng.integers(0, n_src, size=int(rowptr[-1])).astype(np.uint32)
+    x, delta = rand_u64(rng, n_src, D), rand_u64(rng, len(degs), D)
+    csr = cgb.csr_create(to_dev(rowptr, "cpu"), to_dev(col, "cpu"), n_src)
+    for dl in (None, delta):
+        want = oracle.gather_sum_csr(rowptr, col, x, dl)
+        for _ in range(3):  # arrival counters must reset themselves between launches
+            got = cgb.gather_sum(csr, to_dev(x), None if dl is None else to_dev(dl))
+            assert np.array_equal(to_np(got), want)
+    csr.destroy()
+
+
+def test_gather_sum_randomised_shapes(cgb, oracle):
+    rng = np.random.default_rng(2024)
+    for trial in range(25):
+        n_dst, n_src = int(rng.integers(1, 400)), int(rng.integers(1, 300))
+        D = int(rng.integers(1, 90))
+        deg = (rng.pareto(0.8, size=n_dst) * rng.integers(0, 6)).astype(np.int64)
+        deg[rng.random(n_dst) < 0.3] = 0
+        rowptr = np.zeros(n_dst + 1, dtype=np.uint32)
+        rowptr[1:] = np.cumsum(np.minimum(deg, 3000))
+        col = rng.integers(0, n_src, size=int(rowptr[-1])).astype(np.uint32)
+        x = rand_u64(rng, n_src, D)
+        delta = rand_u64(rng, n_dst, D) if trial % 2 else None
+        import torch
+
+        dcol = to_dev(col) if col.size else torch.empty(0, dtype=torch.int32, device="cuda")
+        csr = cgb.csr_create(to_dev(rowptr), dcol, n_src)
+        got = cgb.gather_sum(csr, to_dev(x), None if delta is None else to_dev(delta))
+        assert np.array_equal(to_np(got), oracle.gather_sum_csr(rowptr, col, x, delta)), (trial, n_dst, n_src, D)
+        csr.destroy()
