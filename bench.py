@@ -582,6 +582,14 @@ def main():
         val, sample, cores, secs = cpu_sample(torch, rowptr, col, x, D, args.cpu_frac)
         cpu_baseline = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                         "seconds": secs}
+        try:  # the scalar port on one thread, on a tenth of the rows (same access pattern)
+            v1, s1, _, _ = cpu_sample(torch, rowptr, col, x, D, 0.1, reps=2, threads=1, min_seconds=0.0)
+            cpu_baseline["value_1_thread"] = v1
+            cpu_baseline["sample_1_thread"] = s1
+        finally:
+            from oracle import pyoracle as _po
+
+            _po.set_num_threads(cores)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": P, "steps": K, "warmup": W,

@@ -106,3 +106,26 @@ def test_engine_multi_edges_isolated_vertices_and_block_partition():
     for m in o.msgs:
         assert np.array_equal(got[(m[0], m[1], m[2], m[3])], m[4])
     e.close()
+
+
+def test_engine_matches_committed_golden_digests():
+    """The engine against tests/golden/epoch_small.json directly (no oracle run in between)."""
+    import hashlib
+    import json
+    import os
+
+    from cognn_b200 import engine as eng
+    from tests.golden import make_epoch_golden as mk
+
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "epoch_small.json")))
+    for name, edges, tid, T, feats, labels, cfg in mk.cases():
+        e = eng.Engine(T, cfg, record=True)
+        e.load(edges, tid, feats, labels)
+        e.run(6)
+        for p in range(T):
+            for role, rname in ((0, "own"), (1, "hlp")):
+                for l in (0, 1):
+                    got = hashlib.sha256(np.ascontiguousarray(e.download(p, role, f"W{l}")).tobytes()).hexdigest()
+                    assert got == gold[name][f"W{l}.{rname}{p}"], (name, p, role, l)
+        assert len([m for m in e.messages() if not m[3].startswith("setup")]) == gold[name]["n_messages"]
+        e.close()

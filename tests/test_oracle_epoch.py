@@ -67,3 +67,14 @@ def test_message_schedule_two_parties_has_no_update_blocks():
     assert len(o.msgs) == len(o2.msgs)
     for a, b in zip(o.msgs, o2.msgs):
         assert a[:4] == b[:4] and np.array_equal(a[4], b[4])
+
+
+def test_epoch_digests_match_committed_golden():
+    """Regression pin of the frozen semantics (tests/golden/epoch_small.json, made by make_epoch_golden.py)."""
+    from tests.golden import make_epoch_golden as mk
+
+    gold = json.load(open(os.path.join(HERE, "golden", "epoch_small.json")))
+    for name, edges, tid, T, feats, labels, cfg in mk.cases():
+        o = ep.EpochOracle(edges, tid, T, feats, labels, cfg)
+        o.run(6)
+        assert mk.digest(o) == gold[name], name
