@@ -24,7 +24,7 @@ def build(force=False):
                                                        os.path.abspath(__file__)]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
-    cmd = [_cxx(), "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", LIB] + \
+    cmd = [_cxx(), "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-fopenmp", "-o", LIB] + \
           [os.path.join(HERE, s) for s in SOURCES] + \
           ["-I/usr/local/cuda/include", "-L" + PKG, "-l:libcognn_b200.so", "-Wl,-rpath,$ORIGIN",
            "-L/usr/local/cuda/lib64", "-lcudart", "-lnccl"]
@@ -57,7 +57,8 @@ def build_harness(force=False):
     if not force and os.path.exists(HARNESS) and all(os.path.getmtime(HARNESS) >= os.path.getmtime(d) for d in deps):
         return HARNESS
     cmd = [_cxx(), "-O2", "-g", "-std=c++17", "-Wall", "-Wno-implicit-fallthrough", "-pthread", "-o", HARNESS, src, "-L" + PKG,
-           "-l:libcognn_b200_host.so", "-l:libcognn_b200.so", "-Wl,-rpath,$ORIGIN", "-L/usr/local/cuda/lib64", "-lcudart", "-lnccl"]
+           "-l:libcognn_b200_host.so", "-l:libcognn_b200.so", "-Wl,-rpath,$ORIGIN", "-L/usr/local/cuda/lib64", "-lcudart", "-lnccl",
+           "-fopenmp"]
     subprocess.check_call(cmd)
     return HARNESS
 

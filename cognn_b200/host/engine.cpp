@@ -22,8 +22,18 @@
 #include <fstream>
 #include <numeric>
 #include <stdexcept>
+#include <thread>
 
 namespace cognn {
+
+// threads for the host 2PC-residual stand-in (softmax): COGNN_B200_HOST_THREADS, else the cores divided among the parties
+// that share this host (launchers such as torchrun pin OMP_NUM_THREADS=1, which is not meant for this loop)
+static int host_threads(int parties_on_host) {
+    if (const char* e = getenv("COGNN_B200_HOST_THREADS")) return std::max(1, atoi(e));
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(16u, hw / (unsigned)std::max(1, parties_on_host)));
+}
+
 
 // ------------------------------------------------------------------------------------------------------------------
 // errors: the reference prints and exit(-1)s (ssk.h:794-797); library code throws, the C shim maps to exit(-1)
@@ -635,20 +645,28 @@ static void fn_softmax(SSGcnEngine::Impl& im, int owner, const std::vector<std::
     const auto& labels = im.party.at(owner).labels;
     const uint64_t train = (uint64_t)(n * im.cfg.train_ratio);  // gcn.h:560
     out.assign(2, std::vector<uint64_t>((size_t)n * C));
-    std::vector<double> e(C);
-    for (uint32_t i = 0; i < n; ++i) {
+    const int nt = host_threads(im.T);
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (uint32_t i = 0; i < n; ++i) {  // rows are independent: any thread count gives the same bits
+        double e[64];
+        std::vector<double> big;
+        double* ev = e;
+        if (C > 64) {
+            big.resize(C);
+            ev = big.data();
+        }
         double m = -INFINITY;
         for (uint32_t j = 0; j < C; ++j) {
-            e[j] = (double)(int64_t)in[0][(size_t)i * C + j] / scale;
-            if (e[j] > m) m = e[j];
+            ev[j] = (double)(int64_t)in[0][(size_t)i * C + j] / scale;
+            if (ev[j] > m) m = ev[j];
         }
         double tot = 0.0;
         for (uint32_t j = 0; j < C; ++j) {
-            e[j] = std::exp(e[j] - m);
-            tot += e[j];
+            ev[j] = std::exp(ev[j] - m);
+            tot += ev[j];
         }
         for (uint32_t j = 0; j < C; ++j) {
-            const uint64_t pj = (uint64_t)(int64_t)((e[j] / tot) * scale);
+            const uint64_t pj = (uint64_t)(int64_t)((ev[j] / tot) * scale);
             out[0][(size_t)i * C + j] = pj;
             uint64_t d = pj - ((uint32_t)labels[i] == j ? (1ull << im.f) : 0ull);
             if (i >= train) d = 0;  // gcn.h:639-641
@@ -795,7 +813,6 @@ static DMat* sel_Xz0(Side& s, int k) { return k == 0 ? &s.X : &s.z[0]; }
 void SSGcnEngine::run(uint64_t n_iters) {
     Impl& im = *impl_;
     cgb_ctx* ctx = im.ctx;
-    const int T = im.T;
     const uint32_t F = im.F, H = im.H, C = im.C;
     for (uint64_t step = 0; step < n_iters; ++step, ++iter_) {
         const uint64_t it = iter_;
