@@ -50,9 +50,18 @@ def rmat_edges(torch, n_vertices, n_edges, seed, device, a=0.57, b=0.19, c=0.19)
         src = (src << 1) | sbit
         dst = (dst << 1) | dbit
         del r, sbit, dbit
-    # decorrelate ids from degree (RMAT puts the hubs at small ids) with a fixed odd multiplier, then fold
-    src = (src * 2654435761 + 12345) % n_vertices
-    dst = (dst * 2246822519 + 54321) % n_vertices
+    # decorrelate ids from degree before folding (RMAT puts the hubs at small ids AND skews every id bit: 76 % of the
+    # destinations are even, which a `vid % T` partition would turn into a 76/24 load split no real graph has -- Graph500
+    # scrambles labels for the same reason).  A multiply-xorshift mix; a plain odd multiplier keeps the parity skew.
+    def mix(v, c1, c2):
+        m63 = (1 << 63) - 1
+        v = (v * c1) & m63
+        v = v ^ (v >> 31)
+        v = (v * c2) & m63
+        return v ^ (v >> 29)
+
+    src = mix(src, 2654435761, 0x9E3779B97F4A7C15 & ((1 << 63) - 1)) % n_vertices
+    dst = mix(dst + 54321, 2246822519, 0xBF58476D1CE4E5B9 & ((1 << 63) - 1)) % n_vertices
     return src, dst
 
 
@@ -138,16 +147,33 @@ def setup_pipelined(torch, ctx, win, rowptr, col, rank, P, n_local, D, dev):
     stage = torch.empty((P, n_local, D), dtype=torch.int64, device=dev)
     slot_bytes = n_local * D * 8
     peer = [[torch.as_tensor(RawCuda(win["block_ptrs"][k][t], (n_local, D)), device=dev) for t in range(P)] for k in range(2)]
-    return {"csrs": csrs, "stage": stage, "peer": peer, "copy_streams": [torch.cuda.Stream(device=dev) for _ in range(P)],
-            "ev": [torch.cuda.Event() for _ in range(P)], "done": [torch.cuda.Event() for _ in range(P)],
-            "slot_bytes": slot_bytes}
+    copy_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(P)]  # high priority: copy CTAs are placed ahead of the next gather's
+    copy_ctx = []
+    import cognn_b200
+    for t in range(P):  # one context per copy stream: cgb_peer_copy enqueues on its context's stream
+        with torch.cuda.stream(copy_streams[t]):
+            copy_ctx.append(cognn_b200.Context(dev.index))
+    return {"csrs": csrs, "stage": stage, "peer": peer, "copy_streams": copy_streams, "copy_ctx": copy_ctx,
+            "ev": [torch.cuda.Event(enable_timing=True) for _ in range(P)],
+            "done": [torch.cuda.Event(enable_timing=True) for _ in range(P)],
+            "t0": torch.cuda.Event(enable_timing=True), "bar": torch.cuda.Event(enable_timing=True),
+            "end": torch.cuda.Event(enable_timing=True),
+            "slot_bytes": slot_bytes,
+            # transport of the pushes (profiles/r1_p2p_probe_n2.jsonl, r1_bench_n{2,4,8}_*): the SM copy kernel moves
+            # 690 GB/s per GPU against 537 GB/s for the copy engines, but takes SM slots from the gathers beside it.  With
+            # two parties the single push hides under the second gather either way, so the copy engine is used there; from
+            # three parties on the step is NVLink-bound and the faster SM push wins.
+            "copy": os.environ.get("CGB_BENCH_COPY", "sm" if P > 2 else "ce"),
+            "copy_ctas": int(os.environ.get("CGB_BENCH_COPY_CTAS", "64"))}
 
 
 def pipelined_step(torch, dist, ctx, x, win, pipe, step_idx, v, rank, P):
-    """Gather per destination block (remote blocks first), push each finished block to its owner with an async peer copy
-    on a second stream while the next block is gathered; 4-byte all-reduce as barrier; one-pass sum of the received blocks."""
+    """Gather per destination block (remote blocks first), push each finished block to its owner with an SM-driven peer copy
+    (cgb_peer_copy, 64 CTAs of 128 threads) on a side stream while the next block is gathered; 4-byte all-reduce as barrier; one-pass sum of
+    the received blocks."""
     k = step_idx & 1
     main = torch.cuda.current_stream()
+    pipe["t0"].record(main)
     for j in range(1, P + 1):
         t = (rank + j) % P
         if t != rank:
@@ -155,18 +181,34 @@ def pipelined_step(torch, dist, ctx, x, win, pipe, step_idx, v, rank, P):
             pipe["ev"][t].record(main)
             cs = pipe["copy_streams"][t]  # one copy stream per destination: copies to different peers run concurrently
             cs.wait_event(pipe["ev"][t])
-            with torch.cuda.stream(cs):
-                pipe["peer"][k][t].copy_(pipe["stage"][t], non_blocking=True)
+            if pipe["copy"] == "sm":  # SM-driven push: 64 small CTAs saturate the NVLink egress (profiles/r1_p2p_probe_n2.jsonl)
+                pipe["copy_ctx"][t].peer_copy(win["block_ptrs"][k][t], pipe["stage"][t].data_ptr(), pipe["slot_bytes"],
+                                              pipe["copy_ctas"])
+            else:  # copy engine (cudaMemcpyAsync peer copy)
+                with torch.cuda.stream(cs):
+                    pipe["peer"][k][t].copy_(pipe["stage"][t], non_blocking=True)
             pipe["done"][t].record(cs)
         else:
             ctx.gather_sum(pipe["csrs"][t], x, None, out=pipe["peer"][k][t])  # own window, own slot
+            pipe["ev"][t].record(main)
     for t in range(P):
         if t != rank:
             main.wait_event(pipe["done"][t])
     dist.all_reduce(win["flag"])
+    pipe["bar"].record(main)
     blocks = win["views"][k]
     ctx.sum_n([blocks[j] for j in range(P)], out=v)
+    pipe["end"].record(main)
     return v
+
+
+def pipelined_phases(pipe, rank, P):
+    """Timeline of the LAST pipelined step on this rank (ms after the step's start), read after a synchronize."""
+    t0 = pipe["t0"]
+    order = [(rank + j) % P for j in range(1, P + 1)]
+    return {"gather_done": [round(t0.elapsed_time(pipe["ev"][t]), 3) for t in order],
+            "copy_done": [round(t0.elapsed_time(pipe["done"][t]), 3) for t in order if t != rank],
+            "barrier_done": round(t0.elapsed_time(pipe["bar"]), 3), "sum_done": round(t0.elapsed_time(pipe["end"]), 3)}
 
 
 def algorithmic_bytes(n_rows, n_edges, D):
@@ -307,7 +349,8 @@ def main():
         "l2": "inputs larger than L2 (share rows + indices >> 126 MB); no flush needed",
         "seed": 42,
         "exchange": {"pipelined": "one gather per destination party; each finished block is pushed into its owner's window "
-                                  "(CUDA IPC peer memory over NVLink) by an async copy that overlaps the next gather; "
+                                  "(CUDA IPC peer memory over NVLink) by an SM-driven copy kernel (copy engine at 2 parties) that overlaps "
+                                  "the next gather; "
                                   "4-byte all-reduce as barrier; one-pass sum",
                      "fused": "one gather kernel stores each block straight into the consumer's window over NVLink; "
                               "4-byte all-reduce as barrier",
@@ -445,7 +488,8 @@ def main():
     sampler.start()
     time.sleep(0.25)
     barrier()
-    launches0 = ctx.launches
+    all_ctx = [ctx] + (pipe["copy_ctx"] if pipe else [])
+    launches0 = sum(c.launches for c in all_ctx)
     t_wall0 = time.time()
     torch.cuda.profiler.start()  # ncu --profile-from-start off captures exactly the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -479,10 +523,17 @@ def main():
     barrier()
     torch.cuda.profiler.stop()
     t_wall1 = time.time()
-    launches = ctx.launches - launches0
+    launches = sum(c.launches for c in all_ctx) - launches0
     clocks = sampler.stop(t_wall0, t_wall1)
     ms_total = e0.elapsed_time(e1)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / K
+    piped_timeline = None
+    if piped:
+        allp = [None] * P
+        mine = pipelined_phases(pipe, rank, P)
+        mine["edges_per_block_in_gather_order"] = [pipe["csrs"][(rank + j) % P].n_edges for j in range(1, P + 1)]
+        dist.all_gather_object(allp, mine)
+        piped_timeline = allp
     if piped:
         # the P per-destination gather launches of one step, timed on their own (no copies) for the roofline
         ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -598,6 +649,8 @@ def main():
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline}
         if phases:
             line["multi_gpu_phases"] = phases
+        if piped_timeline:
+            line["multi_gpu_phases"] = {"per_rank_last_step_timeline_ms": piped_timeline}
         print(json.dumps(line))
     if P > 1:
         dist.destroy_process_group()

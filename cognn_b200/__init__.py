@@ -128,6 +128,10 @@ class Context:
     def ipc_close(self, ptr):
         self.check(self.lib.cgb_ipc_close(self.handle, C.c_void_p(ptr)))
 
+    def peer_copy(self, dst_ptr, src_ptr, nbytes, n_ctas=0):
+        """SM-driven copy between raw device addresses (ints); either side may be peer memory."""
+        self.check(self.lib.cgb_peer_copy(self.handle, C.c_void_p(int(dst_ptr)), C.c_void_p(int(src_ptr)), nbytes, n_ctas))
+
     def expand_rows(self, idx, x, delta=None, out=None):
         D = x.shape[1]
         n_out = idx.numel()

@@ -50,6 +50,7 @@ SIGNATURES = {
     "cgb_ipc_export": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p]),
     "cgb_ipc_open": (C.c_int, [ctx_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "cgb_ipc_close": (C.c_int, [ctx_p, C.c_void_p]),
+    "cgb_peer_copy": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]),
     "cgb_expand_rows": (C.c_int, [ctx_p, u32p, C.c_uint64, u64p, u64p, u64p, C.c_uint32]),
     "cgb_segsum": (C.c_int, [ctx_p, u32p, C.c_uint32, C.c_uint64, u64p, u64p, C.c_uint32, C.c_int]),
     "cgb_matmul": (C.c_int, [ctx_p, u64p, u64p, u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int]),

@@ -162,6 +162,27 @@ __global__ void __launch_bounds__(EW_THREADS) sum_n_kernel(const SumArgs a, u64*
     }
 }
 
+
+// SM-driven bulk copy.  Either pointer may be PEER memory (another GPU's buffer mapped with cgb_ipc_open): a warp moves
+// 512 contiguous bytes per instruction and every thread keeps eight independent 128-bit loads in flight, so NVLink sees
+// full-size write (push) or read (pull) packets.  CTAs are small (128 threads, few registers) and the grid is small
+// (n_ctas): NVLink saturates long before HBM does, and a 4-warp CTA fits into the slot any finishing gather CTA frees,
+// so the copy overlaps the gather kernels it runs beside instead of queueing behind them.
+constexpr int PC_THREADS = 128;
+constexpr int PC_UNROLL = 8;
+__global__ void __launch_bounds__(PC_THREADS) peer_copy_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, uint64_t n16) {
+    const uint64_t stride = (uint64_t)gridDim.x * PC_THREADS;
+    uint64_t i = (uint64_t)blockIdx.x * PC_THREADS + threadIdx.x;
+    for (; i + (PC_UNROLL - 1) * stride < n16; i += PC_UNROLL * stride) {
+        uint4 v[PC_UNROLL];
+#pragma unroll
+        for (int k = 0; k < PC_UNROLL; ++k) v[k] = __ldcs(src + i + k * stride);
+#pragma unroll
+        for (int k = 0; k < PC_UNROLL; ++k) __stcs(dst + i + k * stride, v[k]);
+    }
+    for (; i < n16; i += stride) dst[i] = src[i];
+}
+
 // 2PC-RESIDUAL stand-ins (ideal functionality on reconstructed values; NOT secure, see the header)
 __global__ void __launch_bounds__(EW_THREADS) ideal_relu_kernel(const u64* a0, const u64* a1, const u64* z0, const u64* z1,
                                                                u64* out, uint64_t n) {
@@ -198,6 +219,18 @@ int cgb_sum_n(cgb_ctx* ctx, const uint64_t* const* d_in, uint32_t n_in, uint64_t
     a.n_in = (int)n_in;
     sum_n_kernel<<<ew_blocks(ctx, vec ? n / 2 : n), EW_THREADS, 0, ctx->stream>>>(a, (u64*)d_out, n, vec);
     CGB_CHECK_LAUNCH(ctx, "sum_n_kernel");
+    return CGB_OK;
+}
+int cgb_peer_copy(cgb_ctx* ctx, void* d_dst, const void* d_src, size_t bytes, uint32_t n_ctas) {
+    CGB_REQUIRE(ctx, (d_dst && d_src) || bytes == 0, "cgb_peer_copy: null argument");
+    CGB_REQUIRE(ctx, aligned16(d_dst) && aligned16(d_src) && (bytes & 15) == 0, "cgb_peer_copy: 16-byte alignment");
+    if (bytes == 0) return CGB_OK;
+    if (n_ctas == 0) n_ctas = 64;
+    const uint64_t n16 = bytes / 16;
+    const uint64_t need = (n16 + PC_THREADS - 1) / PC_THREADS;
+    if (n_ctas > need) n_ctas = (uint32_t)need;
+    peer_copy_kernel<<<n_ctas, PC_THREADS, 0, ctx->stream>>>((const uint4*)d_src, (uint4*)d_dst, n16);
+    CGB_CHECK_LAUNCH(ctx, "peer_copy_kernel");
     return CGB_OK;
 }
 int cgb_trunc(cgb_ctx* ctx, const uint64_t* d_x, uint64_t* d_out, uint64_t n, int f, int share) {

@@ -112,6 +112,10 @@ int cgb_gather_sum_blocks(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x,
 int cgb_ipc_export(cgb_ctx* ctx, void* d_ptr, void* out_handle64);
 int cgb_ipc_open(cgb_ctx* ctx, const void* handle64, void** d_peer_out);
 int cgb_ipc_close(cgb_ctx* ctx, void* d_peer);
+/* SM-driven bulk copy between two device buffers, either of which may be peer memory (cgb_ipc_open): the transport of the
+ * mirror-update exchange where CommSync::sendShareVecVec / recvShareVecVec moved the block over TCP (comm_sync.h:245-277).
+ * n_ctas CTAs of 128 threads (0 = 64); pointers and size must be multiples of 16 bytes. */
+int cgb_peer_copy(cgb_ctx* ctx, void* d_dst, const void* d_src, size_t bytes, uint32_t n_ctas);
 /* OM online, client side: y[j,:] = (idx[j]==CGB_NO_ROW ? 0 : x[idx[j],:]) + (delta ? delta[j,:] : 0) */
 int cgb_expand_rows(cgb_ctx* ctx, const uint32_t* d_idx, uint64_t n_out, const uint64_t* d_x,
                     const uint64_t* d_delta, uint64_t* d_y, uint32_t D);

@@ -219,3 +219,20 @@ def test_gather_sum_randomised_shapes(cgb, oracle):
         got = cgb.gather_sum(csr, to_dev(x), None if delta is None else to_dev(delta))
         assert np.array_equal(to_np(got), oracle.gather_sum_csr(rowptr, col, x, delta)), (trial, n_dst, n_src, D)
         csr.destroy()
+
+
+@pytest.mark.parametrize("n_words,n_ctas", [(2, 0), (254, 1), (2 * 128 * 8 * 3 + 6, 3), (1 << 20, 0), (1_000_002, 64)])
+def test_peer_copy_is_a_copy(cgb, n_words, n_ctas):
+    """cgb_peer_copy (the push / pull transport of the mirror-update exchange) on local buffers: every word arrives, the
+    words beyond the range are untouched, sizes that are not a multiple of the unrolled tile take the tail loop."""
+    import torch
+
+    rng = np.random.default_rng(n_words)
+    src = to_dev(rand_u64(rng, n_words))
+    dst = torch.full((n_words + 4,), -1, dtype=torch.int64, device="cuda")
+    cgb.peer_copy(dst.data_ptr(), src.data_ptr(), n_words * 8, n_ctas)
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:n_words], src)
+    assert bool((dst[n_words:] == -1).all())
+    with pytest.raises(Exception):
+        cgb.peer_copy(dst.data_ptr() + 8, src.data_ptr(), 16, 0)  # 16-byte alignment is part of the contract
