@@ -269,6 +269,18 @@ class Context:
                                                 _ptr(self._u64(z1)), _ptr(out), g0.numel()))
         return out
 
+    def ideal_softmax(self, z0, z1, labels, train_rows, f=SCALER_BITS):
+        n, Cc = z0.shape
+        assert labels.dtype == self.torch.int32 and labels.is_cuda
+        P, pmy = self.torch.empty_like(z0), self.torch.empty_like(z0)
+        self.check(self.lib.cgb_ideal_softmax(self.handle, _ptr(self._u64(z0)), _ptr(self._u64(z1)), _ptr(labels), n, Cc,
+                                              train_rows, f, _ptr(P), _ptr(pmy)))
+        return P, pmy
+
+    def set_prg_stream_bias(self, bias_tensor):
+        """bias_tensor: 1-element cuda int64 tensor (kept alive by the caller) or None."""
+        self.check(self.lib.cgb_ctx_set_prg_stream_bias(self.handle, _ptr(bias_tensor)))
+
     # -- (4) PRG -----------------------------------------------------------------------------------------------
     def prg_fill(self, key, stream, word_offset, n_words, out=None):
         if out is None:

@@ -30,6 +30,7 @@ SIGNATURES = {
     "cgb_ctx_stream": (C.c_void_p, [ctx_p]),
     "cgb_last_error": (C.c_char_p, [ctx_p]),
     "cgb_ctx_launch_count": (C.c_uint64, [ctx_p]),
+    "cgb_ctx_set_prg_stream_bias": (C.c_int, [ctx_p, C.c_void_p]),
     "cgb_malloc": (C.c_int, [ctx_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "cgb_free": (C.c_int, [ctx_p, C.c_void_p]),
     "cgb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -75,6 +76,7 @@ SIGNATURES = {
     "cgb_prg_mask_sub": (C.c_int, [ctx_p, C.POINTER(C.c_uint32), C.c_uint64, C.c_uint64, u64p, u64p, C.c_uint64]),
     "cgb_ideal_relu": (C.c_int, [ctx_p, u64p, u64p, u64p, C.c_uint64]),
     "cgb_ideal_relu_grad": (C.c_int, [ctx_p, u64p, u64p, u64p, u64p, u64p, C.c_uint64]),
+    "cgb_ideal_softmax": (C.c_int, [ctx_p, u64p, u64p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, u64p, u64p]),
     "cgb_host_gather_sum": (C.c_int, [ctx_p, csr_p, u64p, u64p, u64p, C.c_uint32]),
     "cgb_host_gather_sum_async": (C.c_int, [ctx_p, csr_p, u64p, u64p, u64p, C.c_uint32]),
     "cgb_host_sync": (C.c_int, [ctx_p]),

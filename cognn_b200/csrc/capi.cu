@@ -106,6 +106,11 @@ int cgb_ctx_sync(cgb_ctx* ctx) {
 void* cgb_ctx_stream(cgb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 const char* cgb_last_error(cgb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
 uint64_t cgb_ctx_launch_count(cgb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int cgb_ctx_set_prg_stream_bias(cgb_ctx* ctx, const uint64_t* d_bias) {
+    CGB_REQUIRE(ctx, ctx != nullptr, "cgb_ctx_set_prg_stream_bias: null context");
+    ctx->prg_bias = d_bias;
+    return CGB_OK;
+}
 
 int cgb_malloc(cgb_ctx* ctx, size_t bytes, void** d_out) {
     CGB_REQUIRE(ctx, d_out, "cgb_malloc: null argument");

@@ -14,6 +14,9 @@ struct cgb_ctx {
     int num_sms = 148;
     std::string err;
     uint64_t launches = 0;
+    // device word added to the stream id of every PRG launch (cgb_ctx_set_prg_stream_bias): lets a captured CUDA graph
+    // draw fresh randomness at every replay
+    const uint64_t* prg_bias = nullptr;
     // grow-only device scratch (split-K accumulators, Beaver temporaries)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;

@@ -194,6 +194,54 @@ __global__ void __launch_bounds__(EW_THREADS) ideal_relu_kernel(const u64* a0, c
     }
 }
 
+// exp() from IEEE-754 double +, -, * with explicit round-to-nearest intrinsics (never contracted into FMA), bit-identical
+// to orc_det_exp of the CPU oracle: k = floor(x log2e + 1/2), r = (x - k ln2_hi) - k ln2_lo, 13th-order Horner, times 2^k
+__device__ __forceinline__ double det_exp(double x) {
+    if (x < -700.0) return 0.0;
+    if (x > 700.0) x = 700.0;
+    const double t = __dadd_rn(__dmul_rn(x, 0x1.71547652b82fep+0), 0.5);
+    long long k = __double2ll_rz(t);
+    if (__ll2double_rn(k) > t) k -= 1;
+    const double kd = __ll2double_rn(k);
+    const double r = __dsub_rn(__dsub_rn(x, __dmul_rn(kd, 0x1.62e42fee00000p-1)), __dmul_rn(kd, 0x1.a39ef35793c76p-33));
+    const double c[14] = {0x1.0000000000000p+0, 0x1.0000000000000p+0, 0x1.0000000000000p-1, 0x1.5555555555555p-3,
+                          0x1.5555555555555p-5, 0x1.1111111111111p-7, 0x1.6c16c16c16c17p-10, 0x1.a01a01a01a01ap-13,
+                          0x1.a01a01a01a01ap-16, 0x1.71de3a556c734p-19, 0x1.27e4fb7789f5cp-22, 0x1.ae64567f544e4p-26,
+                          0x1.1eed8eff8d898p-29, 0x1.6124613a86d09p-33};
+    double p = c[13];
+#pragma unroll
+    for (int i = 12; i >= 0; --i) p = __dadd_rn(__dmul_rn(p, r), c[i]);
+    return __dmul_rn(p, __longlong_as_double((k + 1023) << 52));
+}
+// one thread per vertex row (C = number of classes, 3..40 on the named graphs): softmax of the reconstructed logits,
+// P = enc(p), pmy = P - onehot (training rows only, gcn.h:639-641)
+__global__ void __launch_bounds__(EW_THREADS) ideal_softmax_kernel(const u64* __restrict__ z0, const u64* __restrict__ z1,
+                                                                  const int32_t* __restrict__ labels, u64* __restrict__ P,
+                                                                  u64* __restrict__ pmy, uint64_t n, uint32_t C,
+                                                                  uint64_t train_rows, int f) {
+    const double scale = (double)(1ull << f);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u64* a = z0 + i * C;
+        const u64* b = z1 + i * C;
+        double m = 0.0;
+        for (uint32_t j = 0; j < C; ++j) {
+            const double v = __ddiv_rn(__ll2double_rn((long long)(a[j] + b[j])), scale);
+            if (j == 0 || v > m) m = v;
+        }
+        double tot = 0.0;
+        for (uint32_t j = 0; j < C; ++j)
+            tot = __dadd_rn(tot, det_exp(__dsub_rn(__ddiv_rn(__ll2double_rn((long long)(a[j] + b[j])), scale), m)));
+        const uint32_t lab = (uint32_t)labels[i];
+        for (uint32_t j = 0; j < C; ++j) {
+            const double e = det_exp(__dsub_rn(__ddiv_rn(__ll2double_rn((long long)(a[j] + b[j])), scale), m));
+            const u64 pj = (u64)__double2ll_rz(__dmul_rn(__ddiv_rn(e, tot), scale));
+            P[i * C + j] = pj;
+            pmy[i * C + j] = i < train_rows ? pj - (lab == j ? (1ull << f) : 0ull) : 0ull;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -296,6 +344,16 @@ int cgb_ideal_relu_grad(cgb_ctx* ctx, const uint64_t* d_g0, const uint64_t* d_g1
     ideal_relu_kernel<<<ew_blocks(ctx, n), EW_THREADS, 0, ctx->stream>>>((const u64*)d_g0, (const u64*)d_g1, (const u64*)d_z0,
                                                                         (const u64*)d_z1, (u64*)d_out, n);
     CGB_CHECK_LAUNCH(ctx, "ideal_relu_kernel");
+    return CGB_OK;
+}
+int cgb_ideal_softmax(cgb_ctx* ctx, const uint64_t* d_z0, const uint64_t* d_z1, const int32_t* d_labels, uint64_t n,
+                      uint32_t C, uint64_t train_rows, int f, uint64_t* d_P, uint64_t* d_pmy) {
+    CGB_REQUIRE(ctx, (d_z0 && d_z1 && d_labels && d_P && d_pmy) || n == 0, "cgb_ideal_softmax: null argument");
+    CGB_REQUIRE(ctx, C > 0 && f > 0 && f < 63, "cgb_ideal_softmax: bad C/f");
+    if (n == 0) return CGB_OK;
+    ideal_softmax_kernel<<<ew_blocks(ctx, n), EW_THREADS, 0, ctx->stream>>>((const u64*)d_z0, (const u64*)d_z1, d_labels,
+                                                                           (u64*)d_P, (u64*)d_pmy, n, C, train_rows, f);
+    CGB_CHECK_LAUNCH(ctx, "ideal_softmax_kernel");
     return CGB_OK;
 }
 int cgb_encode(cgb_ctx* ctx, const double* d_x, uint64_t* d_out, uint64_t n, int f) {

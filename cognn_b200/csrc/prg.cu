@@ -25,9 +25,10 @@ constexpr int PRG_THREADS = 128;  // 4 warps, 32 blocks (2 KB) each
 
 // MODE 0: out = ks;  MODE 1: out = in - ks
 template <int MODE>
-__global__ void __launch_bounds__(PRG_THREADS) prg_kernel(const Key key, uint64_t stream, uint64_t word_offset,
-                                                         const u64* in, u64* out, uint64_t n_words,
+__global__ void __launch_bounds__(PRG_THREADS) prg_kernel(const Key key, uint64_t stream, const u64* __restrict__ stream_bias,
+                                                         uint64_t word_offset, const u64* in, u64* out, uint64_t n_words,
                                                          uint64_t first_blk, uint64_t n_blks) {
+    if (stream_bias) stream += __ldg(stream_bias);
     __shared__ uint32_t stage[PRG_THREADS / 32][32][17];  // +1 word padding: conflict-free column reads
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t warps_total = (uint64_t)gridDim.x * (PRG_THREADS / 32);
@@ -84,11 +85,11 @@ int launch_prg(cgb_ctx* ctx, int mode, const uint32_t key[8], uint64_t stream, u
     const uint64_t cap = (uint64_t)ctx->num_sms * 16;
     if (blocks > cap) blocks = cap;
     if (mode == 0)
-        prg_kernel<0><<<(unsigned)blocks, PRG_THREADS, 0, ctx->stream>>>(k, stream, word_offset, in, out, n_words,
-                                                                        first_blk, n_blks);
+        prg_kernel<0><<<(unsigned)blocks, PRG_THREADS, 0, ctx->stream>>>(k, stream, (const u64*)ctx->prg_bias, word_offset, in,
+                                                                        out, n_words, first_blk, n_blks);
     else
-        prg_kernel<1><<<(unsigned)blocks, PRG_THREADS, 0, ctx->stream>>>(k, stream, word_offset, in, out, n_words,
-                                                                        first_blk, n_blks);
+        prg_kernel<1><<<(unsigned)blocks, PRG_THREADS, 0, ctx->stream>>>(k, stream, (const u64*)ctx->prg_bias, word_offset, in,
+                                                                        out, n_words, first_blk, n_blks);
     CGB_CHECK_LAUNCH(ctx, "prg_kernel");
     return CGB_OK;
 }

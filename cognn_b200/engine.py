@@ -22,7 +22,7 @@ class CgeConfig(C.Structure):
 ENGINE_SYMBOLS = ["cge_last_error", "cge_nccl_unique_id", "cge_create_loopback", "cge_create_nccl", "cge_destroy",
                   "cge_add_party", "cge_setup", "cge_run", "cge_download", "cge_message_count", "cge_message_info",
                   "cge_message_data", "cge_words_sent", "cge_rounds", "cge_launch_count", "cge_seconds_online", "cge_seconds_offline", "cge_seconds_residual_host",
-                  "cge_metrics_count", "cge_metrics_get", "cge_build_party_graph"]
+                  "cge_metrics_count", "cge_metrics_get", "cge_build_party_graph", "cge_graph_replays"]
 
 
 def load_host():
@@ -38,7 +38,7 @@ def load_host():
     h.cge_download.restype = C.c_int64
     h.cge_download.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32),
                                C.POINTER(C.c_uint32)]
-    for n in ("cge_message_count", "cge_words_sent", "cge_rounds", "cge_launch_count", "cge_metrics_count"):
+    for n in ("cge_message_count", "cge_words_sent", "cge_rounds", "cge_launch_count", "cge_metrics_count", "cge_graph_replays"):
         getattr(h, n).restype = C.c_uint64
         getattr(h, n).argtypes = [C.c_void_p]
     for n in ("cge_seconds_online", "cge_seconds_offline", "cge_seconds_residual_host"):
@@ -187,6 +187,10 @@ class Engine:
     @property
     def launches(self):
         return int(self.h.cge_launch_count(self.e))
+
+    @property
+    def graph_replays(self):
+        return int(self.h.cge_graph_replays(self.e))
 
     def close(self):
         if self.e is not None:

@@ -13,6 +13,8 @@
 // the HOST lets an epoch run end to end (not secure, not accelerated).
 #include "engine.h"
 
+#include <cuda_runtime.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -26,13 +28,8 @@
 
 namespace cognn {
 
-// threads for the host 2PC-residual stand-in (softmax): COGNN_B200_HOST_THREADS, else the cores divided among the parties
-// that share this host (launchers such as torchrun pin OMP_NUM_THREADS=1, which is not meant for this loop)
-static int host_threads(int parties_on_host) {
-    if (const char* e = getenv("COGNN_B200_HOST_THREADS")) return std::max(1, atoi(e));
-    const unsigned hw = std::thread::hardware_concurrency();
-    return (int)std::max(1u, std::min(16u, hw / (unsigned)std::max(1, parties_on_host)));
-}
+// true while the online phase of an iteration is being recorded into a CUDA graph: nothing may allocate or synchronise
+static thread_local bool g_capturing = false;
 
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -157,6 +154,7 @@ struct DMat {
         ctx = c;
         const size_t need = (size_t)r * cl;
         if (need > cap) {
+            if (g_capturing) throw std::runtime_error("engine: a device buffer grew while an iteration was being captured");
             // buffers may still be read by queued kernels: the stream is in order, and cudaFree synchronises
             release();
             void* q = nullptr;
@@ -176,8 +174,11 @@ struct DMat {
 // PRG stream ids (DESIGN.md "Randomness"); must match oracle/epoch.py
 enum Kind : uint64_t { K_FEAT = 1, K_WEIGHT, K_OM_R, K_OM_S, K_MM_U0, K_MM_U1, K_MM_V0, K_MM_V1, K_MM_Z0,
                        K_RM_A0, K_RM_A1, K_RM_B0, K_RM_B1, K_RM_C0, K_RESHARE };
+// The engine passes the id of iteration (it % 6); the epoch part ((it - it % 6) << 16) sits in a device word that every
+// PRG kernel adds (cgb_ctx_set_prg_stream_bias), so that the captured graph of an iteration can be replayed in later
+// epochs.  Sum = (kind << 48) | (it << 16) | (owner << 8) | sub as long as it < 2^32.
 static uint64_t stream_id(uint64_t kind, uint64_t it, uint64_t owner, uint64_t sub) {
-    return (kind << 48) | (it << 16) | (owner << 8) | sub;
+    return (kind << 48) | ((it % 6) << 16) | (owner << 8) | sub;
 }
 
 // one share-side of one owner's state: share 0 lives on the owner, share 1 on its primary helper (owner + 1) % T
@@ -190,7 +191,10 @@ struct Side {
     // dealer correlations of the current iteration (offline phase), indexed by `sub`
     DMat mmU[2], mmV[2], mmZ[2], rmA[2], rmB[2], rmC[2];
     DMat mm_mine, mm_peer, rm_mine, rm_peer;
-    DMat res_in, res_plain, P, Ppeer, grad;
+    DMat res_in, res_plain, res_plain2, P, Ppeer, grad;
+    DMat prob;                    // opened predictions as doubles (bit pattern in u64 words), owner side
+    double* h_prob = nullptr;     // pinned host copy, read after the iteration's synchronise
+    size_t h_prob_cap = 0;
     std::vector<DMat> upd_recv;  // helper side: masked sums received from the other owners
     DMat delta, S;
 };
@@ -200,6 +204,7 @@ struct PartyData {
     cgb_csr* csr = nullptr;
     DMat norm;  // enc((inDeg+1)^-1/2), private to the owner
     std::vector<int32_t> labels;
+    int32_t* d_labels = nullptr;
     std::vector<double> feats;  // normalised, n x F
 };
 
@@ -215,6 +220,32 @@ struct SSGcnEngine::Impl {
     std::map<int, Side> own, hlp;
     std::vector<uint32_t> n_of;  // vertices per party (global knowledge: the partition file is public)
     uint64_t lr_fixed = 0;
+
+    // epoch part of the PRG stream ids, on the device (see stream_id): written before every iteration
+    uint64_t* d_bias = nullptr;
+    uint64_t* h_bias = nullptr;  // pinned
+    // CUDA graphs of the online phase, one per iteration index in the epoch (it % 6).  Epoch 0 runs eagerly (buffers
+    // grow to their final sizes), the first later occurrence of an iteration index is captured, then replayed: the
+    // named graphs are launch-bound (300-600 launches of a few microseconds each per epoch).  COGNN_B200_GRAPHS=0
+    // switches it off; recording the message transcript or profiling phases needs the eager path as well.
+    bool graphs_enabled = !(getenv("COGNN_B200_GRAPHS") && atoi(getenv("COGNN_B200_GRAPHS")) == 0);
+    struct IterGraph {
+        cudaGraphExec_t exec = nullptr;
+        uint64_t launches = 0, words = 0, rounds = 0;
+        std::vector<std::pair<uint32_t, uint32_t>> shapes;  // rows x cols of every side tensor after this iteration
+    } graph[6];
+    // the host-side shape of every tensor a side holds: a replayed graph changes the contents but runs no host code, so
+    // the shapes recorded when the iteration was captured are put back (device pointers never change after epoch 0)
+    template <typename Fn>
+    void for_side_mats(Fn&& fn) {
+        for_sides([&](Side& s) {
+            DMat* mats[] = {&s.X, &s.X_backup, &s.W[0], &s.W[1], &s.h_t[0], &s.h_t[1], &s.z[0], &s.z[1], &s.g, &s.Xp, &s.V,
+                            &s.Y, &s.m, &s.tmp, &s.tmp2, &s.P, &s.Ppeer, &s.grad, &s.prob, &s.res_in, &s.res_plain, &s.res_plain2};
+            for (DMat* m : mats) fn(*m);
+        });
+    }
+    uint64_t replayed_launches = 0, graph_replays = 0, graph_captures = 0;
+    std::vector<int> metrics_pending;  // owners whose opened predictions sit in h_prob until the iteration's synchronise
 
     // per-phase wall time under the reference's print_duration tags (ssk.h:745,765,802,808,822,856,881,897); only when
     // CGB_ENGINE_PROFILE is set, because it synchronises the stream at every tick
@@ -372,13 +403,9 @@ struct SSGcnEngine::Impl {
         comm->exchange();
         for_sides([&](Side& s) {
             DMat& x = getx(s);
-            DMat& o = getout(s);
-            if (&o == &x) {
-                rm_finish(s, sub, x.rows, x.cols, s.tmp);
-                std::swap(s.tmp, x);
-            } else {
-                rm_finish(s, sub, x.rows, x.cols, o);
-            }
+            // rm_finish reads only the opened message and the triple, never x, so the result may land in x itself; buffers
+            // are never swapped, which keeps every device pointer stable across iterations (CUDA-graph replays rely on it)
+            rm_finish(s, sub, x.rows, x.cols, getout(s));
         });
     }
 
@@ -488,14 +515,11 @@ struct SSGcnEngine::Impl {
         });
     }
 
-    // ---- 2PC-RESIDUAL stand-in (ideal functionality on the host; NOT secure, NOT accelerated) ----------------------
-    // helper sends its shares; the owner evaluates fn on the reconstructed values on the host and re-shares: the
-    // helper's new share is a PRG stream both know from the dealer, the owner's is fn(x) - PRG.
-    typedef void (*ResidualFn)(Impl&, int owner, const std::vector<std::vector<uint64_t>>& in,
-                               std::vector<std::vector<uint64_t>>& out);
-    double seconds_residual_host = 0;
-    void residual(uint64_t it, ResidualFn fn, int n_in, int n_out, DMat* (*in_sel)(Side&, int), DMat* (*out_sel)(Side&, int),
-                  int dev_kind = 0) {
+    // ---- 2PC-RESIDUAL stand-in (ideal functionality; NOT secure, NOT the reference's protocol) ----------------------------
+    // helper sends its shares; the owner evaluates the function on the reconstructed values ON THE DEVICE (cgb_ideal_*:
+    // exact integer ReLU / ReLU', softmax in IEEE doubles with a restated exp) and re-shares: the helper's new share is a
+    // PRG stream both know from the dealer, the owner's is fn(x) - PRG.  kind: 1 = ReLU, 2 = ReLU' mask, 3 = softmax, p - y.
+    void residual(uint64_t it, int kind, int n_in, int n_out, DMat* (*in_sel)(Side&, int), DMat* (*out_sel)(Side&, int)) {
         for_sides([&](Side& s) {
             size_t total = 0;
             for (int i = 0; i < n_in; ++i) total += in_sel(s, i)->n();
@@ -514,44 +538,25 @@ struct SSGcnEngine::Impl {
         });
         comm->exchange();
         for_sides([&](Side& s) {
-            std::vector<std::pair<uint32_t, uint32_t>> shapes;
-            if (s.share == 0 && dev_kind != 0) {
-                // exact integer stand-ins evaluated on the device (cgb_ideal_relu*): no host round trip
-                DMat* o = out_sel(s, 0);
+            if (s.share == 0) {
                 DMat* a = in_sel(s, 0);
-                s.res_plain.resize(ctx, a->rows, a->cols);
-                if (dev_kind == 1)
+                DMat* plain[2] = {&s.res_plain, &s.res_plain2};
+                for (int k = 0; k < n_out; ++k) plain[k]->resize(ctx, a->rows, a->cols);
+                if (kind == 1) {
                     ck(ctx, cgb_ideal_relu(ctx, a->p, s.res_in.p, s.res_plain.p, a->n()), "cgb_ideal_relu");
-                else
+                } else if (kind == 2) {
                     ck(ctx, cgb_ideal_relu_grad(ctx, a->p, s.res_in.p, in_sel(s, 1)->p, s.res_in.p + a->n(), s.res_plain.p, a->n()),
                        "cgb_ideal_relu_grad");
-                o->resize(ctx, a->rows, a->cols);
-                ck(ctx, cgb_prg_mask_sub(ctx, key, stream_id(K_RESHARE, it, s.owner, 0), 0, s.res_plain.p, o->p, o->n()), "reshare");
-            } else if (s.share == 0) {
-                auto th0 = std::chrono::high_resolution_clock::now();
-                std::vector<std::vector<uint64_t>> in(n_in), out;
-                size_t off = 0;
-                std::vector<uint64_t> peer(s.res_in.n());
-                ck(ctx, cgb_d2h(ctx, peer.data(), s.res_in.p, peer.size() * 8), "d2h");
-                for (int i = 0; i < n_in; ++i) {
-                    DMat* m = in_sel(s, i);
-                    in[i].resize(m->n());
-                    ck(ctx, cgb_d2h(ctx, in[i].data(), m->p, m->n() * 8), "d2h");
+                } else {
+                    const uint64_t train = (uint64_t)(s.n * cfg.train_ratio);  // gcn.h:560
+                    ck(ctx, cgb_ideal_softmax(ctx, a->p, s.res_in.p, party.at(s.owner).d_labels, a->rows, a->cols, train, f,
+                                              s.res_plain.p, s.res_plain2.p), "cgb_ideal_softmax");
                 }
-                ck(ctx, cgb_ctx_sync(ctx), "sync");
-                for (int i = 0; i < n_in; ++i) {
-                    for (size_t j = 0; j < in[i].size(); ++j) in[i][j] += peer[off + j];
-                    off += in[i].size();
-                }
-                fn(*this, s.owner, in, out);
                 for (int k = 0; k < n_out; ++k) {
                     DMat* o = out_sel(s, k);
-                    s.res_plain.resize(ctx, o->rows, o->cols);
-                    ck(ctx, cgb_h2d(ctx, s.res_plain.p, out[k].data(), out[k].size() * 8), "h2d");
-                    ck(ctx, cgb_prg_mask_sub(ctx, key, stream_id(K_RESHARE, it, s.owner, k), 0, s.res_plain.p, o->p, o->n()), "reshare");
-                    ck(ctx, cgb_ctx_sync(ctx), "sync");  // out[k] is a pageable host vector about to die
+                    o->resize(ctx, a->rows, a->cols);
+                    ck(ctx, cgb_prg_mask_sub(ctx, key, stream_id(K_RESHARE, it, s.owner, k), 0, plain[k]->p, o->p, o->n()), "reshare");
                 }
-                seconds_residual_host += std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - th0).count();
             } else {
                 for (int k = 0; k < n_out; ++k) {
                     DMat* o = out_sel(s, k);
@@ -562,10 +567,14 @@ struct SSGcnEngine::Impl {
     }
 
     // ---- weight averaging (gcn.h:747-802): reduce to parties 0 and 1, public scale 1/T, redistribute ---------------
-    void weight_average(uint64_t it, int layer) {
+    // receive buffers and the averages live in the sides (grow-only), so the online phase never allocates
+    std::map<int, DMat> wa_rx_own[2], wa_rx_hlp[2], wa_rxA0[2], wa_rxA1[2];
+    DMat wa_A0[2], wa_A1[2];
+    void weight_average(uint64_t, int layer) {
         if (T == 1) return;
         char tg[64];
-        std::map<int, DMat> rx_own, rx_hlp;  // at party 1: W0_i of i >= 2; at party 0: W1_{i-1}
+        auto& rx_own = wa_rx_own[layer];  // at party 1: W0_i of i >= 2
+        auto& rx_hlp = wa_rx_hlp[layer];  // at party 0: W1_{i-1}
         for (int i = 2; i < T; ++i) {
             if (Side* s = side(i, 0)) {
                 snprintf(tg, sizeof tg, "w%d.own%d", layer, i);
@@ -586,7 +595,8 @@ struct SSGcnEngine::Impl {
         }
         comm->exchange();
         const uint64_t c = (uint64_t)(int64_t)((1.0 / T) * (double)(1ull << f));  // gcn.h:763-764
-        DMat A0, A1;
+        DMat& A0 = wa_A0[layer];
+        DMat& A1 = wa_A1[layer];
         if (comm->is_local(0)) {
             DMat& w = own.at(0).W[layer];
             A0.copy_from(w);
@@ -601,7 +611,8 @@ struct SSGcnEngine::Impl {
             vadd(A1.p, hlp.at(0).W[layer].p, A1.p, A1.n());
             ck(ctx, cgb_scale_public(ctx, A1.p, c, A1.p, A1.n(), f, 1), "scale");
         }
-        std::map<int, DMat> rxA1, rxA0;
+        auto& rxA1 = wa_rxA1[layer];
+        auto& rxA0 = wa_rxA0[layer];
         for (int i = 2; i < T; ++i) {
             snprintf(tg, sizeof tg, "wavg%d.A1", layer);
             if (comm->is_local(1)) comm->post_send(1, i, A1.p, A1.n(), tg);
@@ -624,56 +635,8 @@ struct SSGcnEngine::Impl {
             own.at(p).W[layer].copy_from(local_w);
             hlp.at((p - 1 + T) % T).W[layer].copy_from(remote_w);  // this party's remoteWeight
         }
-        ck(ctx, cgb_ctx_sync(ctx), "sync");
     }
 };
-
-// ---- host residual functions (bit-identical to oracle/epoch.py; glibc exp, left-to-right sums) ---------------------
-static void fn_relu(SSGcnEngine::Impl&, int, const std::vector<std::vector<uint64_t>>& in, std::vector<std::vector<uint64_t>>& out) {
-    out.assign(1, in[0]);
-    for (auto& v : out[0])
-        if ((int64_t)v <= 0) v = 0;
-}
-static void fn_relu_grad(SSGcnEngine::Impl&, int, const std::vector<std::vector<uint64_t>>& in, std::vector<std::vector<uint64_t>>& out) {
-    out.assign(1, in[0]);  // in[0] = g, in[1] = z
-    for (size_t i = 0; i < out[0].size(); ++i)
-        if ((int64_t)in[1][i] <= 0) out[0][i] = 0;
-}
-static void fn_softmax(SSGcnEngine::Impl& im, int owner, const std::vector<std::vector<uint64_t>>& in, std::vector<std::vector<uint64_t>>& out) {
-    const uint32_t n = im.n_of[owner], C = im.C;
-    const double scale = (double)(1ull << im.f);
-    const auto& labels = im.party.at(owner).labels;
-    const uint64_t train = (uint64_t)(n * im.cfg.train_ratio);  // gcn.h:560
-    out.assign(2, std::vector<uint64_t>((size_t)n * C));
-    const int nt = host_threads(im.T);
-#pragma omp parallel for num_threads(nt) schedule(static)
-    for (uint32_t i = 0; i < n; ++i) {  // rows are independent: any thread count gives the same bits
-        double e[64];
-        std::vector<double> big;
-        double* ev = e;
-        if (C > 64) {
-            big.resize(C);
-            ev = big.data();
-        }
-        double m = -INFINITY;
-        for (uint32_t j = 0; j < C; ++j) {
-            ev[j] = (double)(int64_t)in[0][(size_t)i * C + j] / scale;
-            if (ev[j] > m) m = ev[j];
-        }
-        double tot = 0.0;
-        for (uint32_t j = 0; j < C; ++j) {
-            ev[j] = std::exp(ev[j] - m);
-            tot += ev[j];
-        }
-        for (uint32_t j = 0; j < C; ++j) {
-            const uint64_t pj = (uint64_t)(int64_t)((ev[j] / tot) * scale);
-            out[0][(size_t)i * C + j] = pj;
-            uint64_t d = pj - ((uint32_t)labels[i] == j ? (1ull << im.f) : 0ull);
-            if (i >= train) d = 0;  // gcn.h:639-641
-            out[1][(size_t)i * C + j] = d;
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------------------------
 SSGcnEngine::SSGcnEngine(Comm* comm, const GNNConfig& cfg, int f, const uint32_t key[8]) {
@@ -689,17 +652,34 @@ SSGcnEngine::SSGcnEngine(Comm* comm, const GNNConfig& cfg, int f, const uint32_t
     impl_->C = cfg.num_labels;
     if (cfg.num_layers != 2) throw std::runtime_error("SSGcnEngine: the reference operators hard-code 2 layers (gcn.h:898-927)");
     if (f <= 0 || f >= 31) throw std::runtime_error("SSGcnEngine: SCALER_BIT_LENGTH must be in (0, 31) (gcn.h:191)");
+    cgb_ctx* ctx = impl_->ctx;
+    void* p = nullptr;
+    ck(ctx, cgb_malloc(ctx, 8, &p), "cgb_malloc");
+    impl_->d_bias = (uint64_t*)p;
+    if (cgb_host_alloc(8, &p) != CGB_OK) throw std::runtime_error("SSGcnEngine: pinned allocation failed");
+    impl_->h_bias = (uint64_t*)p;
+    *impl_->h_bias = 0;
+    ck(ctx, cgb_memset(ctx, impl_->d_bias, 0, 8), "memset");
+    ck(ctx, cgb_ctx_set_prg_stream_bias(ctx, impl_->d_bias), "cgb_ctx_set_prg_stream_bias");
+    ck(ctx, cgb_ctx_sync(ctx), "sync");
 }
 
 SSGcnEngine::~SSGcnEngine() {
     if (!impl_) return;
     cgb_ctx_sync(impl_->ctx);
-    if (impl_->profile) {
+    if (impl_->profile)
         for (auto& kv : impl_->phase_s) fprintf(stderr, "::%s took %lf seconds (all iterations)\n", kv.first.c_str(), kv.second);
-        fprintf(stderr, "::residual host stand-in took %lf seconds\n", impl_->seconds_residual_host);
-    }
-    for (auto& kv : impl_->party)
+    for (auto& g : impl_->graph)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    cgb_ctx_set_prg_stream_bias(impl_->ctx, nullptr);
+    cgb_free(impl_->ctx, impl_->d_bias);
+    cgb_host_free(impl_->h_bias);
+    for (auto& kv : impl_->own)
+        if (kv.second.h_prob) cgb_host_free(kv.second.h_prob);
+    for (auto& kv : impl_->party) {
         if (kv.second.csr) cgb_csr_destroy(impl_->ctx, kv.second.csr);
+        if (kv.second.d_labels) cgb_free(impl_->ctx, kv.second.d_labels);
+    }
     delete impl_;
 }
 
@@ -727,6 +707,10 @@ void SSGcnEngine::add_party(const PartyGraph& g, const double* feats_local, cons
         nv[i] = g.in_deg[i] == 0 ? 0 : (uint64_t)(int64_t)(std::pow((double)g.in_deg[i] + 1.0, -0.5) * (double)(1ull << im.f));
     pd.norm.resize(im.ctx, 1, n);
     ck(im.ctx, cgb_h2d(im.ctx, pd.norm.p, nv.data(), n * 8), "h2d");
+    void* dl = nullptr;  // labels on the device: the prediction-layer stand-in (cgb_ideal_softmax) forms p - y there
+    ck(im.ctx, cgb_malloc(im.ctx, std::max<size_t>(n, 1) * sizeof(int32_t), &dl), "cgb_malloc");
+    pd.d_labels = (int32_t*)dl;
+    if (n) ck(im.ctx, cgb_h2d(im.ctx, pd.d_labels, pd.labels.data(), n * sizeof(int32_t)), "h2d");
     ck(im.ctx, cgb_ctx_sync(im.ctx), "sync");
 }
 
@@ -810,151 +794,225 @@ static DMat* sel_X(Side& s, int) { return &s.X; }
 static DMat* sel_XP(Side& s, int k) { return k == 0 ? &s.P : &s.X; }
 static DMat* sel_Xz0(Side& s, int k) { return k == 0 ? &s.X : &s.z[0]; }
 
+// online phase of iteration `it` (everything after the dealer hand-out): only stream-ordered work, no allocation once the
+// buffers have their final sizes, no host synchronisation -- so it can be recorded into a CUDA graph
+static void online_iteration(SSGcnEngine::Impl& im, uint64_t it) {
+    cgb_ctx* ctx = im.ctx;
+    const uint32_t F = im.F, H = im.H, C = im.C;
+    const int ph = (int)(it % 6);
+    if (ph == 0) im.for_sides([&](Side& s) { s.X.copy_from(s.X_backup); });  // ssk.h:695, 938
+    im.tick(nullptr);
+
+    if (ph == 0 || ph == 1) {
+        // ---------------- forward layer `ph` ----------------
+        const int layer = ph;
+        const uint32_t Din = layer == 0 ? F : H, Dout = layer == 0 ? H : C;
+        im.for_sides([&](Side& s) {  // PreScatterComp (gcn.h:198-255)
+            s.h_t[layer].resize(ctx, Din, s.n);
+            ck(ctx, cgb_transpose(ctx, s.X.p, s.h_t[layer].p, s.n, Din), "transpose");  // gcn.h:230-231
+            im.mm_prepare(s, it, 0, s.X, s.W[layer]);
+            im.mm_post(s, 0);
+        });
+        im.comm->exchange();
+        im.for_sides([&](Side& s) { im.mm_finish(s, 0, s.n, Din, Dout, s.Xp); });
+        if (layer != 0)  // gcn.h:243-254
+            im.rowscale_all(it, 0, [](Side& s) -> DMat& { return s.Xp; }, [](Side& s) -> DMat& { return s.Xp; });
+        im.tick("PreScatterComp");
+        im.gas(it);
+        im.tick("Scatter+Gather (OM message, fused gather-sum, update exchange, adds)");
+        // gcn.h:470-484: in-degree scaling ((it + 1) % 6 != 0 for the forward layers)
+        im.rowscale_all(it, 1, [](Side& s) -> DMat& { return s.V; }, [](Side& s) -> DMat& { return s.V; });
+        im.tick("Gather_computation (in-degree scale)");
+        im.for_sides([&](Side& s) { s.z[layer].copy_from(s.V); });
+        if (layer == 0) {  // gcn.h:546-558: ReLU -- 2PC-RESIDUAL
+            im.for_sides([&](Side& s) { s.X.resize(ctx, s.n, Dout); });
+            im.residual(it, 1, 1, 1, sel_V, sel_X);
+        } else {  // gcn.h:559-642: softmax, p - y -- 2PC-RESIDUAL; then p is opened to the owner (gcn.h:604)
+            im.for_sides([&](Side& s) {
+                s.X.resize(ctx, s.n, Dout);
+                s.P.resize(ctx, s.n, Dout);
+            });
+            im.residual(it, 3, 1, 2, sel_V, sel_XP);
+            im.for_sides([&](Side& s) {
+                if (s.share == 1) im.send(im.q(s.owner), s.owner, s.P, SSGcnEngine::Impl::tagf("open_p", -1, s.owner));
+                else {
+                    s.Ppeer.resize(ctx, s.n, Dout);
+                    im.recv(s.owner, im.q(s.owner), s.Ppeer);
+                }
+            });
+            im.comm->exchange();
+            im.for_sides([&](Side& s) {  // getPlainShareVecVec (gcn.h:604): decode on the device, copy to pinned host memory
+                if (s.share != 0) return;
+                s.prob.resize(ctx, s.n, Dout);
+                if (s.h_prob_cap < s.prob.n()) {
+                    if (g_capturing) throw std::runtime_error("engine: host buffer grew while an iteration was being captured");
+                    if (s.h_prob) cgb_host_free(s.h_prob);
+                    void* hp = nullptr;
+                    if (cgb_host_alloc(std::max<size_t>(s.prob.n(), 1) * 8, &hp) != CGB_OK) throw std::runtime_error("cgb_host_alloc");
+                    s.h_prob = (double*)hp;
+                    s.h_prob_cap = s.prob.n();
+                }
+                ck(ctx, cgb_open_decode(ctx, s.P.p, s.Ppeer.p, (double*)s.prob.p, s.P.n(), im.f), "open_decode");
+                if (s.prob.n()) ck(ctx, cgb_d2h(ctx, s.h_prob, s.prob.p, s.prob.n() * 8), "d2h");
+                im.metrics_pending.push_back(s.owner);
+            });
+        }
+    } else if (ph == 2) {
+        // ---------------- backward, first step of the last layer: apply only (ssk.h:709-732; gcn.h:664-669) -----
+        im.for_sides([&](Side& s) {
+            s.tmp2.resize(ctx, C, H);
+            ck(ctx, cgb_transpose(ctx, s.W[1].p, s.tmp2.p, H, C), "transpose");  // weightT (gcn.h:648)
+            im.mm_prepare(s, it, 0, s.X, s.tmp2);
+            im.mm_post(s, 0);
+        });
+        im.comm->exchange();
+        im.for_sides([&](Side& s) { im.mm_finish(s, 0, s.n, C, H, s.g); });
+    } else if (ph == 3 || ph == 5) {
+        // ---------------- backward GAS + weight gradient (gcn.h:247-254, 470-484, 671-684 / 710-736) -------------
+        const int layer = ph == 3 ? 1 : 0;
+        const uint32_t Din = layer == 0 ? F : H, Dout = layer == 0 ? H : C;
+        im.rowscale_all(it, 0, [](Side& s) -> DMat& { return s.X; }, [](Side& s) -> DMat& { return s.Xp; });
+        im.tick("PreScatterComp");
+        im.gas(it);
+        im.tick("Scatter+Gather (OM message, fused gather-sum, update exchange, adds)");
+        if ((it + 1) % 6 != 0)  // gcn.h:470: no in-degree scaling on the last iteration of the epoch
+            im.rowscale_all(it, 1, [](Side& s) -> DMat& { return s.V; }, [](Side& s) -> DMat& { return s.V; });
+        im.tick("Gather_computation (in-degree scale)");
+        im.for_sides([&](Side& s) {
+            im.mm_prepare(s, it, 1, s.h_t[layer], s.V);  // d = h_t * v
+            im.mm_post(s, 1);
+        });
+        im.comm->exchange();
+        im.for_sides([&](Side& s) {
+            DMat& d = s.grad;
+            im.mm_finish(s, 1, Din, s.n, Dout, d);
+            const uint64_t train = (uint64_t)(s.n * im.cfg.train_ratio);
+            const uint64_t gs = train ? (uint64_t)(int64_t)((1.0 / (double)train) * (double)(1ull << im.f)) : 0;  // gcn.h:673-676
+            ck(ctx, cgb_scale_public(ctx, d.p, gs, d.p, d.n(), im.f, s.share), "scale");
+            ck(ctx, cgb_apply_gradient(ctx, s.W[layer].p, d.p, im.lr_fixed, s.W[layer].p, d.n(), im.f, s.share), "apply_gradient");
+            if (layer == 1) s.X.copy_from(s.g);  // dstVec.swap(g) (gcn.h:684)
+            else s.X.copy_from(s.V);             // first layer: g is empty in the reference; never used again
+        });
+        im.tick("Apply_computation");
+        im.weight_average(it, layer);
+        im.tick("Apply_computation (weight averaging)");
+    } else {
+        // ---------------- ph == 4: ReLU' mask, first layer so no further matmul (gcn.h:702-708) -- 2PC-RESIDUAL ---
+        im.residual(it, 2, 2, 1, sel_Xz0, sel_X);
+    }
+    im.tick("Apply_computation");
+}
+
+// loss / accuracy the owner prints after the prediction layer (gcn.h:603-632), from the opened probabilities
+static Metrics owner_metrics(SSGcnEngine::Impl& im, uint64_t it, int owner, bool verbose) {
+    Side& s = im.own.at(owner);
+    const uint32_t C = im.C, n = s.n;
+    double* prob = s.h_prob;
+    const auto& labels = im.party.at(owner).labels;
+    const uint64_t train = (uint64_t)(n * im.cfg.train_ratio), val = (uint64_t)(n * im.cfg.val_ratio);
+    double loss = 0;
+    uint64_t hit_full = 0, hit_train = 0, hit_test = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t best = 0;
+        for (uint32_t j = 0; j < C; ++j) {
+            double& pj = prob[(size_t)i * C + j];
+            if (pj == 0) pj = 0.001;  // gcn.h:615
+            if (pj > prob[(size_t)i * C + best]) best = j;
+        }
+        loss -= std::log(std::max(prob[(size_t)i * C + labels[i]], 1e-30));
+        const bool ok = best == (uint32_t)labels[i];
+        hit_full += ok;
+        if (i < train) hit_train += ok;
+        if (i >= train + val) hit_test += ok;
+    }
+    Metrics m{it, owner, n ? loss / n : 0.0, n ? (double)hit_full / n : 0.0, train ? (double)hit_train / train : 0.0,
+              n > train + val ? (double)hit_test / (n - train - val) : 0.0};
+    if (verbose) {  // the reference's log lines (gcn.h:620-632)
+        printf("cross-entropy-loss = %lf\n", m.loss);
+        printf("full set accuracy = %lf\n", m.acc_full);
+        printf("training set accuracy = %lf\n", m.acc_train);
+        printf("test set accuracy = %lf\n", m.acc_test);
+    }
+    return m;
+}
+
+static void ckc(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
 void SSGcnEngine::run(uint64_t n_iters) {
     Impl& im = *impl_;
     cgb_ctx* ctx = im.ctx;
-    const uint32_t F = im.F, H = im.H, C = im.C;
+    cudaStream_t stream = (cudaStream_t)cgb_ctx_stream(ctx);
     for (uint64_t step = 0; step < n_iters; ++step, ++iter_) {
         const uint64_t it = iter_;
         const int ph = (int)(it % 6);
         im.comm->cur_iter = it;
         auto t_deal = std::chrono::high_resolution_clock::now();
+        *im.h_bias = (it - (uint64_t)ph) << 16;  // epoch part of every PRG stream id of this iteration (see stream_id)
+        ck(ctx, cgb_h2d(ctx, im.d_bias, im.h_bias, 8), "h2d");
         im.deal_iteration(it);  // offline phase (dealer emulation), timed separately
         ck(ctx, cgb_ctx_sync(ctx), "sync");
         auto t0 = std::chrono::high_resolution_clock::now();
         seconds_offline += std::chrono::duration<double>(t0 - t_deal).count();
-        if (ph == 0) im.for_sides([&](Side& s) { s.X.copy_from(s.X_backup); });  // ssk.h:695, 938
-        im.tick(nullptr);
 
-        if (ph == 0 || ph == 1) {
-            // ---------------- forward layer `ph` ----------------
-            const int layer = ph;
-            const uint32_t Din = layer == 0 ? F : H, Dout = layer == 0 ? H : C;
-            im.for_sides([&](Side& s) {  // PreScatterComp (gcn.h:198-255)
-                s.h_t[layer].resize(ctx, Din, s.n);
-                ck(ctx, cgb_transpose(ctx, s.X.p, s.h_t[layer].p, s.n, Din), "transpose");  // gcn.h:230-231
-                im.mm_prepare(s, it, 0, s.X, s.W[layer]);
-                im.mm_post(s, 0);
+        // eager in the first epoch, while tests record the transcript, or while phases are profiled; otherwise the first
+        // later occurrence of this iteration index is captured and every further one replays the graph
+        const bool use_graph = im.graphs_enabled && !im.profile && !im.comm->record && it >= 6 && stream != nullptr;
+        Impl::IterGraph& ig = im.graph[ph];
+        if (use_graph && ig.exec) {
+            ckc(cudaGraphLaunch(ig.exec, stream), "cudaGraphLaunch");
+            im.replayed_launches += ig.launches;
+            im.comm->words_sent += ig.words;
+            im.comm->rounds += ig.rounds;
+            im.graph_replays++;
+            size_t k = 0;
+            im.for_side_mats([&](DMat& m) {
+                m.rows = ig.shapes[k].first;
+                m.cols = ig.shapes[k].second;
+                ++k;
             });
-            im.comm->exchange();
-            im.for_sides([&](Side& s) { im.mm_finish(s, 0, s.n, Din, Dout, s.Xp); });
-            if (layer != 0)  // gcn.h:243-254
-                im.rowscale_all(it, 0, [](Side& s) -> DMat& { return s.Xp; }, [](Side& s) -> DMat& { return s.Xp; });
-            im.tick("PreScatterComp");
-            im.gas(it);
-            im.tick("Scatter+Gather (OM message, fused gather-sum, update exchange, adds)");
-            // gcn.h:470-484: in-degree scaling ((it + 1) % 6 != 0 for the forward layers)
-            im.rowscale_all(it, 1, [](Side& s) -> DMat& { return s.V; }, [](Side& s) -> DMat& { return s.V; });
-            im.tick("Gather_computation (in-degree scale)");
-            im.for_sides([&](Side& s) { s.z[layer].copy_from(s.V); });
-            if (layer == 0) {  // gcn.h:546-558: ReLU -- 2PC-RESIDUAL
-                im.for_sides([&](Side& s) { s.X.resize(ctx, s.n, Dout); });
-                im.residual(it, fn_relu, 1, 1, sel_V, sel_X, 1);
-            } else {  // gcn.h:559-642: softmax, p - y -- 2PC-RESIDUAL; then p is opened to the owner (gcn.h:604)
-                im.for_sides([&](Side& s) {
-                    s.X.resize(ctx, s.n, Dout);
-                    s.P.resize(ctx, s.n, Dout);
-                });
-                im.residual(it, fn_softmax, 1, 2, sel_V, sel_XP);
-                im.for_sides([&](Side& s) {
-                    if (s.share == 1) im.send(im.q(s.owner), s.owner, s.P, Impl::tagf("open_p", -1, s.owner));
-                    else {
-                        s.Ppeer.resize(ctx, s.n, Dout);
-                        im.recv(s.owner, im.q(s.owner), s.Ppeer);
-                    }
-                });
-                im.comm->exchange();
-                im.for_sides([&](Side& s) {
-                    if (s.share != 0) return;
-                    std::vector<double> prob(s.P.n());
-                    void* dv = nullptr;
-                    ck(ctx, cgb_malloc(ctx, std::max<size_t>(prob.size(), 1) * 8, &dv), "malloc");
-                    ck(ctx, cgb_open_decode(ctx, s.P.p, s.Ppeer.p, (double*)dv, s.P.n(), im.f), "open_decode");
-                    ck(ctx, cgb_d2h(ctx, prob.data(), dv, prob.size() * 8), "d2h");
-                    ck(ctx, cgb_ctx_sync(ctx), "sync");
-                    cgb_free(ctx, dv);
-                    const auto& labels = im.party.at(s.owner).labels;
-                    const uint32_t n = s.n;
-                    const uint64_t train = (uint64_t)(n * im.cfg.train_ratio), val = (uint64_t)(n * im.cfg.val_ratio);
-                    double loss = 0;
-                    uint64_t hit_full = 0, hit_train = 0, hit_test = 0;
-                    for (uint32_t i = 0; i < n; ++i) {
-                        uint32_t best = 0;
-                        for (uint32_t j = 0; j < C; ++j) {
-                            double& pj = prob[(size_t)i * C + j];
-                            if (pj == 0) pj = 0.001;  // gcn.h:615
-                            if (pj > prob[(size_t)i * C + best]) best = j;
-                        }
-                        loss -= std::log(std::max(prob[(size_t)i * C + labels[i]], 1e-30));
-                        const bool ok = best == (uint32_t)labels[i];
-                        hit_full += ok;
-                        if (i < train) hit_train += ok;
-                        if (i >= train + val) hit_test += ok;
-                    }
-                    Metrics m{it, s.owner, n ? loss / n : 0.0, n ? (double)hit_full / n : 0.0,
-                              train ? (double)hit_train / train : 0.0,
-                              n > train + val ? (double)hit_test / (n - train - val) : 0.0};
-                    metrics_.push_back(m);
-                    if (verbose) {  // the reference's log lines (gcn.h:620-632)
-                        printf("cross-entropy-loss = %lf\n", m.loss);
-                        printf("full set accuracy = %lf\n", m.acc_full);
-                        printf("training set accuracy = %lf\n", m.acc_train);
-                        printf("test set accuracy = %lf\n", m.acc_test);
-                    }
-                });
+            if (ph == 1)
+                for (auto& kv : im.own) im.metrics_pending.push_back(kv.first);
+        } else if (use_graph) {
+            const uint64_t l0 = cgb_ctx_launch_count(ctx), w0 = im.comm->words_sent, r0 = im.comm->rounds;
+            cudaGraph_t g = nullptr;
+            ckc(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+            g_capturing = true;
+            try {
+                online_iteration(im, it);
+            } catch (...) {
+                g_capturing = false;
+                cudaStreamEndCapture(stream, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
             }
-        } else if (ph == 2) {
-            // ---------------- backward, first step of the last layer: apply only (ssk.h:709-732; gcn.h:664-669) -----
-            im.for_sides([&](Side& s) {
-                s.tmp2.resize(ctx, C, H);
-                ck(ctx, cgb_transpose(ctx, s.W[1].p, s.tmp2.p, H, C), "transpose");  // weightT (gcn.h:648)
-                im.mm_prepare(s, it, 0, s.X, s.tmp2);
-                im.mm_post(s, 0);
-            });
-            im.comm->exchange();
-            im.for_sides([&](Side& s) { im.mm_finish(s, 0, s.n, C, H, s.g); });
-        } else if (ph == 3 || ph == 5) {
-            // ---------------- backward GAS + weight gradient (gcn.h:247-254, 470-484, 671-684 / 710-736) -------------
-            const int layer = ph == 3 ? 1 : 0;
-            const uint32_t Din = layer == 0 ? F : H, Dout = layer == 0 ? H : C;
-            im.rowscale_all(it, 0, [](Side& s) -> DMat& { return s.X; }, [](Side& s) -> DMat& { return s.Xp; });
-            im.tick("PreScatterComp");
-            im.gas(it);
-            im.tick("Scatter+Gather (OM message, fused gather-sum, update exchange, adds)");
-            if ((it + 1) % 6 != 0)  // gcn.h:470: no in-degree scaling on the last iteration of the epoch
-                im.rowscale_all(it, 1, [](Side& s) -> DMat& { return s.V; }, [](Side& s) -> DMat& { return s.V; });
-            im.tick("Gather_computation (in-degree scale)");
-            im.for_sides([&](Side& s) {
-                im.mm_prepare(s, it, 1, s.h_t[layer], s.V);  // d = h_t * v
-                im.mm_post(s, 1);
-            });
-            im.comm->exchange();
-            im.for_sides([&](Side& s) {
-                DMat& d = s.grad;
-                im.mm_finish(s, 1, Din, s.n, Dout, d);
-                const uint64_t train = (uint64_t)(s.n * im.cfg.train_ratio);
-                const uint64_t gs = train ? (uint64_t)(int64_t)((1.0 / (double)train) * (double)(1ull << im.f)) : 0;  // gcn.h:673-676
-                ck(ctx, cgb_scale_public(ctx, d.p, gs, d.p, d.n(), im.f, s.share), "scale");
-                ck(ctx, cgb_apply_gradient(ctx, s.W[layer].p, d.p, im.lr_fixed, s.W[layer].p, d.n(), im.f, s.share), "apply_gradient");
-                if (layer == 1) s.X.copy_from(s.g);  // dstVec.swap(g) (gcn.h:684)
-                else s.X.copy_from(s.V);             // first layer: g is empty in the reference; never used again
-            });
-            im.tick("Apply_computation");
-            im.weight_average(it, layer);
-            im.tick("Apply_computation (weight averaging)");
+            g_capturing = false;
+            ckc(cudaStreamEndCapture(stream, &g), "cudaStreamEndCapture");
+            ckc(cudaGraphInstantiate(&ig.exec, g, 0), "cudaGraphInstantiate");
+            cudaGraphDestroy(g);
+            ig.launches = cgb_ctx_launch_count(ctx) - l0;  // counted once while recording = the launch right below
+            ig.words = im.comm->words_sent - w0;
+            ig.rounds = im.comm->rounds - r0;
+            ig.shapes.clear();
+            im.for_side_mats([&](DMat& m) { ig.shapes.push_back({m.rows, m.cols}); });
+            im.graph_captures++;
+            ckc(cudaGraphLaunch(ig.exec, stream), "cudaGraphLaunch");
         } else {
-            // ---------------- ph == 4: ReLU' mask, first layer so no further matmul (gcn.h:702-708) -- 2PC-RESIDUAL ---
-            im.residual(it, fn_relu_grad, 2, 1, sel_Xz0, sel_X, 2);
+            online_iteration(im, it);
         }
-        im.tick("Apply_computation");
         ck(ctx, cgb_ctx_sync(ctx), "sync");
+        for (int owner : im.metrics_pending) metrics_.push_back(owner_metrics(im, it, owner, verbose));
+        im.metrics_pending.clear();
         const double dt = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
         seconds_online += dt;
         if (verbose) printf("::iteration took %lf seconds\n", dt);
     }
 }
 
-double SSGcnEngine::seconds_residual_host() const { return impl_->seconds_residual_host; }
+double SSGcnEngine::seconds_residual_host() const { return 0.0; }  // the stand-ins run on the device since round 1b
+uint64_t SSGcnEngine::replayed_launches() const { return impl_->replayed_launches; }
+uint64_t SSGcnEngine::graph_replays() const { return impl_->graph_replays; }
 
 std::vector<uint64_t> SSGcnEngine::download(int owner, int role, const std::string& name, uint32_t* rows, uint32_t* cols) {
     Impl& im = *impl_;

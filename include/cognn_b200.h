@@ -69,6 +69,12 @@ const char* cgb_last_error(cgb_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t cgb_ctx_launch_count(cgb_ctx* ctx);
 
+/* From now on every PRG launch of this context (cgb_prg_fill, cgb_prg_mask_sub, cgb_share_split) uses stream id
+ * `stream + *d_bias`, the device word being read when the kernel RUNS: a CUDA graph captured once (one GAS iteration of
+ * the engine) draws the randomness of a later iteration when it is replayed after the word was updated.  NULL switches
+ * the bias off.  The word must stay allocated while such launches or graphs can still execute. */
+int cgb_ctx_set_prg_stream_bias(cgb_ctx* ctx, const uint64_t* d_bias);
+
 /* ---- memory --------------------------------------------------------------------------------------------- */
 int cgb_malloc(cgb_ctx* ctx, size_t bytes, void** d_out);
 int cgb_free(cgb_ctx* ctx, void* d_ptr);
@@ -175,6 +181,12 @@ int cgb_prg_mask_sub(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, uint6
 int cgb_ideal_relu(cgb_ctx* ctx, const uint64_t* d_a0, const uint64_t* d_a1, uint64_t* d_out, uint64_t n);
 int cgb_ideal_relu_grad(cgb_ctx* ctx, const uint64_t* d_g0, const uint64_t* d_g1, const uint64_t* d_z0,
                         const uint64_t* d_z1, uint64_t* d_out, uint64_t n);
+/* sci::twoPartyGCNForwardNNPredictionWithoutWeight (gcn.h:578,591), same kind of stand-in: row-wise softmax of the
+ * reconstructed logits z0+z1 (n x C) in double with exp restated from IEEE + - * only (bit-identical to the oracle's
+ * orc_det_exp), P = enc(p), pmy = P - (onehot(label) << f) on the first train_rows rows and 0 below (gcn.h:639-641).
+ * d_labels: n int32 class ids on the device. */
+int cgb_ideal_softmax(cgb_ctx* ctx, const uint64_t* d_z0, const uint64_t* d_z1, const int32_t* d_labels, uint64_t n,
+                      uint32_t C, uint64_t train_rows, int f, uint64_t* d_P, uint64_t* d_pmy);
 
 /* ---- host-buffer entry point (what a CoGNN operator holding std::vector data calls) ------------------------ */
 /* One gather-sum step with HOST share rows: H2D of x (and delta if given), kernel, D2H of y,

@@ -46,10 +46,13 @@ int cge_message_info(cge_engine* h, uint64_t i, uint64_t* iter, int* src, int* d
 int cge_message_data(cge_engine* h, uint64_t i, uint64_t* out, uint64_t capacity);
 uint64_t cge_words_sent(cge_engine* h);
 uint64_t cge_rounds(cge_engine* h);
-uint64_t cge_launch_count(cge_engine* h);
+uint64_t cge_launch_count(cge_engine* h);   /* kernels launched, including those inside replayed CUDA graphs */
+/* From the second epoch on, the online phase of each GAS iteration is one CUDA graph (captured at its first later
+ * occurrence, replayed afterwards; COGNN_B200_GRAPHS=0 or record_messages keep the eager path).  Number of replays: */
+uint64_t cge_graph_replays(cge_engine* h);
 double cge_seconds_online(cge_engine* h);   /* host wall time of the online phases, stream-synchronised */
-double cge_seconds_offline(cge_engine* h);
-double cge_seconds_residual_host(cge_engine* h); /* part of online spent in the host 2PC-residual stand-in (softmax) */  /* dealer emulation (correlation generation), excluded from online */
+double cge_seconds_offline(cge_engine* h);  /* dealer emulation (correlation generation), excluded from online */
+double cge_seconds_residual_host(cge_engine* h); /* always 0: the 2PC-residual stand-ins run on the device (cgb_ideal_*) */
 uint64_t cge_metrics_count(cge_engine* h);
 int cge_metrics_get(cge_engine* h, uint64_t i, uint64_t* iter, int* party, double* loss, double* acc_full, double* acc_train,
                     double* acc_test);

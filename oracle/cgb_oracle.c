@@ -147,6 +147,50 @@ void orc_transpose(const uint64_t* in, uint64_t* out, size_t rows, size_t cols) 
         for (size_t c = 0; c < cols; ++c) out[c * rows + r] = in[r * cols + c];
 }
 
+
+/* ------------------------------------------------------------------------------------------------ */
+/* 2PC-RESIDUAL stand-ins (ideal functionality; see cgb_oracle.h).  Built with -ffp-contract=off.     */
+/* ------------------------------------------------------------------------------------------------ */
+static const double ORC_EXP_C[14] = {0x1.0000000000000p+0, 0x1.0000000000000p+0, 0x1.0000000000000p-1, 0x1.5555555555555p-3,
+                                     0x1.5555555555555p-5, 0x1.1111111111111p-7, 0x1.6c16c16c16c17p-10, 0x1.a01a01a01a01ap-13,
+                                     0x1.a01a01a01a01ap-16, 0x1.71de3a556c734p-19, 0x1.27e4fb7789f5cp-22, 0x1.ae64567f544e4p-26,
+                                     0x1.1eed8eff8d898p-29, 0x1.6124613a86d09p-33};
+double orc_det_exp(double x) {
+    if (x < -700.0) return 0.0;
+    if (x > 700.0) x = 700.0;
+    const double t = x * 0x1.71547652b82fep+0 + 0.5;
+    long long k = (long long)t;
+    if ((double)k > t) k -= 1; /* floor */
+    const double kd = (double)k;
+    const double r = (x - kd * 0x1.62e42fee00000p-1) - kd * 0x1.a39ef35793c76p-33;
+    double p = ORC_EXP_C[13];
+    for (int i = 12; i >= 0; --i) p = p * r + ORC_EXP_C[i];
+    union { uint64_t u; double d; } two_k;
+    two_k.u = (uint64_t)(k + 1023) << 52; /* |k| <= 1011 */
+    return p * two_k.d;
+}
+void orc_ideal_softmax(const uint64_t* z0, const uint64_t* z1, const int32_t* labels, size_t n, size_t C,
+                       size_t train_rows, int f, uint64_t* P, uint64_t* pmy) {
+    const double scale = (double)(1ull << f);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) {
+        double m = 0.0;
+        for (size_t j = 0; j < C; ++j) {
+            const double v = (double)(int64_t)(z0[i * C + j] + z1[i * C + j]) / scale;
+            if (j == 0 || v > m) m = v;
+        }
+        double tot = 0.0;
+        for (size_t j = 0; j < C; ++j)
+            tot += orc_det_exp((double)(int64_t)(z0[i * C + j] + z1[i * C + j]) / scale - m);
+        for (size_t j = 0; j < C; ++j) {
+            const double e = orc_det_exp((double)(int64_t)(z0[i * C + j] + z1[i * C + j]) / scale - m);
+            const uint64_t pj = (uint64_t)(int64_t)((e / tot) * scale);
+            P[i * C + j] = pj;
+            pmy[i * C + j] = i < train_rows ? pj - ((size_t)labels[i] == j ? (1ull << f) : 0ull) : 0ull;
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* (1) scatter / gather-sum                                                                           */
 /* ------------------------------------------------------------------------------------------------ */

@@ -65,6 +65,17 @@ void orc_rowmul_beaver_finish(const uint64_t* e, const uint64_t* fv, const uint6
 void orc_cond_add(const uint64_t* v, const uint64_t* u, const uint8_t* cond, uint64_t* out, size_t rows, size_t D);
 void orc_transpose(const uint64_t* in, uint64_t* out, size_t rows, size_t cols); /* task.h transpose(), gcn.h:230,648 */
 
+/* ---- 2PC-RESIDUAL stand-ins (ideal functionality on RECONSTRUCTED values; not secure, not the reference's protocol) ---- */
+/* exp() restated with IEEE-754 double +, -, * only (no libm, no fused multiply-add), so that the C oracle, the numpy
+ * restatement and the CUDA kernel produce the same bits:  k = floor(x*log2(e) + 1/2),  r = (x - k*ln2_hi) - k*ln2_lo,
+ * exp(r) = sum_{i<=13} r^i / i! by Horner, result = that times 2^k.  x < -700 gives 0, x > 700 is clamped. */
+double orc_det_exp(double x);
+/* sci::twoPartyGCNForwardNNPredictionWithoutWeight (gcn.h:578,591) on the reconstructed logits z = z0 + z1 (n x C):
+ * row-wise softmax in double (max subtracted, left-to-right sum), P = enc(p), pmy = P - onehot(label)<<f, rows >= train_rows
+ * get pmy = 0 (gcn.h:639-641). */
+void orc_ideal_softmax(const uint64_t* z0, const uint64_t* z1, const int32_t* labels, size_t n, size_t C,
+                       size_t train_rows, int f, uint64_t* P, uint64_t* pmy);
+
 /* ---- (1) scatter / gather-sum ------------------------------------------------------------------- */
 /* Fused expand + group-by-destination sum: y[v] = (delta ? delta[v] : 0) + sum_{e in [rowptr[v],rowptr[v+1])} x[col[e]].
  * Composite of the OM expand (ss_vertex_centric_algo_kernel.h:751-763), ScatterComp copy (gcn.h:300),

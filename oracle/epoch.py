@@ -210,22 +210,8 @@ class EpochOracle:
         n = self.n[p]
         train = int(n * self.cfg["train_ratio"])  # gcn.h:560: (uint64_t)(vecSize * train_ratio)
 
-        def fn(z):
-            zd = po.decode(z, f)
-            prob = np.zeros_like(zd)
-            for i in range(n):  # glibc exp, left-to-right sums: the engine's host stand-in does exactly this
-                row = zd[i].tolist()
-                m = max(row)
-                e = [math.exp(v - m) for v in row]
-                tot = 0.0
-                for v in e:
-                    tot += v
-                prob[i] = [v / tot for v in e]
-            P = po.encode(prob, f)
-            onehot = np.zeros((n, C), dtype=U64)
-            onehot[np.arange(n), labels] = U64(1 << f)
-            pmy = po.sub(P, onehot)
-            pmy[train:] = 0  # gcn.h:639-641: only training rows keep a gradient
+        def fn(z):  # device stand-in of the engine: cgb_ideal_softmax (exp restated with IEEE + - * only, orc_det_exp)
+            P, pmy = po.ideal_softmax(z, np.zeros_like(z), labels, train, f)
             return [P, pmy]
 
         return fn

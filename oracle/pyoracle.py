@@ -37,6 +37,8 @@ def lib():
         _lib.orc_trunc_share.restype = C.c_uint64
         _lib.orc_trunc_share.argtypes = [C.c_uint64, C.c_int, C.c_int]
         _lib.orc_num_threads.restype = C.c_int
+        _lib.orc_det_exp.restype = C.c_double
+        _lib.orc_det_exp.argtypes = [C.c_double]
     return _lib
 
 
@@ -162,6 +164,57 @@ def cond_add(v, u, cond):
     out = np.zeros(v.shape, dtype=np.uint64)
     lib().orc_cond_add(_p(v), _p(u), _p(cond), _p(out), C.c_size_t(rows), C.c_size_t(D))
     return out
+
+
+def det_exp(x):
+    return float(lib().orc_det_exp(float(x)))
+
+
+_EXP_C = [float.fromhex(h) for h in (
+    "0x1.0000000000000p+0", "0x1.0000000000000p+0", "0x1.0000000000000p-1", "0x1.5555555555555p-3", "0x1.5555555555555p-5",
+    "0x1.1111111111111p-7", "0x1.6c16c16c16c17p-10", "0x1.a01a01a01a01ap-13", "0x1.a01a01a01a01ap-16", "0x1.71de3a556c734p-19",
+    "0x1.27e4fb7789f5cp-22", "0x1.ae64567f544e4p-26", "0x1.1eed8eff8d898p-29", "0x1.6124613a86d09p-33")]
+
+
+def det_exp_numpy(x):
+    """numpy restatement of orc_det_exp (every ufunc rounds once, so no fused multiply-add can sneak in)."""
+    x = np.asarray(x, dtype=np.float64)
+    zero = x < -700.0
+    xc = np.minimum(np.where(zero, 0.0, x), 700.0)
+    k = np.floor(xc * float.fromhex("0x1.71547652b82fep+0") + 0.5)
+    r = (xc - k * float.fromhex("0x1.62e42fee00000p-1")) - k * float.fromhex("0x1.a39ef35793c76p-33")
+    p = np.full_like(xc, _EXP_C[13])
+    for i in range(12, -1, -1):
+        p = p * r + _EXP_C[i]
+    two_k = ((k.astype(np.int64) + 1023).astype(np.uint64) << np.uint64(52)).view(np.float64)
+    return np.where(zero, 0.0, p * two_k)
+
+
+def ideal_softmax(z0, z1, labels, train_rows, f):
+    """2PC-RESIDUAL stand-in for the prediction layer (gcn.h:578,591) on reconstructed logits: returns (P, P - onehot)."""
+    z0, z1 = _u64(z0), _u64(z1)
+    n, Cc = z0.shape
+    lab = np.ascontiguousarray(labels, dtype=np.int32)
+    P = np.zeros((n, Cc), dtype=np.uint64)
+    pmy = np.zeros((n, Cc), dtype=np.uint64)
+    lib().orc_ideal_softmax(_p(z0), _p(z1), _p(lab), C.c_size_t(n), C.c_size_t(Cc), C.c_size_t(train_rows), f, _p(P), _p(pmy))
+    return P, pmy
+
+
+def ideal_softmax_numpy(z0, z1, labels, train_rows, f):
+    """numpy restatement of orc_ideal_softmax (left-to-right row sums)."""
+    z = (_u64(z0) + _u64(z1)).view(np.int64).astype(np.float64) / float(1 << f)
+    n, Cc = z.shape
+    e = det_exp_numpy(z - z.max(axis=1, keepdims=True))
+    tot = np.zeros(n)
+    for j in range(Cc):
+        tot = tot + e[:, j]
+    P = ((e / tot[:, None]) * float(1 << f)).astype(np.int64).view(np.uint64)
+    onehot = np.zeros((n, Cc), dtype=np.uint64)
+    onehot[np.arange(n), np.asarray(labels)] = np.uint64(1 << f)
+    pmy = P - onehot
+    pmy[train_rows:] = 0
+    return P, pmy
 
 
 def transpose(x):

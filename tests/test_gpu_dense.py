@@ -131,6 +131,52 @@ def test_ideal_functionality_standins(cgb):
     assert np.array_equal(got, np.where(z.astype(np.int64) > 0, v, np.uint64(0)))
 
 
+def test_prg_stream_bias_is_read_on_the_device(cgb, oracle):
+    """cgb_ctx_set_prg_stream_bias: stream id = argument + device word, read when the kernel runs (graph replays)."""
+    import torch
+
+    key = list(range(11, 19))
+    bias = torch.zeros(1, dtype=torch.int64, device="cuda")
+    x = rand_u64(np.random.default_rng(5), 1000)
+    cgb.set_prg_stream_bias(bias)
+    try:
+        for b in (0, 6 << 16, (12 << 16) + 3):
+            bias.fill_(b)
+            assert np.array_equal(to_np(cgb.prg_fill(key, 77 << 48, 9, 1000)), oracle.prg_fill(key, (77 << 48) + b, 9, 1000))
+            assert np.array_equal(to_np(cgb.prg_mask_sub(key, 5, 0, to_dev(x))), x - oracle.prg_fill(key, 5 + b, 0, 1000))
+    finally:
+        cgb.set_prg_stream_bias(None)
+    assert np.array_equal(to_np(cgb.prg_fill(key, 5, 0, 64)), oracle.prg_fill(key, 5, 0, 64))
+
+
+@pytest.mark.parametrize("n,C,spread", [(1, 3, 1.0), (257, 7, 3.0), (5000, 40, 8.0), (300, 70, 40.0)])
+def test_ideal_softmax_bit_exact(cgb, oracle, n, C, spread):
+    """Device stand-in of the prediction layer == CPU oracle, bit for bit (exp is restated from IEEE + - * on both sides).
+    Logits up to +-40*4 fixed-point units apart exercise the exp underflow-to-zero range; ties and equal rows too."""
+    import torch
+
+    rng = np.random.default_rng(n * 100 + C)
+    f = 16
+    z = (rng.normal(0, spread, size=(n, C)) * (1 << f)).astype(np.int64)
+    z[0] = z[0, 0]            # a constant row: uniform probabilities
+    if n > 2:
+        z[1, 0] = 700 << f    # one dominant class: the others underflow
+        z[2] = -(1 << 40)     # large negative, all equal
+    z = z.view(np.uint64)
+    z1 = rand_u64(rng, n, C)
+    z0 = z - z1
+    labels = rng.integers(0, C, size=n).astype(np.int32)
+    train = n * 2 // 5
+    want_P, want_d = oracle.ideal_softmax(z0, z1, labels, train, f)
+    P, d = cgb.ideal_softmax(to_dev(z0), to_dev(z1), torch.from_numpy(labels).cuda(), train, f)
+    assert np.array_equal(to_np(P), want_P)
+    assert np.array_equal(to_np(d), want_d)
+    assert not to_np(d)[train:].any()
+    # probabilities sum to one up to the C truncations
+    tot = to_np(P).astype(np.int64).sum(axis=1)
+    assert ((1 << f) - C <= tot).all() and (tot <= (1 << f)).all()
+
+
 def test_sum_n_matches_oracle(cgb, oracle):
     rng = np.random.default_rng(8)
     for n in (1, 7, 4096, 100_001):

@@ -57,6 +57,36 @@ def test_engine_epoch_bit_exact(T, n_iters):
     e.close()
 
 
+@pytest.mark.parametrize("T,n_iters", [(2, 18), (3, 24), (4, 14)])
+def test_engine_graph_replay_bit_exact(T, n_iters):
+    """From the second epoch on the online phase of every iteration is a CUDA graph (captured in epoch 1, replayed from
+    epoch 2).  Several epochs without the transcript recorder (which forces the eager path): every share still equals the
+    oracle's, also when the run stops in the middle of an epoch, and the PRG streams advance through the device bias word."""
+    from cognn_b200 import engine as eng
+
+    g = small_graph(n=70, n_edges=260, F=10, C=4, T=T, seed=60 + T)
+    cfg = dict(input_dim=10, hidden_dim=8, num_labels=4, learning_rate=0.5, train_ratio=0.4, val_ratio=0.2)
+    o = ep.EpochOracle(g["edges"], g["tid"], T, g["feats"], g["labels"], cfg)
+    o.run(n_iters)
+    e = eng.Engine(T, cfg)
+    e.load(g["edges"], g["tid"], g["feats"], g["labels"])
+    for chunk in (5, 4, n_iters - 9):  # uneven run() calls: graphs are keyed by the iteration index in the epoch
+        e.run(chunk)
+    assert e.graph_replays == max(0, n_iters - 12)
+    for owner in range(T):
+        for role in (0, 1):
+            for name in NAMES:
+                want = oracle_tensor(o, owner, role, name)
+                got = e.download(owner, role, name)
+                assert np.array_equal(got, want), (owner, role, name)
+    gm = {(m["iter"], m["party"]): m for m in e.metrics()}
+    assert len(gm) == len(o.log)
+    for m in o.log:
+        assert abs(gm[(m["iter"], m["party"])]["acc_full"] - m["acc_full"]) < 1e-12
+        assert abs(gm[(m["iter"], m["party"])]["loss"] - m["loss"]) < 1e-9
+    e.close()
+
+
 def test_engine_cora_shaped_epoch_tracks_float64():
     """BASELINE configs[0] shape (Cora: 2708 vertices, 10556 edge entries, F=1433, H=16, C=7), 2 parties."""
     from cognn_b200 import engine as eng

@@ -156,3 +156,39 @@ def test_transpose_cond_add(oracle):
     v, u = rand_u64(6, 9), rand_u64(6, 9)
     cond = np.array([1, 0, 1, 1, 0, 0], dtype=np.uint8)
     assert np.array_equal(oracle.cond_add(v, u, cond), v + u * cond[:, None].astype(np.uint64))
+
+
+def test_det_exp_c_equals_numpy_and_tracks_libm():
+    """orc_det_exp (the exp of the 2PC-residual softmax stand-in) is plain IEEE arithmetic: the C build and the numpy
+    restatement agree bit for bit, and both stay within 2 ulp of libm over the range a max-subtracted softmax visits."""
+    import math
+
+    from oracle import pyoracle as po
+
+    po.build()
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([np.linspace(-60, 0, 6001), -rng.exponential(8, 5000), [-700.0, -700.5, -745.0, -1e4, 0.0, -1e-300]])
+    c = np.array([po.det_exp(v) for v in xs])
+    n = po.det_exp_numpy(xs)
+    assert np.array_equal(c.view(np.uint64), n.view(np.uint64))
+    ref = np.array([math.exp(v) if v > -700 else 0.0 for v in xs])
+    ok = ref > 1e-290
+    assert np.max(np.abs(c[ok] - ref[ok]) / ref[ok]) < 5e-16
+    assert (c[xs < -700] == 0).all() and po.det_exp(0.0) == 1.0
+
+
+def test_ideal_softmax_c_equals_numpy():
+    from oracle import pyoracle as po
+
+    rng = np.random.default_rng(1)
+    for n, C, f in [(1, 3, 16), (400, 7, 16), (90, 40, 13)]:
+        z = (rng.normal(0, 4, size=(n, C)) * (1 << f)).astype(np.int64).view(np.uint64)
+        z1 = rng.integers(0, 1 << 64, size=(n, C), dtype=np.uint64)
+        labels = rng.integers(0, C, size=n)
+        a = po.ideal_softmax(z - z1, z1, labels, n // 2, f)
+        b = po.ideal_softmax_numpy(z - z1, z1, labels, n // 2, f)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        p = a[0].astype(np.int64) / float(1 << f)
+        zz = z.view(np.int64) / float(1 << f)
+        e = np.exp(zz - zz.max(axis=1, keepdims=True))
+        assert np.abs(p - e / e.sum(axis=1, keepdims=True)).max() < 2.0 / (1 << f)
