@@ -33,6 +33,12 @@ def main():
         assert eng.load_host().cge_nccl_unique_id(buf) == 0
         uid = torch.frombuffer(bytearray(bytes(buf)), dtype=torch.uint8).clone()
     dist.broadcast(uid, 0)
+    uid2 = torch.zeros(128, dtype=torch.uint8)  # a second NCCL communicator for the graph-replay leg
+    if rank == 0:
+        buf = (ctypes.c_char * 128)()
+        assert eng.load_host().cge_nccl_unique_id(buf) == 0
+        uid2 = torch.frombuffer(bytearray(bytes(buf)), dtype=torch.uint8).clone()
+    dist.broadcast(uid2, 0)
     g = small_graph(n=90, n_edges=400, F=12, C=4, T=T, seed=77)
     cfg = dict(input_dim=12, hidden_dim=8, num_labels=4, learning_rate=0.5, train_ratio=0.4, val_ratio=0.2)
     e = eng.Engine(T, cfg, device=local_rank, rank=rank, nccl_uid=uid.numpy().tobytes(), record=True)
@@ -52,11 +58,29 @@ def main():
         bad.append(("message keys", len(got), len(want)))
     else:
         bad += [k for k in want if not np.array_equal(got[k], want[k])]
+    e.close()
+    # second leg: no transcript recorder, so from epoch 1 on each iteration's online phase (NCCL send/recv groups included)
+    # is captured into a CUDA graph and replayed in epochs 2 and 3; the run ends in the middle of an epoch
+    n2 = 20
+    e = eng.Engine(T, cfg, device=local_rank, rank=rank, nccl_uid=uid2.numpy().tobytes())
+    e.load(g["edges"], g["tid"], g["feats"], g["labels"])
+    e.run(n2)
+    replays = e.graph_replays
+    o = ep.EpochOracle(g["edges"], g["tid"], T, g["feats"], g["labels"], cfg)
+    o.run(n2)
+    for owner, role in ((rank, 0), ((rank - 1) % T, 1)):
+        for name in NAMES:
+            if not np.array_equal(e.download(owner, role, name), oracle_tensor(o, owner, role, name)):
+                bad.append(("graph", owner, role, name))
+    if os.environ.get("COGNN_B200_GRAPHS", "1") != "0" and replays != n2 - 12:
+        bad.append(("graph replays", replays))
+    if bad:
+        sys.stderr.write(f"[rank {rank}] mismatches: {bad[:40]}\n")
     res = torch.tensor([len(bad)], dtype=torch.int64)
     dist.all_reduce(res)
     if rank == 0:
-        print(json.dumps({"check": "engine_nccl_vs_oracle", "parties": T, "iterations": 12, "mismatches": int(res.item()),
-                          "messages_rank0": len(got), "ok": int(res.item()) == 0}), flush=True)
+        print(json.dumps({"check": "engine_nccl_vs_oracle", "parties": T, "iterations": [12, n2], "mismatches": int(res.item()),
+                          "messages_rank0": len(got), "graph_replays_rank0": replays, "ok": int(res.item()) == 0}), flush=True)
     e.close()
     dist.destroy_process_group()
     sys.exit(0 if int(res.item()) == 0 else 1)
