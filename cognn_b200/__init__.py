@@ -128,6 +128,47 @@ class Context:
     def ipc_close(self, ptr):
         self.check(self.lib.cgb_ipc_close(self.handle, C.c_void_p(ptr)))
 
+    def party_graph_build(self, edges, tid, T, me):
+        """Device ingest (include/cognn_b200.h, cgb_party_graph_build).  edges: (E, 2) int64, tid: (V,) int64; cuda tensors take
+        the device entry point, cpu tensors / numpy arrays the host one.  Returns a dict of torch tensors (device) plus the
+        handle-owning PartyGraph object under "handle"."""
+        t = self.torch
+        edges = t.as_tensor(edges, dtype=t.int64).reshape(-1, 2).contiguous()
+        tid = t.as_tensor(tid, dtype=t.int64).contiguous()
+        h = C.c_void_p()
+        fn = self.lib.cgb_party_graph_build if edges.is_cuda else self.lib.cgb_party_graph_build_host
+        assert edges.is_cuda == tid.is_cuda
+        self.check(fn(self.handle, _ptr(edges) if edges.numel() else None, edges.shape[0], _ptr(tid), tid.numel(), T, me,
+                      C.byref(h)))
+        lib = self.lib
+        n_local, n_rows = lib.cgb_party_graph_num_local(h), lib.cgb_party_graph_num_rows(h)
+        m = lib.cgb_party_graph_num_out_edges(h)
+        offsets = list((C.c_uint32 * (T + 1)).from_address(lib.cgb_party_graph_offsets(h)))
+        dev = self._dev()
+
+        def grab(ptr, n, dtype):
+            if n == 0:
+                return t.empty(0, dtype=dtype, device=dev)
+            typestr = {t.int64: "<i8", t.int32: "<i4", t.uint8: "|u1"}[dtype]
+
+            class _V:
+                __cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+            return t.as_tensor(_V(), device=dev).clone()
+
+        out = {"n_local": n_local, "n_rows": n_rows, "n_out_edges": m, "offsets": offsets,
+               "vids": grab(lib.cgb_party_graph_vids(h), n_local, t.int64),
+               "in_deg_raw": grab(lib.cgb_party_graph_in_deg_raw(h), n_local, t.int64),
+               "in_deg": grab(lib.cgb_party_graph_in_deg(h), n_local, t.int64),
+               "is_border": grab(lib.cgb_party_graph_is_border(h), n_local, t.uint8),
+               "rowptr": grab(lib.cgb_party_graph_rowptr(h), n_rows + 1, t.int32),
+               "col": grab(lib.cgb_party_graph_col(h), m, t.int32)}
+        ch = C.c_void_p()
+        self.check(lib.cgb_party_graph_csr(self.handle, h, C.byref(ch)))
+        out["csr"] = Csr(self, ch, n_rows, m, n_local)
+        self.check(lib.cgb_party_graph_destroy(self.handle, h))
+        return out
+
     def peer_copy(self, dst_ptr, src_ptr, nbytes, n_ctas=0):
         """SM-driven copy between raw device addresses (ints); either side may be peer memory."""
         self.check(self.lib.cgb_peer_copy(self.handle, C.c_void_p(int(dst_ptr)), C.c_void_p(int(src_ptr)), nbytes, n_ctas))

@@ -52,6 +52,21 @@ SIGNATURES = {
     "cgb_ipc_open": (C.c_int, [ctx_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "cgb_ipc_close": (C.c_int, [ctx_p, C.c_void_p]),
     "cgb_peer_copy": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]),
+    "cgb_party_graph_build": (C.c_int, [ctx_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "cgb_party_graph_build_host": (C.c_int, [ctx_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_int,
+                                             C.POINTER(C.c_void_p)]),
+    "cgb_party_graph_destroy": (C.c_int, [ctx_p, C.c_void_p]),
+    "cgb_party_graph_num_local": (C.c_uint32, [C.c_void_p]),
+    "cgb_party_graph_num_rows": (C.c_uint32, [C.c_void_p]),
+    "cgb_party_graph_num_out_edges": (C.c_uint64, [C.c_void_p]),
+    "cgb_party_graph_offsets": (C.c_void_p, [C.c_void_p]),
+    "cgb_party_graph_vids": (C.c_void_p, [C.c_void_p]),
+    "cgb_party_graph_in_deg_raw": (C.c_void_p, [C.c_void_p]),
+    "cgb_party_graph_in_deg": (C.c_void_p, [C.c_void_p]),
+    "cgb_party_graph_is_border": (C.c_void_p, [C.c_void_p]),
+    "cgb_party_graph_rowptr": (C.c_void_p, [C.c_void_p]),
+    "cgb_party_graph_col": (C.c_void_p, [C.c_void_p]),
+    "cgb_party_graph_csr": (C.c_int, [ctx_p, C.c_void_p, C.POINTER(csr_p)]),
     "cgb_expand_rows": (C.c_int, [ctx_p, u32p, C.c_uint64, u64p, u64p, u64p, C.c_uint32]),
     "cgb_segsum": (C.c_int, [ctx_p, u32p, C.c_uint32, C.c_uint64, u64p, u64p, C.c_uint32, C.c_int]),
     "cgb_matmul": (C.c_int, [ctx_p, u64p, u64p, u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int]),

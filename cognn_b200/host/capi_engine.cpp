@@ -2,6 +2,7 @@
 // bench.py can drive the C++ engine through ctypes, and a C/C++ harness (the reference's harness.cpp:50-212 shape)
 // can link it directly.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -100,7 +101,10 @@ int cge_destroy(cge_engine* h) {
 int cge_add_party(cge_engine* h, int party, const int64_t* edges, uint64_t n_edges, const int64_t* tid, uint64_t n_vertices,
                   const double* feats_global, const int32_t* labels_global) {
     CGE_TRY(h, {
-        PartyGraph g = build_party_graph(edges, n_edges, tid, n_vertices, h->T, party);
+        // graph ingest + index vectors on the device (cgb_party_graph_build); COGNN_B200_INGEST=host keeps the host builder
+        const char* ing = getenv("COGNN_B200_INGEST");
+        PartyGraph g = (ing && std::string(ing) == "host") ? build_party_graph(edges, n_edges, tid, n_vertices, h->T, party)
+                                                           : build_party_graph_device(h->ctx, edges, n_edges, tid, n_vertices, h->T, party);
         const size_t n = g.vids.size();
         std::vector<double> feats(n * h->F);
         std::vector<int32_t> labels(n);

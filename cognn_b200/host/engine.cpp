@@ -123,6 +123,34 @@ PartyGraph build_party_graph(const int64_t* edges, size_t n_edges, const int64_t
     return g;
 }
 
+PartyGraph build_party_graph_device(cgb_ctx* ctx, const int64_t* edges, size_t n_edges, const int64_t* tid, size_t n_vertices,
+                                    int T, int me) {
+    cgb_party_graph* pg = nullptr;
+    ck(ctx, cgb_party_graph_build_host(ctx, edges, n_edges, tid, n_vertices, T, me, &pg), "cgb_party_graph_build_host");
+    PartyGraph g;
+    g.T = T;
+    g.me = me;
+    const uint32_t n = cgb_party_graph_num_local(pg);
+    g.offsets.assign(cgb_party_graph_offsets(pg), cgb_party_graph_offsets(pg) + T + 1);
+    g.vids.resize(n);
+    g.in_deg_raw.resize(n);
+    g.in_deg.resize(n);
+    g.is_border.resize(n);
+    int rc = CGB_OK;
+    if (n) {
+        rc |= cgb_d2h(ctx, g.vids.data(), cgb_party_graph_vids(pg), (size_t)n * 8);
+        rc |= cgb_d2h(ctx, g.in_deg_raw.data(), cgb_party_graph_in_deg_raw(pg), (size_t)n * 8);
+        rc |= cgb_d2h(ctx, g.in_deg.data(), cgb_party_graph_in_deg(pg), (size_t)n * 8);
+        rc |= cgb_d2h(ctx, g.is_border.data(), cgb_party_graph_is_border(pg), (size_t)n);
+    }
+    rc |= cgb_ctx_sync(ctx);
+    if (rc == CGB_OK) rc = cgb_party_graph_csr(ctx, pg, &g.csr);
+    std::string err = rc == CGB_OK ? "" : cgb_last_error(ctx);
+    cgb_party_graph_destroy(ctx, pg);
+    if (rc != CGB_OK) throw std::runtime_error("build_party_graph_device: " + err);
+    return g;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // device matrices
 // ------------------------------------------------------------------------------------------------------------------
@@ -700,7 +728,12 @@ void SSGcnEngine::add_party(const PartyGraph& g, const double* feats_local, cons
         const double sc = std::pow((double)g.in_deg_raw[i] + 1.0, -0.5);
         for (uint32_t j = 0; j < im.F; ++j) pd.feats[(size_t)i * im.F + j] = feats_local[(size_t)i * im.F + j] * sc;
     }
-    ck(im.ctx, cgb_csr_create(im.ctx, g.rowptr.data(), g.col.data(), g.offsets[im.T], g.col.size(), n, &pd.csr), "cgb_csr_create");
+    if (g.csr) {  // device ingest: the CSR is resident already
+        pd.csr = g.csr;
+        pd.g.csr = nullptr;
+    } else {
+        ck(im.ctx, cgb_csr_create(im.ctx, g.rowptr.data(), g.col.data(), g.offsets[im.T], g.col.size(), n, &pd.csr), "cgb_csr_create");
+    }
     // normaliser (gcn.h:219-221): deg == 0 ? 0 : enc((deg+1)^-1/2); PreScatter is handed inDeg as well (ssk.h:739)
     std::vector<uint64_t> nv(n);
     for (uint32_t i = 0; i < n; ++i)

@@ -64,9 +64,16 @@ struct PartyGraph {
     std::vector<uint64_t> in_deg;      // localVertexInDeg after the -r 1 dummy rule
     std::vector<uint32_t> rowptr, col;
     std::vector<uint8_t> is_border;    // isLocalVertexBorder (graph_io_util.h:169)
+    cgb_csr* csr = nullptr;            // device ingest: the gather CSR is already resident (rowptr / col stay empty);
+                                       // ownership passes to the engine in add_party
 };
 // edges: n_edges x 2 (src, dst) directed entries as in the .edge file; tid: vertex -> party (the .part file)
 PartyGraph build_party_graph(const int64_t* edges, size_t n_edges, const int64_t* tid, size_t n_vertices, int T, int me);
+// the same derivation by device passes (cgb_party_graph_build_host: scans, one edge pass, radix sort); the CSR never visits
+// the host, only the per-vertex arrays come back.  This is what the engine's loaders use; the host builder above remains
+// as the reference-shaped restatement the tests compare against.
+PartyGraph build_party_graph_device(cgb_ctx* ctx, const int64_t* edges, size_t n_edges, const int64_t* tid, size_t n_vertices,
+                                    int T, int me);
 
 struct Metrics {
     uint64_t iter;

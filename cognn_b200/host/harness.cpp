@@ -249,7 +249,11 @@ int main(int argc, char* argv[]) {
         auto t_pre = std::chrono::high_resolution_clock::now();
         for (int p = 0; p < T; ++p) {
             if (!comm->is_local(p)) continue;
-            PartyGraph g = build_party_graph(edges.data(), edges.size() / 2, tid.data(), N, T, p);
+            // graph tile + index vectors (graph_io_util.h:40-208, ssk.h:295-534) by device passes; COGNN_B200_INGEST=host keeps
+            // the host builder
+            const char* ing = getenv("COGNN_B200_INGEST");
+            PartyGraph g = (ing && std::string(ing) == "host") ? build_party_graph(edges.data(), edges.size() / 2, tid.data(), N, T, p)
+                                                               : build_party_graph_device(ctx, edges.data(), edges.size() / 2, tid.data(), N, T, p);
             std::vector<double> fl(g.vids.size() * F);
             std::vector<int32_t> ll(g.vids.size());
             for (size_t i = 0; i < g.vids.size(); ++i) {

@@ -131,6 +131,39 @@ int cgb_expand_rows(cgb_ctx* ctx, const uint32_t* d_idx, uint64_t n_out, const u
 int cgb_segsum(cgb_ctx* ctx, const uint32_t* d_segptr, uint32_t n_seg, uint64_t n_in, const uint64_t* d_in,
                uint64_t* d_out, uint32_t D, int dup);
 
+/* ---- graph ingest + index vectors on the device ------------------------------------------------ */
+/* What a party derives from the reference's .edge and .part files before the first iteration: graphTilesFromEdgeList
+ * (graph_io_util.h:40-208), GraphTile finalize (graph.h:607-641) and the index vectors of
+ * SSEdgeCentricAlgoKernel (ss_vertex_centric_algo_kernel.h:295-534, with -r 1), flattened into
+ *   vids        n_local      localVertexPos: the party's vertex ids, ascending
+ *   offsets     T + 1 (host) first output row of each destination party (row = offsets[tid[d]] + index of d in its party)
+ *   rowptr/col  ONE CSR-by-destination over all of the party's out-edges (rows = destinations of party 0, 1, ...;
+ *               sources ascending inside a row, repeated edges kept): updateSrcVertexPos / updateDstVertexPos of every t
+ *   in_deg_raw  in-degree over ALL edges (local, graph.h:627-632, and remote, graph_io_util.h:170-175)
+ *   in_deg      the same after the dummy rule of ssk.h:412-418 (+1 for a vertex without a LOCAL in-edge)
+ *   is_border   isLocalVertexBorder (graph_io_util.h:169)
+ * d_edges: n_edges x 2 int64 (src, dst) as in the .edge file, 16-byte aligned; d_tid: n_vertices int64 (the .part file).
+ * Everything is computed by device passes (scans, one edge pass, a radix sort); synchronises.  T <= 16. */
+typedef struct cgb_party_graph cgb_party_graph;
+int cgb_party_graph_build(cgb_ctx* ctx, const int64_t* d_edges, uint64_t n_edges, const int64_t* d_tid, uint64_t n_vertices,
+                          int T, int me, cgb_party_graph** out);
+/* same from HOST arrays (uploaded first) */
+int cgb_party_graph_build_host(cgb_ctx* ctx, const int64_t* h_edges, uint64_t n_edges, const int64_t* h_tid,
+                               uint64_t n_vertices, int T, int me, cgb_party_graph** out);
+int cgb_party_graph_destroy(cgb_ctx* ctx, cgb_party_graph* g);
+uint32_t cgb_party_graph_num_local(const cgb_party_graph* g);
+uint32_t cgb_party_graph_num_rows(const cgb_party_graph* g);
+uint64_t cgb_party_graph_num_out_edges(const cgb_party_graph* g);
+const uint32_t* cgb_party_graph_offsets(const cgb_party_graph* g);    /* HOST, T + 1 */
+const uint64_t* cgb_party_graph_vids(const cgb_party_graph* g);       /* device pointers from here on */
+const uint64_t* cgb_party_graph_in_deg_raw(const cgb_party_graph* g);
+const uint64_t* cgb_party_graph_in_deg(const cgb_party_graph* g);
+const uint8_t* cgb_party_graph_is_border(const cgb_party_graph* g);
+const uint32_t* cgb_party_graph_rowptr(const cgb_party_graph* g);
+const uint32_t* cgb_party_graph_col(const cgb_party_graph* g);
+/* the gather-sum CSR (with its balanced work list) of the party's out-edges, ready for cgb_gather_sum */
+int cgb_party_graph_csr(cgb_ctx* ctx, const cgb_party_graph* g, cgb_csr** out);
+
 /* ---- (2) dense contraction mod 2^64 ---------------------------------------------------------------------- */
 /* C (M x N) = (accumulate ? C : 0) + op(A) * B.  op(A) = A (M x K), or A^T with A stored K x M if transA. */
 int cgb_matmul(cgb_ctx* ctx, const uint64_t* d_A, const uint64_t* d_B, uint64_t* d_C, uint32_t M, uint32_t K,
