@@ -225,6 +225,9 @@ struct Side {
     size_t h_prob_cap = 0;
     std::vector<DMat> upd_recv;  // helper side: masked sums received from the other owners
     DMat delta, S;
+    // dealer emulation temporaries (offline phase): grow-only members, so that phase neither allocates nor synchronises
+    // after the first epoch and can be replayed as a CUDA graph like the online phase
+    DMat dl_U0, dl_V0, dl_Z0, dl_a0, dl_b0, dl_c0, dl_zero_mat, dl_zero_vec, dl_negc, dl_r;
 };
 
 struct PartyData {
@@ -261,14 +264,16 @@ struct SSGcnEngine::Impl {
         cudaGraphExec_t exec = nullptr;
         uint64_t launches = 0, words = 0, rounds = 0;
         std::vector<std::pair<uint32_t, uint32_t>> shapes;  // rows x cols of every side tensor after this iteration
-    } graph[6];
+    } graph[6], deal_graph[6];
     // the host-side shape of every tensor a side holds: a replayed graph changes the contents but runs no host code, so
     // the shapes recorded when the iteration was captured are put back (device pointers never change after epoch 0)
     template <typename Fn>
     void for_side_mats(Fn&& fn) {
         for_sides([&](Side& s) {
             DMat* mats[] = {&s.X, &s.X_backup, &s.W[0], &s.W[1], &s.h_t[0], &s.h_t[1], &s.z[0], &s.z[1], &s.g, &s.Xp, &s.V,
-                            &s.Y, &s.m, &s.tmp, &s.tmp2, &s.P, &s.Ppeer, &s.grad, &s.prob, &s.res_in, &s.res_plain, &s.res_plain2};
+                            &s.Y, &s.m, &s.tmp, &s.tmp2, &s.P, &s.Ppeer, &s.grad, &s.prob, &s.res_in, &s.res_plain, &s.res_plain2,
+                            &s.mmU[0], &s.mmU[1], &s.mmV[0], &s.mmV[1], &s.mmZ[0], &s.mmZ[1], &s.rmA[0], &s.rmA[1], &s.rmB[0],
+                            &s.rmB[1], &s.rmC[0], &s.rmC[1], &s.delta, &s.S, &s.mm_mine, &s.mm_peer, &s.rm_mine, &s.rm_peer};
             for (DMat* m : mats) fn(*m);
         });
     }
@@ -320,7 +325,7 @@ struct SSGcnEngine::Impl {
             prg(K_MM_Z0, it, s.owner, sub, s.mmZ[sub], M, N);
         } else {
             // Z1 = (U0+U1)(V0+V1) - Z0
-            DMat U0, V0, Z0;
+            DMat &U0 = s.dl_U0, &V0 = s.dl_V0, &Z0 = s.dl_Z0;
             prg(K_MM_U0, it, s.owner, sub, U0, M, K);
             prg(K_MM_V0, it, s.owner, sub, V0, K, N);
             prg(K_MM_Z0, it, s.owner, sub, Z0, M, N);
@@ -331,7 +336,6 @@ struct SSGcnEngine::Impl {
             s.mmZ[sub].resize(ctx, M, N);
             ck(ctx, cgb_matmul(ctx, U0.p, V0.p, s.mmZ[sub].p, M, K, N, 0, 0), "cgb_matmul(dealer)");
             vsub(s.mmZ[sub].p, Z0.p, s.mmZ[sub].p, s.mmZ[sub].n());
-            ck(ctx, cgb_ctx_sync(ctx), "sync");  // U0/V0/Z0 are freed at scope exit
         }
     }
     // online: [E_i | F_i] = [A - U | B - V] in one message
@@ -364,7 +368,7 @@ struct SSGcnEngine::Impl {
             prg(K_RM_B0, it, s.owner, sub, s.rmB[sub], 1, rows);
             prg(K_RM_C0, it, s.owner, sub, s.rmC[sub], rows, D);
         } else {
-            DMat a0, b0, c0;
+            DMat &a0 = s.dl_a0, &b0 = s.dl_b0, &c0 = s.dl_c0;
             prg(K_RM_A0, it, s.owner, sub, a0, rows, D);
             prg(K_RM_B0, it, s.owner, sub, b0, 1, rows);
             prg(K_RM_C0, it, s.owner, sub, c0, rows, D);
@@ -373,7 +377,7 @@ struct SSGcnEngine::Impl {
             vadd(a0.p, s.rmA[sub].p, a0.p, a0.n());
             vadd(b0.p, s.rmB[sub].p, b0.p, b0.n());
             // c1 = (a0+a1) * (b0+b1)[row] - c0, with the generic kernel: out = c + e*b' + fv*a' + e*fv, a' = b' = 0, c = -c0
-            DMat zero_mat, zero_vec, negc;
+            DMat &zero_mat = s.dl_zero_mat, &zero_vec = s.dl_zero_vec, &negc = s.dl_negc;
             zero_mat.resize(ctx, rows, D);
             zero_vec.resize(ctx, 1, rows);
             ck(ctx, cgb_memset(ctx, zero_mat.p, 0, zero_mat.n() * 8), "memset");
@@ -383,7 +387,6 @@ struct SSGcnEngine::Impl {
             s.rmC[sub].resize(ctx, rows, D);
             ck(ctx, cgb_rowmul_beaver_finish(ctx, a0.p, b0.p, zero_mat.p, zero_vec.p, negc.p, s.rmC[sub].p, rows, D, 0, -1),
                "rowmul(dealer)");
-            ck(ctx, cgb_ctx_sync(ctx), "sync");
         }
     }
     void rm_prepare(Side& s, uint64_t, int sub, const DMat& x, const DMat* scaler) {
@@ -442,7 +445,7 @@ struct SSGcnEngine::Impl {
         if (s.share != 0) return;
         PartyData& pd = party[s.owner];
         const uint32_t n_rows = pd.g.offsets[T];
-        DMat r;
+        DMat& r = s.dl_r;
         prg(K_OM_R, it, s.owner, 0, r, s.n, D);
         s.S.resize(ctx, n_rows, D);
         for (int t = 0; t < T; ++t) {
@@ -452,7 +455,6 @@ struct SSGcnEngine::Impl {
         s.delta.resize(ctx, n_rows, D);
         ck(ctx, cgb_gather_sum(ctx, pd.csr, r.p, nullptr, s.delta.p, D), "gather(dealer)");
         vsub(s.delta.p, s.S.p, s.delta.p, s.delta.n());
-        ck(ctx, cgb_ctx_sync(ctx), "sync");  // r freed at scope exit
     }
 
     // everything the dealer hands out for iteration `it` (shapes per SURVEY 3.4)
@@ -698,6 +700,8 @@ SSGcnEngine::~SSGcnEngine() {
     if (impl_->profile)
         for (auto& kv : impl_->phase_s) fprintf(stderr, "::%s took %lf seconds (all iterations)\n", kv.first.c_str(), kv.second);
     for (auto& g : impl_->graph)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto& g : impl_->deal_graph)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     cgb_ctx_set_prg_stream_bias(impl_->ctx, nullptr);
     cgb_free(impl_->ctx, impl_->d_bias);
@@ -973,6 +977,54 @@ static void ckc(cudaError_t e, const char* what) {
     if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+// runs `body` eagerly, or records it into `ig` (and launches the new graph), or replays `ig`
+template <typename Body>
+static void run_phase(SSGcnEngine::Impl& im, cudaStream_t stream, bool use_graph, SSGcnEngine::Impl::IterGraph& ig, bool online,
+                      Body&& body) {
+    cgb_ctx* ctx = im.ctx;
+    if (!use_graph) {
+        body();
+        return;
+    }
+    if (ig.exec) {
+        ckc(cudaGraphLaunch(ig.exec, stream), "cudaGraphLaunch");
+        im.replayed_launches += ig.launches;
+        im.comm->words_sent += ig.words;
+        im.comm->rounds += ig.rounds;
+        if (online) im.graph_replays++;
+        size_t k = 0;
+        im.for_side_mats([&](DMat& m) {
+            m.rows = ig.shapes[k].first;
+            m.cols = ig.shapes[k].second;
+            ++k;
+        });
+        return;
+    }
+    const uint64_t l0 = cgb_ctx_launch_count(ctx), w0 = im.comm->words_sent, r0 = im.comm->rounds;
+    cudaGraph_t g = nullptr;
+    ckc(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+    g_capturing = true;
+    try {
+        body();
+    } catch (...) {
+        g_capturing = false;
+        cudaStreamEndCapture(stream, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+    }
+    g_capturing = false;
+    ckc(cudaStreamEndCapture(stream, &g), "cudaStreamEndCapture");
+    ckc(cudaGraphInstantiate(&ig.exec, g, 0), "cudaGraphInstantiate");
+    cudaGraphDestroy(g);
+    ig.launches = cgb_ctx_launch_count(ctx) - l0;  // counted once while recording = the launch right below
+    ig.words = im.comm->words_sent - w0;
+    ig.rounds = im.comm->rounds - r0;
+    ig.shapes.clear();
+    im.for_side_mats([&](DMat& m) { ig.shapes.push_back({m.rows, m.cols}); });
+    im.graph_captures++;
+    ckc(cudaGraphLaunch(ig.exec, stream), "cudaGraphLaunch");
+}
+
 void SSGcnEngine::run(uint64_t n_iters) {
     Impl& im = *impl_;
     cgb_ctx* ctx = im.ctx;
@@ -981,59 +1033,22 @@ void SSGcnEngine::run(uint64_t n_iters) {
         const uint64_t it = iter_;
         const int ph = (int)(it % 6);
         im.comm->cur_iter = it;
+        // eager in the first epoch, while tests record the transcript, or while phases are profiled; otherwise the first
+        // later occurrence of this iteration index is captured and every further one replays the graph
+        const bool use_graph = im.graphs_enabled && !im.profile && !im.comm->record && it >= 6 && stream != nullptr;
         auto t_deal = std::chrono::high_resolution_clock::now();
         *im.h_bias = (it - (uint64_t)ph) << 16;  // epoch part of every PRG stream id of this iteration (see stream_id)
         ck(ctx, cgb_h2d(ctx, im.d_bias, im.h_bias, 8), "h2d");
-        im.deal_iteration(it);  // offline phase (dealer emulation), timed separately
+        // offline phase (dealer emulation), timed separately
+        run_phase(im, stream, use_graph, im.deal_graph[ph], false, [&] { im.deal_iteration(it); });
         ck(ctx, cgb_ctx_sync(ctx), "sync");
         auto t0 = std::chrono::high_resolution_clock::now();
         seconds_offline += std::chrono::duration<double>(t0 - t_deal).count();
 
-        // eager in the first epoch, while tests record the transcript, or while phases are profiled; otherwise the first
-        // later occurrence of this iteration index is captured and every further one replays the graph
-        const bool use_graph = im.graphs_enabled && !im.profile && !im.comm->record && it >= 6 && stream != nullptr;
-        Impl::IterGraph& ig = im.graph[ph];
-        if (use_graph && ig.exec) {
-            ckc(cudaGraphLaunch(ig.exec, stream), "cudaGraphLaunch");
-            im.replayed_launches += ig.launches;
-            im.comm->words_sent += ig.words;
-            im.comm->rounds += ig.rounds;
-            im.graph_replays++;
-            size_t k = 0;
-            im.for_side_mats([&](DMat& m) {
-                m.rows = ig.shapes[k].first;
-                m.cols = ig.shapes[k].second;
-                ++k;
-            });
-            if (ph == 1)
-                for (auto& kv : im.own) im.metrics_pending.push_back(kv.first);
-        } else if (use_graph) {
-            const uint64_t l0 = cgb_ctx_launch_count(ctx), w0 = im.comm->words_sent, r0 = im.comm->rounds;
-            cudaGraph_t g = nullptr;
-            ckc(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
-            g_capturing = true;
-            try {
-                online_iteration(im, it);
-            } catch (...) {
-                g_capturing = false;
-                cudaStreamEndCapture(stream, &g);
-                if (g) cudaGraphDestroy(g);
-                throw;
-            }
-            g_capturing = false;
-            ckc(cudaStreamEndCapture(stream, &g), "cudaStreamEndCapture");
-            ckc(cudaGraphInstantiate(&ig.exec, g, 0), "cudaGraphInstantiate");
-            cudaGraphDestroy(g);
-            ig.launches = cgb_ctx_launch_count(ctx) - l0;  // counted once while recording = the launch right below
-            ig.words = im.comm->words_sent - w0;
-            ig.rounds = im.comm->rounds - r0;
-            ig.shapes.clear();
-            im.for_side_mats([&](DMat& m) { ig.shapes.push_back({m.rows, m.cols}); });
-            im.graph_captures++;
-            ckc(cudaGraphLaunch(ig.exec, stream), "cudaGraphLaunch");
-        } else {
-            online_iteration(im, it);
-        }
+        const bool replay = use_graph && im.graph[ph].exec;
+        run_phase(im, stream, use_graph, im.graph[ph], true, [&] { online_iteration(im, it); });
+        if (replay && ph == 1)
+            for (auto& kv : im.own) im.metrics_pending.push_back(kv.first);
         ck(ctx, cgb_ctx_sync(ctx), "sync");
         for (int owner : im.metrics_pending) metrics_.push_back(owner_metrics(im, it, owner, verbose));
         im.metrics_pending.clear();
