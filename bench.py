@@ -565,7 +565,7 @@ def main():
     n_rows = n_local * P
     alg = algorithmic_bytes(n_rows, E, D)
     achieved = alg / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "gather_chunk_kernel<2,8,4,128,1536> (cgb_gather_sum)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "gather_chunk_kernel<4,4,4,128,1024,2> (cgb_gather_sum, 256-bit row loads)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(D), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "kernel_ms": kernel_ms,
                 "frac_of_8TBs_nominal": achieved / 8000.0}

@@ -18,6 +18,12 @@
 
 #include "common.cuh"
 
+// 256-bit row accesses by default (round 1b: +22 % at D = 16, +34 % at D = 64, +42 % at D = 128 over the 128-bit form,
+// profiles/r1b_sweep_gather_vec*.jsonl); CGB_GATHER_VEC=2 selects the 128-bit kernels for A/B runs
+#ifndef CGB_GATHER_DEFAULT_VEC
+#define CGB_GATHER_DEFAULT_VEC 4
+#endif
+
 namespace {
 
 struct GatherArgs {
@@ -66,6 +72,29 @@ struct Acc<2> {
     __device__ __forceinline__ void add(const Acc& o) { a += o.a; b += o.b; }
     __device__ __forceinline__ void store(u64* p) const { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(a, b); }
     __device__ __forceinline__ void store_cs(u64* p) const { st_cs_v2(p, a, b); }
+};
+
+// 256-bit accesses (LDG.E.256 / STG.E.256, new on sm_100): four u64 columns per lane, so a D = 16 row is one load
+// instruction of four lanes -- half the address arithmetic, shuffles and flag tests per byte of the 128-bit form
+template <>
+struct Acc<4> {
+    u64 a, b, c, d;
+    __device__ __forceinline__ void zero() { a = 0; b = 0; c = 0; d = 0; }
+    __device__ __forceinline__ void load_nc(const u64* p) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    }
+    // the piece paths (rows cut by a chunk boundary) are rare: plain 64-/128-bit accesses there
+    __device__ __forceinline__ void load_cg(const u64* p) {
+        a = ld_cg_u64(p); b = ld_cg_u64(p + 1); c = ld_cg_u64(p + 2); d = ld_cg_u64(p + 3);
+    }
+    __device__ __forceinline__ void add(const Acc& o) { a += o.a; b += o.b; c += o.c; d += o.d; }
+    __device__ __forceinline__ void store(u64* p) const {
+        reinterpret_cast<ulonglong2*>(p)[0] = make_ulonglong2(a, b);
+        reinterpret_cast<ulonglong2*>(p)[1] = make_ulonglong2(c, d);
+    }
+    __device__ __forceinline__ void store_cs(u64* p) const {
+        asm volatile("st.global.cs.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+    }
 };
 
 template <int LANES>
@@ -207,8 +236,8 @@ __device__ __forceinline__ u64* out_row(const ChunkArgs& a, uint32_t row) {
 // A row segment cut by a chunk boundary has been stored as a "piece"; count the arrival and, if this was the last
 // piece of the row, fold them.  Rare relative to the edge loop, so kept out of line.
 template <int VEC, int LANES>
-__device__ __noinline__ void piece_arrive(const ChunkArgs& a, uint32_t row, uint32_t ct, uint32_t col0, bool active,
-                                          int lane, unsigned mask) {
+__device__ __forceinline__ void piece_arrive_body(const ChunkArgs& a, uint32_t row, uint32_t ct, uint32_t col0, bool active,
+                                                  int lane, unsigned mask) {
     __threadfence();
     __syncwarp(mask);
     const uint32_t rb = __ldg(a.rowptr + row), re = __ldg(a.rowptr + row + 1);
@@ -237,9 +266,18 @@ __device__ __noinline__ void piece_arrive(const ChunkArgs& a, uint32_t row, uint
     }
 }
 
-template <int VEC, int LANES, int U, int BLOCK, int OCC_THREADS>
+template <int VEC, int LANES>
+__device__ __noinline__ void piece_arrive(const ChunkArgs& a, uint32_t row, uint32_t ct, uint32_t col0, bool active, int lane,
+                                          unsigned mask) {
+    piece_arrive_body<VEC, LANES>(a, row, ct, col0, active, lane, mask);
+}
+
+// IPL: column indices each lane holds per batch (a batch is LANES * IPL edges; narrow 256-bit groups of 2 or 4 lanes keep
+// 8 edges per batch this way, so U can stay above the lane count)
+template <int VEC, int LANES, int U, int BLOCK, int OCC_THREADS, int IPL = 1>
 __global__ void __launch_bounds__(BLOCK, OCC_THREADS / BLOCK)
 gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
+    constexpr int BATCH = LANES * IPL;
     constexpr int GROUPS = BLOCK / LANES;
     const int lane = threadIdx.x & (LANES - 1);
     const unsigned mask = group_mask<LANES>(threadIdx.x & 31);
@@ -272,16 +310,20 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
     uint32_t head_row = 0;
     Acc<VEC> acc;
     acc.zero();
-    uint32_t my = (e + lane < end) ? __ldg(a.colf + e + lane) : 0u;
+    uint32_t my[IPL], nxt[IPL];
+#pragma unroll
+    for (int i = 0; i < IPL; ++i) my[i] = (e + i * LANES + lane < end) ? __ldg(a.colf + e + i * LANES + lane) : 0u;
     while (e < end) {
-        const uint32_t n = min((uint32_t)LANES, end - e);
-        const uint32_t nxt = (e + LANES + lane < end) ? __ldg(a.colf + e + LANES + lane) : 0u;  // prefetch
-        for (uint32_t k0 = 0; k0 < n; k0 += U) {
+        const uint32_t n = min((uint32_t)BATCH, end - e);
+#pragma unroll
+        for (int i = 0; i < IPL; ++i)  // prefetch the next batch of indices
+            nxt[i] = (e + BATCH + i * LANES + lane < end) ? __ldg(a.colf + e + BATCH + i * LANES + lane) : 0u;
+        auto sub_batch = [&](const uint32_t k0) {
             Acc<VEC> v[U];
             uint32_t id[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                id[u] = __shfl_sync(mask, my, k0 + u, LANES);
+                id[u] = __shfl_sync(mask, my[(k0 + u) / LANES], (k0 + u) % LANES, LANES);
                 if (active && (k0 + u < n)) v[u].load_nc(a.x + (size_t)(id[u] & ~CGB_END_FLAG) * a.D + col0);
                 else v[u].zero();
             }
@@ -323,9 +365,30 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
                     }
                 }
             }
+        };
+        if constexpr (IPL == 1) {  // the register-lean form the 128-bit kernels were tuned with (no unrolling over k0)
+            for (uint32_t k0 = 0; k0 < n; k0 += U) sub_batch(k0);
+        } else {  // unrolled, so that my[(k0 + u) / LANES] is a register, not a local-memory array
+#pragma unroll
+            for (uint32_t k0 = 0; k0 < (uint32_t)BATCH; k0 += U) {
+                if (k0 >= n) break;
+                sub_batch(k0);
+            }
         }
-        e += LANES;
-        my = nxt;
+        e += BATCH;
+#pragma unroll
+        for (int i = 0; i < IPL; ++i) my[i] = nxt[i];
+    }
+    // The 256-bit instantiations keep a few registers spilled around the main loop; with the piece fold out of line
+    // (a call, as below) the IPL = 2 variant returned wrong columns 1..3 of every lane for rows cut by a chunk boundary
+    // (accumulator halves restored from the stack after the call), so they inline it.
+    if constexpr (VEC == 4) {
+        if (have_head) piece_arrive_body<VEC, LANES>(a, head_row, ct, col0, active, lane, mask);
+        if (open) {
+            if (active) acc.store((head_open ? a.piece_head : a.piece_tail) + (size_t)c * a.D + col0);
+            piece_arrive_body<VEC, LANES>(a, __ldg(a.nz_row + k), ct, col0, active, lane, mask);
+        }
+        return;
     }
     if (have_head) piece_arrive<VEC, LANES>(a, head_row, ct, col0, active, lane, mask);
     if (open) {  // the chunk ends inside a row
@@ -566,6 +629,29 @@ inline Shape pick_shape(uint32_t D, bool aligned16) {
     return s;
 }
 inline bool is_aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline bool is_aligned32(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+// 256-bit shape for the edge-balanced kernel: D a multiple of 4 columns and every base 32-byte aligned
+inline Shape pick_shape4(uint32_t D) {
+    Shape s;
+    s.vec = 4;
+    const uint32_t need = D / 4;
+    int lanes = 2;
+    while ((uint32_t)lanes < need && lanes < 32) lanes *= 2;
+    s.lanes = lanes;
+    s.n_ct = (D + 4 * lanes - 1) / (4 * lanes);
+    return s;
+}
+template <typename F>
+int dispatch_shape4(const Shape& s, F&& f) {
+#define CGB_CASE4(L, U_)                          \
+    if (s.vec == 4 && s.lanes == L) {             \
+        f(std::integral_constant<int, 4>(), std::integral_constant<int, L>(), std::integral_constant<int, U_>()); \
+        return 0;                                 \
+    }
+    CGB_CASE4(2, 2) CGB_CASE4(4, 4) CGB_CASE4(8, 8) CGB_CASE4(16, 8) CGB_CASE4(32, 8)
+#undef CGB_CASE4
+    return -1;
+}
 
 template <typename F>
 int dispatch_shape(const Shape& s, F&& f) {
@@ -749,7 +835,14 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
     if (csr->n_rows == 0) return CGB_OK;
     bool al = is_aligned16(d_x) && is_aligned16(d_delta) && is_aligned16(d_y);
     for (int t = 0; t < n_blk; ++t) al = al && is_aligned16(blk_base[t]);
-    const Shape s = pick_shape(D, al);
+    Shape s = pick_shape(D, al);
+    // CGB_GATHER_VEC=4|2: 256-bit accesses when the shape allows (D % 4 == 0, 32-byte aligned bases), else 128 / 64 bit
+    static const int want_vec = getenv("CGB_GATHER_VEC") ? atoi(getenv("CGB_GATHER_VEC")) : CGB_GATHER_DEFAULT_VEC;
+    static const bool async_impl = getenv("CGB_GATHER_IMPL") && std::string(getenv("CGB_GATHER_IMPL")) == "async";
+    bool al32 = is_aligned32(d_x) && is_aligned32(d_delta) && is_aligned32(d_y);
+    for (int t = 0; t < n_blk; ++t) al32 = al32 && is_aligned32(blk_base[t]);
+    const bool vec4 = want_vec == 4 && D % 4 == 0 && al32 && !use_row_schedule() && !async_impl;
+    if (vec4) s = pick_shape4(D);
     CGB_REQUIRE(ctx, n_blk == 0 || !use_row_schedule(), "cgb_gather_sum_blocks: needs the edge-balanced schedule");
     if (!use_row_schedule()) {
         CGB_REQUIRE(ctx, csr->n_src_rows < CGB_END_FLAG, "cgb_gather_sum: source rows must fit 31 bits");
@@ -819,6 +912,44 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
         }
         static const int use_u8 = getenv("CGB_GATHER_U8") ? 1 : 0;
         static const int occ = getenv("CGB_GATHER_OCC") ? atoi(getenv("CGB_GATHER_OCC")) : 1536;
+        if (vec4) {
+            static const int occ4 = getenv("CGB_GATHER_OCC") ? atoi(getenv("CGB_GATHER_OCC")) : 1024;
+            static const int u4 = getenv("CGB_GATHER_U") ? atoi(getenv("CGB_GATHER_U")) : 4;
+            int rc4 = dispatch_shape4(s, [&](auto V, auto L, auto U_) {
+                constexpr int BLOCK = 128;
+                constexpr int VV = decltype(V)::value, LL = decltype(L)::value;
+                constexpr int GROUPS = BLOCK / LL;
+                constexpr int UU = decltype(U_)::value;
+                constexpr int UH = UU >= 4 ? 4 : UU;
+                constexpr int U2 = UU >= 2 ? 2 : UU;
+                const unsigned blocks = (unsigned)((total + GROUPS - 1) / GROUPS);
+                static const int ipl = getenv("CGB_GATHER_IPL") ? atoi(getenv("CGB_GATHER_IPL")) : 2;
+                if (ipl == 2 && LL <= 4) {  // 8 (LANES = 4) or 4 (LANES = 2) edges per batch
+                    constexpr int B2 = LL * 2;
+                    constexpr int U8 = B2 >= 8 ? 8 : B2;
+                    constexpr int U4 = B2 >= 4 ? 4 : B2;
+                    if (u4 == 8) {
+                        if (occ4 >= 1024) gather_chunk_kernel<VV, LL, U8, BLOCK, 1024, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                        else if (occ4 >= 768) gather_chunk_kernel<VV, LL, U8, BLOCK, 768, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                        else gather_chunk_kernel<VV, LL, U8, BLOCK, 640, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                    } else {
+                        if (occ4 >= 1280) gather_chunk_kernel<VV, LL, U4, BLOCK, 1280, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                        else if (occ4 >= 1024) gather_chunk_kernel<VV, LL, U4, BLOCK, 1024, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                        else gather_chunk_kernel<VV, LL, U4, BLOCK, 896, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                    }
+                } else if (u4 == 2) {
+                    if (occ4 >= 1536) gather_chunk_kernel<VV, LL, U2, BLOCK, 1536><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                    else gather_chunk_kernel<VV, LL, U2, BLOCK, 1024><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                } else {
+                    if (occ4 >= 1536) gather_chunk_kernel<VV, LL, UH, BLOCK, 1536><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                    else if (occ4 >= 1280) gather_chunk_kernel<VV, LL, UH, BLOCK, 1280><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                    else gather_chunk_kernel<VV, LL, UH, BLOCK, 1024><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                }
+            });
+            CGB_REQUIRE(ctx, rc4 == 0, "cgb_gather_sum: no 256-bit kernel for this shape");
+            CGB_CHECK_LAUNCH(ctx, "gather_chunk_kernel");
+            return CGB_OK;
+        }
         int rc = dispatch_shape(s, [&](auto V, auto L, auto U_) {
             constexpr int BLOCK = 128;
             constexpr int VV = decltype(V)::value, LL = decltype(L)::value;

@@ -236,3 +236,34 @@ def test_peer_copy_is_a_copy(cgb, n_words, n_ctas):
     assert bool((dst[n_words:] == -1).all())
     with pytest.raises(Exception):
         cgb.peer_copy(dst.data_ptr() + 8, src.data_ptr(), 16, 0)  # 16-byte alignment is part of the contract
+
+
+@pytest.mark.parametrize("env", [{"CGB_GATHER_VEC": "2"}, {"CGB_GATHER_VEC": "4", "CGB_GATHER_IPL": "1"},
+                                 {"CGB_GATHER_IMPL": "rows"}, {"CGB_GATHER_IMPL": "async", "CGB_GATHER_VEC": "2"}])
+def test_gather_alternative_kernels_in_subprocess(env):
+    """The default is the 256-bit edge-balanced kernel; the 128-bit, row-schedule and cp.async variants stay selectable for
+    A/B measurements (environment read once per process), so they are checked against the oracle in a child process."""
+    import os
+    import subprocess
+    import sys
+
+    code = r"""
+import numpy as np, sys
+sys.path.insert(0, %r)
+import cognn_b200
+from oracle import pyoracle
+from tests.util import power_law_csr, rand_u64, to_dev, to_np
+pyoracle.build()
+ctx = cognn_b200.Context(0)
+for D in (4, 16, 40, 64, 128):
+    rng = np.random.default_rng(D)
+    rowptr, col = power_law_csr(rng, 2000, 1500, 30000)
+    x, delta = rand_u64(rng, 1500, D), rand_u64(rng, 2000, D)
+    csr = ctx.csr_create(to_dev(rowptr, "cpu"), to_dev(col, "cpu"), 1500)
+    for dl in (None, delta):
+        got = to_np(ctx.gather_sum(csr, to_dev(x), None if dl is None else to_dev(dl)))
+        assert np.array_equal(got, pyoracle.gather_sum_csr(rowptr, col, x, dl)), D
+print("ok")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
