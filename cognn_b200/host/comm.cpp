@@ -82,7 +82,17 @@ public:
         NCCL_CK(ncclCommInitRank(&comm_, world, id, rank));
     }
     ~NcclComm() override {
+        if (d_flag_) cudaFree(d_flag_);
         if (comm_) ncclCommDestroy(comm_);
+    }
+    void barrier() override {
+        cudaStream_t st = (cudaStream_t)cgb_ctx_stream(ctx_);
+        if (!d_flag_) {
+            if (cudaMalloc(&d_flag_, sizeof(int)) != cudaSuccess) throw std::runtime_error("NcclComm: cudaMalloc failed");
+            cudaMemsetAsync(d_flag_, 0, sizeof(int), st);
+        }
+        NCCL_CK(ncclAllReduce(d_flag_, d_flag_, 1, ncclInt, ncclSum, comm_, st));
+        if (cudaStreamSynchronize(st) != cudaSuccess) throw std::runtime_error("NcclComm: barrier failed");
     }
     int world() const override { return world_; }
     bool is_local(int p) const override { return p == rank_; }
@@ -135,6 +145,7 @@ private:
     int rank_, world_;
     cgb_ctx* ctx_;
     ncclComm_t comm_ = nullptr;
+    int* d_flag_ = nullptr;
     std::vector<Post> posts_;
 };
 

@@ -1042,6 +1042,7 @@ void SSGcnEngine::run(uint64_t n_iters) {
         // offline phase (dealer emulation), timed separately
         run_phase(im, stream, use_graph, im.deal_graph[ph], false, [&] { im.deal_iteration(it); });
         ck(ctx, cgb_ctx_sync(ctx), "sync");
+        im.comm->barrier();  // every party has its correlations: online time below is protocol time, not dealer skew
         auto t0 = std::chrono::high_resolution_clock::now();
         seconds_offline += std::chrono::duration<double>(t0 - t_deal).count();
 

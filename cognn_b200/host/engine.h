@@ -41,6 +41,9 @@ public:
     virtual void post_send(int src, int dst, const uint64_t* d, size_t n, const std::string& tag) = 0;
     virtual void post_recv(int dst, int src, uint64_t* d, size_t n) = 0;
     virtual void exchange() = 0;
+    // all parties have reached this point and their streams are idle (no data message; used between the offline and the
+    // online phase so that one party's dealer time is not counted as another party's online waiting time)
+    virtual void barrier() {}
     bool record = false;        // keep a copy of every message sent by a local party (tests)
     uint64_t cur_iter = 0;
     std::vector<Message> transcript;
