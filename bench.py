@@ -568,7 +568,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": "gather_chunk_kernel<4,4,4,128,1024,2> (cgb_gather_sum, 256-bit row loads)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(D), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "kernel_ms": kernel_ms,
-                "frac_of_8TBs_nominal": achieved / 8000.0}
+                "frac_of_8TBs_nominal": achieved / 8000.0,
+                "note": "algorithmic bytes charge every edge a full 8*D-byte row read (SURVEY 8d, no cache-reuse credit); hub rows "
+                        "are served by L2, so `traffic` (DRAM bytes per launch, ncu) is below them and frac can exceed 1"}
 
     # ---- e2e: host buffers through the C-ABI host entry point, H2D + D2H inside the timed region -----------
     e2e = None
