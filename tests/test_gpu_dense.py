@@ -177,6 +177,22 @@ def test_ideal_softmax_bit_exact(cgb, oracle, n, C, spread):
     assert ((1 << f) - C <= tot).all() and (tot <= (1 << f)).all()
 
 
+def test_ideal_softmax_matches_committed_golden(cgb):
+    """The CUDA stand-in against tests/golden/ideal_softmax.json directly (no oracle run in between)."""
+    import json
+    import os
+
+    import torch
+
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ideal_softmax.json")))
+    shape = tuple(g["shape"])
+    z0 = np.array(g["z0"], dtype=np.uint64).reshape(shape)
+    z1 = np.array(g["z1"], dtype=np.uint64).reshape(shape)
+    P, d = cgb.ideal_softmax(to_dev(z0), to_dev(z1), torch.tensor(g["labels"], dtype=torch.int32, device="cuda"),
+                             g["train_rows"], g["f"])
+    assert to_np(P).ravel().tolist() == g["P"] and to_np(d).ravel().tolist() == g["pmy"]
+
+
 def test_sum_n_matches_oracle(cgb, oracle):
     rng = np.random.default_rng(8)
     for n in (1, 7, 4096, 100_001):

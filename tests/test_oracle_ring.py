@@ -192,3 +192,23 @@ def test_ideal_softmax_c_equals_numpy():
         zz = z.view(np.int64) / float(1 << f)
         e = np.exp(zz - zz.max(axis=1, keepdims=True))
         assert np.abs(p - e / e.sum(axis=1, keepdims=True)).max() < 2.0 / (1 << f)
+
+
+def test_softmax_golden_vectors():
+    """tests/golden/ideal_softmax.json (made by make_softmax_golden.py): the C oracle and its numpy restatement reproduce the
+    committed bits of the restated exp and of the prediction-layer stand-in."""
+    import json
+    import os
+
+    from oracle import pyoracle as po
+
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ideal_softmax.json")))
+    for x, bits in g["det_exp"].items():
+        assert int(np.float64(po.det_exp(float(x))).view(np.uint64)) == bits, x
+        assert int(po.det_exp_numpy(np.array([float(x)]))[0].view(np.uint64)) == bits, x
+    shape = tuple(g["shape"])
+    z0 = np.array(g["z0"], dtype=np.uint64).reshape(shape)
+    z1 = np.array(g["z1"], dtype=np.uint64).reshape(shape)
+    for fn in (po.ideal_softmax, po.ideal_softmax_numpy):
+        P, pmy = fn(z0, z1, np.array(g["labels"]), g["train_rows"], g["f"])
+        assert P.ravel().tolist() == g["P"] and pmy.ravel().tolist() == g["pmy"], fn.__name__
