@@ -156,7 +156,7 @@ private:
 
 // dealer PRG stream ids: same layout as the engine (DESIGN.md "Randomness"); `op` plays the role of the iteration
 enum Kind : uint64_t { K_MM_U0 = 5, K_MM_U1, K_MM_V0, K_MM_V1, K_MM_Z0, K_RM_A0, K_RM_A1, K_RM_B0, K_RM_B1, K_RM_C0,
-                       K_OM_R = 32, K_OM_S = 33, K_SPLIT = 34 };
+                       K_OM_R = 32, K_OM_S = 33, K_SPLIT = 34, K_RESHARE = 35 };
 inline uint64_t stream_id(uint64_t kind, uint64_t op, uint64_t owner, uint64_t sub) {
     return (kind << 48) | (op << 16) | (owner << 8) | sub;
 }
@@ -465,6 +465,130 @@ inline void getPlainShareVecVec(const ShareTensor& st, DoubleTensor& plain, uint
     for (size_t i = 0; i < rows; ++i)
         for (size_t j = 0; j < cols; ++j) plain[i][j] = h[i * cols + j];
 }
+
+#ifdef COGNN_SHIM_IDEAL_NONLINEAR
+// ---- 2PC-RESIDUAL stand-ins: IDEAL FUNCTIONALITY, **NOT SECURE** -------------------------------------------------------------
+// sci::twoPartyGCNRelu (gcn.h:549), sci::twoPartyGCNForwardNNPredictionWithoutWeight (gcn.h:578,591) and
+// sci::twoPartyGCNBackwardNNWithoutAH (gcn.h:705) are comparison / exponentiation protocols of the reference's MPC backend
+// (SCI-SilentOT) and are NOT replaced by this library.  Only when COGNN_SHIM_IDEAL_NONLINEAR is defined -- to run an epoch
+// end to end on test data -- the shim defines them as the same stand-in the engine uses: BOB sends its share to ALICE, ALICE
+// evaluates the function on the RECONSTRUCTED values (cgb_ideal_*: she sees the plaintext) and re-shares the result with a
+// dealer PRG stream both sides can derive.  Never define the macro in a deployment.
+namespace detail {
+// BOB: send shares, take the dealer stream(s) as new share(s).  ALICE: receive, return the peer's words.
+inline bool ideal_exchange(cognn_shim::Call& k, int party, const std::vector<uint64_t>& mine, std::vector<uint64_t>& peer) {
+    if (party == BOB) {
+        k.ch.send(mine);
+        return false;
+    }
+    k.ch.recv(peer);
+    if (peer.size() != mine.size()) cognn_shim::fatal("cognn_shim ideal stand-in", "share size mismatch");
+    return true;
+}
+inline void ideal_reshare(cognn_shim::Call& k, int party, int sub, const cognn_shim::Dev* plain, size_t rows, size_t cols, ShareVecVec& out) {
+    using namespace cognn_shim;
+    Dev r(k.c, rows * cols);
+    prg(k.c, k.rt.key, stream_id(K_RESHARE, k.op, k.owner, sub), r);
+    if (party == BOB) {
+        unflatten(r.down(), rows, cols, out);
+        return;
+    }
+    Dev o(k.c, rows * cols);
+    ok(k.c, cgb_sub(k.c, plain->p, r.p, o.p, o.n), "cgb_sub");
+    unflatten(o.down(), rows, cols, out);
+}
+}  // namespace detail
+
+inline void twoPartyGCNRelu(const ShareVecVec& in, ShareTensor& out, uint64_t coTid, int party) {
+    using namespace cognn_shim;
+    Call k(coTid, party);
+    size_t rows, cols;
+    std::vector<uint64_t> x = flatten(in, &rows, &cols), other;
+    if (!detail::ideal_exchange(k, party, x, other)) return detail::ideal_reshare(k, party, 0, nullptr, rows, cols, out);
+    Dev a(k.c, x.size()), b(k.c, x.size()), plain(k.c, x.size());
+    a.up(x);
+    b.up(other);
+    ok(k.c, cgb_ideal_relu(k.c, a.p, b.p, plain.p, x.size()), "cgb_ideal_relu");
+    detail::ideal_reshare(k, party, 0, &plain, rows, cols, out);
+}
+
+// p = softmax(z) (fixed point), p_minus_y = p - label; ALICE passes the one-hot label rows, BOB zeros (gcn.h:574-590);
+// the rows outside the training set are zeroed by the caller afterwards (gcn.h:639-641)
+inline void twoPartyGCNForwardNNPredictionWithoutWeight(const ShareVecVec& z, const ShareVecVec& label, ShareVecVec& p,
+                                                        ShareVecVec& p_minus_y, uint64_t coTid, int party) {
+    using namespace cognn_shim;
+    Call k(coTid, party);
+    size_t rows, cols, lr, lc;
+    std::vector<uint64_t> x = flatten(z, &rows, &cols), lab = flatten(label, &lr, &lc), other, other_lab;
+    if (lr != rows || lc != cols) fatal("twoPartyGCNForwardNNPredictionWithoutWeight", "label shape differs from the logits");
+    const bool alice = detail::ideal_exchange(k, party, x, other);
+    if (!alice) {
+        k.ch.send(lab);
+        detail::ideal_reshare(k, party, 0, nullptr, rows, cols, p);
+        return detail::ideal_reshare(k, party, 1, nullptr, rows, cols, p_minus_y);
+    }
+    k.ch.recv(other_lab);
+    if (other_lab.size() != lab.size()) fatal("twoPartyGCNForwardNNPredictionWithoutWeight", "label size mismatch");
+    std::vector<int32_t> cls(rows, 0);  // class of each row = position of the 1.0 in the reconstructed one-hot label
+    for (size_t i = 0; i < rows; ++i)
+        for (size_t j = 0; j < cols; ++j)
+            if (lab[i * cols + j] + other_lab[i * cols + j] != 0) cls[i] = (int32_t)j;
+    Dev a(k.c, x.size()), b(k.c, x.size()), P(k.c, x.size()), D(k.c, x.size());
+    a.up(x);
+    b.up(other);
+    void* dl = nullptr;
+    ok(k.c, cgb_malloc(k.c, (rows ? rows : 1) * sizeof(int32_t), &dl), "cgb_malloc");
+    if (rows) ok(k.c, cgb_h2d(k.c, dl, cls.data(), rows * sizeof(int32_t)), "cgb_h2d");
+    ok(k.c, cgb_ideal_softmax(k.c, a.p, b.p, (const int32_t*)dl, rows, (uint32_t)cols, rows, SCALER_BIT_LENGTH, P.p, D.p),
+       "cgb_ideal_softmax");
+    cgb_ctx_sync(k.c);
+    cgb_free(k.c, dl);
+    // rows whose reconstructed label is all zero (inference: zero_label on both sides) keep p_minus_y = p - 0
+    bool any_unlabelled = false;
+    std::vector<uint8_t> has(rows, 0);
+    for (size_t i = 0; i < rows; ++i) {
+        for (size_t j = 0; j < cols; ++j) has[i] |= (lab[i * cols + j] + other_lab[i * cols + j]) != 0;
+        any_unlabelled |= !has[i];
+    }
+    if (any_unlabelled) {
+        std::vector<uint64_t> hp = P.down(), hd = D.down();
+        for (size_t i = 0; i < rows; ++i)
+            if (!has[i])
+                for (size_t j = 0; j < cols; ++j) hd[i * cols + j] = hp[i * cols + j];
+        D.up(hd);
+    }
+    detail::ideal_reshare(k, party, 0, &P, rows, cols, p);
+    detail::ideal_reshare(k, party, 1, &D, rows, cols, p_minus_y);
+}
+
+// dstVec = in (.) ReLU'(z); g = dstVec * weightT unless this is the first layer (gcn.h:702-708)
+inline void twoPartyGCNBackwardNNWithoutAH(const ShareVecVec& in, const ShareVecVec& z, const ShareTensor& weightT, ShareVecVec& dstVec,
+                                           ShareVecVec& g, bool isFirstLayer, uint64_t coTid, int party) {
+    using namespace cognn_shim;
+    {
+        Call k(coTid, party);
+        size_t rows, cols, zr, zc;
+        std::vector<uint64_t> x = flatten(in, &rows, &cols), zz = flatten(z, &zr, &zc), ox, oz;
+        if (zr != rows || zc != cols) fatal("twoPartyGCNBackwardNNWithoutAH", "z shape differs from the gradient");
+        if (!detail::ideal_exchange(k, party, x, ox)) {
+            k.ch.send(zz);
+            detail::ideal_reshare(k, party, 0, nullptr, rows, cols, dstVec);
+        } else {
+            k.ch.recv(oz);
+            if (oz.size() != zz.size()) fatal("twoPartyGCNBackwardNNWithoutAH", "z size mismatch");
+            Dev g0(k.c, x.size()), g1(k.c, x.size()), z0(k.c, x.size()), z1(k.c, x.size()), plain(k.c, x.size());
+            g0.up(x);
+            g1.up(ox);
+            z0.up(zz);
+            z1.up(oz);
+            ok(k.c, cgb_ideal_relu_grad(k.c, g0.p, g1.p, z0.p, z1.p, plain.p, x.size()), "cgb_ideal_relu_grad");
+            detail::ideal_reshare(k, party, 0, &plain, rows, cols, dstVec);
+        }
+    }
+    if (!isFirstLayer) twoPartyGCNMatMul(dstVec, weightT, g, coTid, party);
+    else g.clear();
+}
+#endif  // COGNN_SHIM_IDEAL_NONLINEAR
 
 }  // namespace sci
 
