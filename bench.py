@@ -159,11 +159,10 @@ def setup_pipelined(torch, ctx, win, rowptr, col, rank, P, n_local, D, dev):
             "t0": torch.cuda.Event(enable_timing=True), "bar": torch.cuda.Event(enable_timing=True),
             "end": torch.cuda.Event(enable_timing=True),
             "slot_bytes": slot_bytes,
-            # transport of the pushes (profiles/r1_p2p_probe_n2.jsonl, r1_bench_n{2,4,8}_*): the SM copy kernel moves
-            # 690 GB/s per GPU against 537 GB/s for the copy engines, but takes SM slots from the gathers beside it.  With
-            # two parties the single push hides under the second gather either way, so the copy engine is used there; from
-            # three parties on the step is NVLink-bound and the faster SM push wins.
-            "copy": os.environ.get("CGB_BENCH_COPY", "sm" if P > 2 else "ce"),
+            # transport of the pushes (profiles/r1_p2p_probe_n2.jsonl, r1b_bench_n{2,4,8}*): the SM copy kernel moves 690 GB/s
+            # per GPU against 537 GB/s for the copy engines; it takes SM slots from the gathers beside it, but wins at every
+            # party count measured (N=2: 2.99 vs 3.14 ms, N=4: 5.5 vs 6.1 ms).  CGB_BENCH_COPY=ce selects the copy engines.
+            "copy": os.environ.get("CGB_BENCH_COPY", "sm"),
             "copy_ctas": int(os.environ.get("CGB_BENCH_COPY_CTAS", "64"))}
 
 
@@ -349,8 +348,7 @@ def main():
         "l2": "inputs larger than L2 (share rows + indices >> 126 MB); no flush needed",
         "seed": 42,
         "exchange": {"pipelined": "one gather per destination party; each finished block is pushed into its owner's window "
-                                  "(CUDA IPC peer memory over NVLink) by an SM-driven copy kernel (copy engine at 2 parties) that overlaps "
-                                  "the next gather; "
+                                  "(CUDA IPC peer memory over NVLink) by an SM-driven copy kernel that overlaps the next gather; "
                                   "4-byte all-reduce as barrier; one-pass sum",
                      "fused": "one gather kernel stores each block straight into the consumer's window over NVLink; "
                               "4-byte all-reduce as barrier",
