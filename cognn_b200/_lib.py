@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcognn_b200.so")
+# COGNN_B200_LIB: load another build of the same C ABI (A/B runs of compile-time variants, e.g. -DCGB_CHUNK_EDGES=128u)
+LIB_PATH = os.environ.get("COGNN_B200_LIB") or os.path.join(_HERE, "libcognn_b200.so")
 
 u64p = C.c_void_p  # device / host pointers travel as integers
 u32p = C.c_void_p

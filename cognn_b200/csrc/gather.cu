@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) gather_sum_kernel(const GatherArgs a) {
 // ------------------------------------------------------------------------------------------------------------
 // Edge-balanced schedule.  The row-per-group kernel above leaves a power-law graph latency bound: a block lives
 // as long as its longest row, and every row pays the rowptr -> col -> x dependent-load chain (ncu, round 1:
-// 25% DRAM utilisation, 34% of peak warps active).  Here every group owns exactly CGB_CHUNK_EDGES consecutive
+// 25% DRAM utilisation, 34% of peak warps active).  Here every group owns exactly 1 << chunk_shift (64 or 128) consecutive
 // edges, whatever rows they belong to.  Row boundaries travel in bit 31 of the column index (set on the last
 // edge of each row), the next batch of indices is prefetched while the current batch of row loads is in flight,
 // rows that lie inside one chunk are stored directly, and a row cut by a chunk boundary leaves one "piece" per
@@ -213,6 +213,7 @@ struct ChunkArgs {
     const u64* delta;
     u64* y;
     uint32_t n_chunks, n_empty, n_edges;
+    uint32_t chunk_shift;  // log2(edges per chunk)
     uint32_t D, n_ct;
     uint32_t* counters;
     u64* piece_head;  // n_chunks x D: sum of the chunk's leading edges when they continue a row from an earlier chunk
@@ -241,7 +242,7 @@ __device__ __forceinline__ void piece_arrive_body(const ChunkArgs& a, uint32_t r
     __threadfence();
     __syncwarp(mask);
     const uint32_t rb = __ldg(a.rowptr + row), re = __ldg(a.rowptr + row + 1);
-    const uint32_t c1 = rb / CGB_CHUNK_EDGES, c2 = (re - 1) / CGB_CHUNK_EDGES;
+    const uint32_t c1 = rb >> a.chunk_shift, c2 = (re - 1) >> a.chunk_shift;
     uint32_t* ctr = a.counters + (size_t)c1 * a.n_ct + ct;
     uint32_t prev = 0;
     if (lane == 0) prev = atomicAdd(ctr, 1u);
@@ -301,8 +302,8 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
         return;
     }
     const uint32_t c = item;
-    uint32_t e = c * CGB_CHUNK_EDGES;
-    const uint32_t end = min(a.n_edges, e + CGB_CHUNK_EDGES);
+    uint32_t e = c << a.chunk_shift;
+    const uint32_t end = min(a.n_edges, e + (1u << a.chunk_shift));
     const uint32_t cn = __ldg(a.chunk_nz + c);
     uint32_t k = cn & ~CGB_END_FLAG;
     bool head_open = (cn & CGB_END_FLAG) != 0;
@@ -461,8 +462,8 @@ __global__ void __launch_bounds__(BLOCK) gather_chunk_async_kernel(const __grid_
     const u64* xcol = a.x + col0;
 
     const uint32_t c = item;
-    uint32_t e = c * CGB_CHUNK_EDGES;
-    const uint32_t end = min(a.n_edges, e + CGB_CHUNK_EDGES);
+    uint32_t e = c << a.chunk_shift;
+    const uint32_t end = min(a.n_edges, e + (1u << a.chunk_shift));
     const uint32_t cn = __ldg(a.chunk_nz + c);
     uint32_t k = cn & ~CGB_END_FLAG;
     bool head_open = (cn & CGB_END_FLAG) != 0;
@@ -708,11 +709,15 @@ int build_chunks(cgb_ctx* ctx, cgb_csr* c, const uint32_t* h_rowptr) {
     }
     c->n_nz = (uint32_t)nz.size();
     c->n_empty = (uint32_t)empty.size();
-    c->n_chunks = (uint32_t)((c->n_edges + CGB_CHUNK_EDGES - 1) / CGB_CHUNK_EDGES);
+    static const int forced_shift = getenv("CGB_CHUNK_SHIFT") ? atoi(getenv("CGB_CHUNK_SHIFT")) : 0;
+    c->chunk_shift = forced_shift >= 4 && forced_shift <= 12 ? (uint32_t)forced_shift
+                     : (c->n_edges >= CGB_BIG_GRAPH_EDGES ? CGB_CHUNK_SHIFT_BIG : CGB_CHUNK_SHIFT_SMALL);
+    const uint64_t chunk_edges = 1ull << c->chunk_shift;
+    c->n_chunks = (uint32_t)((c->n_edges + chunk_edges - 1) / chunk_edges);
     std::vector<uint32_t> chunk_nz(c->n_chunks);
     uint32_t k = 0;
     for (uint32_t ch = 0; ch < c->n_chunks; ++ch) {
-        const uint32_t e = ch * CGB_CHUNK_EDGES;
+        const uint32_t e = ch << c->chunk_shift;
         while (h_rowptr[nz[k] + 1] <= e) ++k;  // advance to the non-empty row that holds edge e
         chunk_nz[ch] = k | (h_rowptr[nz[k]] < e ? CGB_END_FLAG : 0u);
     }
@@ -872,6 +877,7 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
         a.empty_row = csr->d_empty_row;
         a.x = (const u64*)d_x; a.delta = (const u64*)d_delta; a.y = (u64*)d_y;
         a.n_chunks = csr->n_chunks; a.n_empty = csr->n_empty; a.n_edges = (uint32_t)csr->n_edges;
+        a.chunk_shift = csr->chunk_shift;
         a.D = D; a.n_ct = s.n_ct;
         a.counters = csr->d_chunk_ctr;
         a.piece_head = (u64*)csr->d_piece;

@@ -15,6 +15,8 @@
 // The result feeds cgb_csr_create_device directly; only the small per-vertex arrays go back to the host.
 // CUB (shipped with the CUDA toolkit) provides the scan and the sort; the passes around them are hand written.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <vector>
 
@@ -40,8 +42,9 @@ constexpr int IG_THREADS = 256;
 struct IsParty {
     const int64_t* tid;
     int64_t t;
-    __device__ uint32_t operator()(uint64_t v) const { return tid[v] == t ? 1u : 0u; }
+    __host__ __device__ uint32_t operator()(uint64_t v) const { return tid[v] == t ? 1u : 0u; }
 };
+typedef thrust::transform_iterator<IsParty, thrust::counting_iterator<uint64_t>> PartyFlagIter;
 
 __global__ void __launch_bounds__(IG_THREADS) check_tid_kernel(const int64_t* __restrict__ tid, uint64_t n, int T, int* err) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -190,15 +193,13 @@ int cgb_party_graph_build(cgb_ctx* ctx, const int64_t* d_edges, uint64_t n_edges
     // 1. local index of every vertex inside its party
     size_t scan_bytes = 0;
     {
-        cub::TransformInputIterator<uint32_t, IsParty, cub::CountingInputIterator<uint64_t>> it(
-            cub::CountingInputIterator<uint64_t>(0), IsParty{d_tid, 0});
+        PartyFlagIter it(thrust::counting_iterator<uint64_t>(0), IsParty{d_tid, 0});
         CGB_CHECK_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, it, d_scan, n_vertices, st));
     }
     void* d_scan_tmp = nullptr;
     CGB_CHECK_CUDA(ctx, tmp.alloc((uint8_t**)&d_scan_tmp, scan_bytes));
     for (int t = 0; t < T; ++t) {
-        cub::TransformInputIterator<uint32_t, IsParty, cub::CountingInputIterator<uint64_t>> it(
-            cub::CountingInputIterator<uint64_t>(0), IsParty{d_tid, (int64_t)t});
+        PartyFlagIter it(thrust::counting_iterator<uint64_t>(0), IsParty{d_tid, (int64_t)t});
         CGB_CHECK_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_bytes, it, d_scan, n_vertices, st));
         ctx->launches++;
         take_local_index_kernel<<<ig_blocks(ctx, n_vertices), IG_THREADS, 0, st>>>(d_tid, d_scan, n_vertices, t, d_local_index,

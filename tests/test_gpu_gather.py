@@ -239,10 +239,12 @@ def test_peer_copy_is_a_copy(cgb, n_words, n_ctas):
 
 
 @pytest.mark.parametrize("env", [{"CGB_GATHER_VEC": "2"}, {"CGB_GATHER_VEC": "4", "CGB_GATHER_IPL": "1"},
-                                 {"CGB_GATHER_IMPL": "rows"}, {"CGB_GATHER_IMPL": "async", "CGB_GATHER_VEC": "2"}])
+                                 {"CGB_GATHER_IMPL": "rows"}, {"CGB_GATHER_IMPL": "async", "CGB_GATHER_VEC": "2"},
+                                 {"CGB_CHUNK_SHIFT": "7"}, {"CGB_CHUNK_SHIFT": "5", "CGB_GATHER_VEC": "2"}])
 def test_gather_alternative_kernels_in_subprocess(env):
-    """The default is the 256-bit edge-balanced kernel; the 128-bit, row-schedule and cp.async variants stay selectable for
-    A/B measurements (environment read once per process), so they are checked against the oracle in a child process."""
+    """The default is the 256-bit edge-balanced kernel with 64-edge chunks (128 from 16M edges on); the 128-bit, row-schedule
+    and cp.async variants and other chunk sizes stay selectable for A/B measurements (environment read once per process), so
+    they are checked against the oracle in a child process."""
     import os
     import subprocess
     import sys

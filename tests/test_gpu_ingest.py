@@ -31,10 +31,17 @@ def check_against_host_builder(cgb, edges, tid, T):
             assert np.array_equal(to_np(got["in_deg"]), want["in_deg"]), (me, src)
             assert np.array_equal(to_np(got["rowptr"]), want["rowptr"]), (me, src)
             assert np.array_equal(to_np(got["col"]), want["col"]), (me, src)
+            # isLocalVertexBorder (graph_io_util.h:169): a local vertex with at least one out-edge into another party
+            border = np.zeros(int(got["n_local"]), dtype=np.uint8)
+            if edges.size:
+                out_remote = (tid[edges[:, 0]] == me) & (tid[edges[:, 1]] != me)
+                local_of = np.cumsum(tid == me) - 1
+                border[local_of[edges[out_remote, 0]]] = 1
+            assert np.array_equal(to_np(got["is_border"]), border), (me, src)
             yield me, got, want
 
 
-@pytest.mark.parametrize("T,partition", [(1, "mod"), (2, "mod"), (3, "block"), (4, "mod"), (8, "mod")])
+@pytest.mark.parametrize("T,partition", [(1, "mod"), (2, "mod"), (3, "block"), (4, "mod"), (8, "mod"), (16, "mod")])
 def test_ingest_matches_host_builder_and_oracle(cgb, oracle, T, partition):
     g = small_graph(n=300, n_edges=2000, F=4, C=3, T=T, seed=10 + T, partition=partition, multi_edges=40, isolated=7)
     edges, tid = np.asarray(g["edges"], dtype=np.int64), np.asarray(g["tid"], dtype=np.int64)
