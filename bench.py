@@ -210,6 +210,26 @@ def pipelined_phases(pipe, rank, P):
             "barrier_done": round(t0.elapsed_time(pipe["bar"]), 3), "sum_done": round(t0.elapsed_time(pipe["end"]), 3)}
 
 
+def secure_gcn_epoch_probe(timeout_s=240):
+    """BASELINE.json configs[0]: 2-party CoGNN-Opt training epoch on the synthetic Cora-shaped graph, both parties on this GPU
+    (loopback plane; `tools/epoch_bench.py` under torchrun is the one-party-per-GPU form).  Runs in a child process so that
+    nothing it does can disturb the gather measurement; any failure is reported, never raised."""
+    import subprocess
+
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "epoch_bench.py"), "--shape", "cora", "--parties", "2", "--epochs", "4", "--cpu"]
+    try:
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+        rec = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        keep = ("shape", "parties", "plane", "N", "E", "cfg", "iterations", "online_s", "online_mode", "offline_dealer_s", "launches",
+                "rounds", "graph_replays", "cpu_oracle", "note")
+        out = {k: rec[k] for k in keep if k in rec}
+        out["unit"] = "s per epoch (online phase; offline = trusted-dealer emulation, reported beside it)"
+        return out
+    except Exception as ex:  # noqa: BLE001
+        return {"error": f"{type(ex).__name__}: {ex}"[:300]}
+
+
 def algorithmic_bytes(n_rows, n_edges, D):
     # SURVEY.md 8d, fused SpMM form: every edge = one 8*D-byte row read + a 4-byte index, no cache-reuse credit
     return (8 * D + 4) * n_edges + 4 * (n_rows + 1) + 8 * D * n_rows
@@ -325,6 +345,7 @@ def main():
     ap.add_argument("--cpu-frac", type=float, default=1.0, help="fraction of rows in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-epoch", action="store_true", help="skip the secure-GCN epoch probe (N = 1 only)")
     ap.add_argument("--exchange", default="pipelined", choices=["pipelined", "fused", "nccl"],
                     help="N > 1: pipelined = per-destination gathers overlapped with async peer copies over NVLink (default); "
                          "fused = one gather kernel storing straight into peer windows; nccl = gather then all_to_all")
@@ -642,6 +663,11 @@ def main():
 
             _po.set_num_threads(cores)
 
+    # ---- the other half of BASELINE.json's metric: secure-GCN epoch time (configs[0] shape), in a child process ------------
+    epoch = None
+    if rank == 0 and P == 1 and not args.no_epoch and not args.no_e2e:
+        epoch = secure_gcn_epoch_probe()
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": P, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -651,6 +677,8 @@ def main():
             line["multi_gpu_phases"] = phases
         if piped_timeline:
             line["multi_gpu_phases"] = {"per_rank_last_step_timeline_ms": piped_timeline}
+        if epoch is not None:
+            line["secure_gcn_epoch"] = epoch
         print(json.dumps(line))
     if P > 1:
         dist.destroy_process_group()
