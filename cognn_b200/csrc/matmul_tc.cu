@@ -278,6 +278,156 @@ __global__ void __launch_bounds__(192, 1) matmul_tc_kernel(const __grid_constant
     }
 }
 
+#ifdef CGB_EXPERIMENTAL_TC_MC
+// ---- EXPERIMENTAL, NOT PART OF THE PRODUCT BUILD (compile with -DCGB_EXPERIMENTAL_TC_MC) ------------------------------------
+// Next step named in DESIGN.md section 8: the kernel above keeps the tensor pipe 54 % busy because each 128x64 tile pulls
+// 48 KB of limb planes per k-step through the L2 -> SM path, which is at its cap chip-wide.  Here the four CTAs that compute
+// the four N-tiles of the same 128-row block form a cluster and SHARE the A planes: CTA r loads only slice r (8 KB, two limb
+// planes) of each A stage and multicasts it into the same shared-memory offset of all four CTAs, so every SM pulls 8 + 16 KB
+// per k-step instead of 32 + 16 KB.  Written and compile-checked in round 1 after the GPU budget was spent: it has NOT run on
+// hardware yet and is therefore not selectable in the product library.
+//
+// Barrier protocol per stage s (all barriers live at the same shared-memory offset in the four CTAs):
+//   full_bar[s]   count 1: the CTA's own producer arrives with expect_tx = 32 KB (A, delivered by four multicasts, one from
+//                 each CTA of the cluster, its own included) + 16 KB (its own B).  A peer's bytes may land before the local
+//                 expect_tx of the same round; the phase still cannot complete before the local arrive.
+//   empty_bar[s]  count MC: every CTA's MMA warp commits with a multicast arrive on the four CTAs' empty_bar[s], so a producer
+//                 overwrites slice r of stage s everywhere only after all four CTAs have finished reading that stage.
+// The cluster is synchronised after barrier initialisation (before the first remote operation) and before exit (no CTA may
+// leave while peers can still arrive on its barriers).
+constexpr int TC_MC = 4;
+constexpr uint32_t A_SLICE_BYTES = A_STAGE_BYTES / TC_MC;
+
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(TC_MC, 1, 1) __launch_bounds__(192, 1) matmul_tc_mc_kernel(const __grid_constant__ TcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], acc_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t mb = blockIdx.y, nb = blockIdx.x;  // the cluster spans four consecutive nb of one mb
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const uint16_t all = (uint16_t)((1u << TC_MC) - 1);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + TC_STAGES * A_STAGE_BYTES;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), TC_MC);
+        }
+        mbar_init(smem_u32(&acc_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_smem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();  // every CTA's barriers are initialised before any peer multicasts into it
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint8_t* gA = a.A + (size_t)mb * a.n_ksteps * A_STAGE_BYTES + (size_t)rank * A_SLICE_BYTES;
+            const uint8_t* gB = a.B + (size_t)nb * a.n_ksteps * B_STAGE_BYTES;
+            for (uint32_t ks = 0; ks < a.n_ksteps; ++ks) {
+                const uint32_t s = ks % TC_STAGES, ph = (ks / TC_STAGES) & 1;
+                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);  // all four CTAs have released stage s
+                mbar_expect_tx(smem_u32(&full_bar[s]), A_STAGE_BYTES + B_STAGE_BYTES);
+                bulk_g2s_multicast(smem_u32(sA + s * A_STAGE_BYTES + rank * A_SLICE_BYTES), gA + (size_t)ks * A_STAGE_BYTES, A_SLICE_BYTES,
+                                   smem_u32(&full_bar[s]), all);
+                bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), gB + (size_t)ks * B_STAGE_BYTES, B_STAGE_BYTES, smem_u32(&full_bar[s]));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc0 = (2u << 4) | ((uint32_t)(TC_BM >> 4) << 24);
+            for (uint32_t ks = 0; ks < a.n_ksteps; ++ks) {
+                const uint32_t s = ks % TC_STAGES, ph = (ks / TC_STAGES) & 1;
+                mbar_wait(smem_u32(&full_bar[s]), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = smem_u32(sA + s * A_STAGE_BYTES), b0 = smem_u32(sB + s * B_STAGE_BYTES);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint64_t da = smem_desc(a0 + i * A_PLANE_BYTES, TC_BM * 16, 128);
+#pragma unroll
+                    for (int j0 = 0; j0 + i < 8; j0 += 4) {
+                        const int planes = (8 - i - j0) < 4 ? (8 - i - j0) : 4;
+                        const uint32_t n = (uint32_t)planes * TC_BN;
+                        const uint64_t db = smem_desc(b0 + (uint32_t)j0 * TC_BN * 16, 8 * TC_BN * 16, 128);
+                        tc_mma_i8(tmem_base + (uint32_t)(i + j0) * TC_BN, da, db, idesc0 | ((n >> 3) << 17), (ks > 0 || i > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit_multicast(smem_u32(&empty_bar[s]), all);  // this CTA is done with stage s: tell all four producers
+            }
+            tc_commit(smem_u32(&acc_bar));
+        }
+    } else {
+        mbar_wait(smem_u32(&acc_bar), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t q = warp & 3;
+        const uint32_t gm = mb * TC_BM + q * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((q * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < TC_BN / 16; ++c) {
+            u64 acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                uint32_t r[16];
+                const uint32_t taddr = lane_addr + (uint32_t)(d * TC_BN + c * 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                      "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] += (u64)r[j] << (8 * d);
+            }
+            if (gm < a.M) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t gn = nb * TC_BN + c * 16 + j;
+                    if (gn < a.N) {
+                        const size_t o = (size_t)gm * a.N + gn;
+                        u64 v = acc[j];
+                        if (a.Z) v += a.Z[o];
+                        if (a.accumulate) v += a.C[o];
+                        a.C[o] = trunc_share(v, a.f, a.share);
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_sync_all();  // peers may still arrive on this CTA's empty barriers until all four are done
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+#endif  // CGB_EXPERIMENTAL_TC_MC
+
 }  // namespace
 
 // One tensor-core launch over a K range that fits the 32-bit diagonal accumulators (n_pairs * K <= 4096).
@@ -320,6 +470,19 @@ static int tc_chunk(cgb_ctx* ctx, const u64* const A[2], const u64* const B[2], 
     a.A = dA; a.B = dB; a.Z = Z; a.C = C; a.M = M; a.N = N; a.n_ksteps = n_ksteps;
     a.f = f; a.share = share; a.accumulate = accumulate;
     dim3 grid(Npad / TC_BN, Mpad / TC_BM);
+#ifdef CGB_EXPERIMENTAL_TC_MC
+    static const bool use_mc = getenv("CGB_MATMUL_IMPL") && std::string(getenv("CGB_MATMUL_IMPL")) == "tc_mc";
+    if (use_mc && grid.x % TC_MC == 0) {  // whole clusters of four N-tiles only (N a multiple of 256)
+        static bool mc_attr_set = false;
+        if (!mc_attr_set) {
+            CGB_CHECK_CUDA(ctx, cudaFuncSetAttribute(matmul_tc_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+            mc_attr_set = true;
+        }
+        matmul_tc_mc_kernel<<<grid, 192, TC_SMEM_BYTES, ctx->stream>>>(a);
+        CGB_CHECK_LAUNCH(ctx, "matmul_tc_mc_kernel");
+        return CGB_OK;
+    }
+#endif
     matmul_tc_kernel<<<grid, 192, TC_SMEM_BYTES, ctx->stream>>>(a);
     CGB_CHECK_LAUNCH(ctx, "matmul_tc_kernel");
     return CGB_OK;

@@ -51,3 +51,26 @@ def test_sass_is_sm100a_only():
     out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
     assert archs == {"sm_100a"}, archs
+
+
+def test_experimental_multicast_matmul_still_compiles(tmp_path):
+    """cognn_b200/csrc/matmul_tc.cu carries the next-round cluster-multicast kernel behind CGB_EXPERIMENTAL_TC_MC (not in the
+    product build, not yet run on hardware).  Compile-only check so the draft does not rot; the SASS must contain the
+    multicast bulk copy and the multicast commit."""
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        return
+    obj = str(tmp_path / "mtc_mc.o")
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
+                        "-DCGB_EXPERIMENTAL_TC_MC", "-c", os.path.join(ROOT, "cognn_b200", "csrc", "matmul_tc.cu"), "-o", obj],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    sass = subprocess.run([shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    assert "UBLKCP.S.G.MULTICAST" in sass and "UTCBAR.MULTICAST" in sass
+    # and the product library does not contain it
+    names = subprocess.run([shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump", "-res-usage", _lib.LIB_PATH], capture_output=True,
+                           text=True).stdout
+    assert "matmul_tc_mc_kernel" not in names and "matmul_tc_kernel" in names
