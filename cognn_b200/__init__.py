@@ -23,6 +23,20 @@ class Csr:
         self.ctx, self.handle = ctx, handle
         self.n_rows, self.n_edges, self.n_src_rows = n_rows, n_edges, n_src_rows
 
+    @property
+    def n_nonempty(self):
+        return int(self.ctx.lib.cgb_csr_num_nonempty_rows(self.handle))
+
+    def nonempty_rows(self):
+        """Device int32 tensor (a copy) of the destination rows that have at least one edge, ascending."""
+        t = self.ctx.torch
+        n = self.n_nonempty
+        out = t.empty(n, dtype=t.int32, device=self.ctx._dev())
+        if n:
+            self.ctx.check(self.ctx.lib.cgb_d2d(self.ctx.handle, C.c_void_p(out.data_ptr()),
+                                                C.c_void_p(self.ctx.lib.cgb_csr_nonempty_rows(self.handle)), 4 * n))
+        return out
+
     def destroy(self):
         if self.handle is not None:
             self.ctx.lib.cgb_csr_destroy(self.ctx.handle, self.handle)
@@ -97,6 +111,56 @@ class Context:
         self.check(self.lib.cgb_gather_sum(self.handle, csr.handle, _ptr(self._u64(x)),
                                            _ptr(delta), _ptr(self._u64(out)), D))
         return out
+
+    def gather_sum_compact(self, csr, x, delta=None, out=None, out_ptr=None):
+        """Compact mirror-update block: row k = k-th non-empty destination row (csr.nonempty_rows()).  `out_ptr`: raw device
+        address (e.g. an IPC-exported staging buffer) instead of a tensor."""
+        D = x.shape[1]
+        assert x.shape[0] == csr.n_src_rows
+        if out_ptr is None:
+            if out is None:
+                out = self.empty(csr.n_nonempty, D)
+            out_ptr = self._u64(out).data_ptr()
+        self.check(self.lib.cgb_gather_sum_compact(self.handle, csr.handle, _ptr(self._u64(x)), _ptr(delta),
+                                                   C.c_void_p(int(out_ptr)), D))
+        return out
+
+    def scatter_add_rows(self, idx, src, v, assign=False, n=None, D=None, n_ctas=0):
+        """v[idx[k], :] (+)= src[k, :].  `src` may be a raw device address (int; e.g. a peer's staging buffer) with n given."""
+        D = v.shape[1] if D is None else D
+        if isinstance(src, int):
+            src_ptr = src
+        else:
+            src_ptr, n = self._u64(src).data_ptr(), src.shape[0]
+        assert idx.dtype == self.torch.int32 and idx.is_cuda and idx.numel() >= n
+        self.check(self.lib.cgb_scatter_add_rows(self.handle, _ptr(idx), n, C.c_void_p(int(src_ptr)), _ptr(self._u64(v)), D,
+                                                 int(assign), n_ctas))
+        return v
+
+    def flag_signal(self, flag_ptr, value):
+        self.check(self.lib.cgb_flag_signal(self.handle, C.c_void_p(int(flag_ptr)), int(value) & 0xFFFFFFFF))
+
+    def flag_wait(self, flag_ptr, value, mode=0, err_ptr=None):
+        self.check(self.lib.cgb_flag_wait(self.handle, C.c_void_p(int(flag_ptr)), int(value) & 0xFFFFFFFF, int(mode),
+                                          C.c_void_p(int(err_ptr)) if err_ptr else None))
+
+    def set_matmul_impl(self, impl):
+        """'auto' | 'imad' | 'tc' | None (environment)."""
+        self.check(self.lib.cgb_ctx_set_matmul_impl(self.handle, {None: -1, "auto": 0, "imad": 1, "tc": 2}[impl]))
+
+    def probe_imad_peak(self):
+        v = C.c_double()
+        self.check(self.lib.cgb_probe_imad_peak(self.handle, C.byref(v)))
+        return v.value
+
+    def probe_tensor_i8_peak(self):
+        v = C.c_double()
+        self.check(self.lib.cgb_probe_tensor_i8_peak(self.handle, C.byref(v)))
+        return v.value
+
+    @property
+    def last_kernel(self):
+        return (self.lib.cgb_ctx_last_kernel(self.handle) or b"").decode()
 
     def gather_sum_blocks(self, csr, x, block_ptrs, block_offsets, delta=None):
         """block_ptrs: list of raw device addresses (ints; may be peer memory), block_offsets: row offsets (len + 1)."""

@@ -49,6 +49,16 @@ SIGNATURES = {
     "cgb_csr_col": (C.c_void_p, [csr_p]),
     "cgb_gather_sum": (C.c_int, [ctx_p, csr_p, u64p, u64p, u64p, C.c_uint32]),
     "cgb_gather_sum_blocks": (C.c_int, [ctx_p, csr_p, u64p, u64p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "cgb_gather_sum_compact": (C.c_int, [ctx_p, csr_p, u64p, u64p, u64p, C.c_uint32]),
+    "cgb_csr_num_nonempty_rows": (C.c_uint32, [csr_p]),
+    "cgb_csr_nonempty_rows": (C.c_void_p, [csr_p]),
+    "cgb_scatter_add_rows": (C.c_int, [ctx_p, u32p, C.c_uint64, u64p, u64p, C.c_uint32, C.c_int, C.c_uint32]),
+    "cgb_flag_signal": (C.c_int, [ctx_p, C.c_void_p, C.c_uint32]),
+    "cgb_flag_wait": (C.c_int, [ctx_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]),
+    "cgb_ctx_last_kernel": (C.c_char_p, [ctx_p]),
+    "cgb_ctx_set_matmul_impl": (C.c_int, [ctx_p, C.c_int]),
+    "cgb_probe_imad_peak": (C.c_int, [ctx_p, C.POINTER(C.c_double)]),
+    "cgb_probe_tensor_i8_peak": (C.c_int, [ctx_p, C.POINTER(C.c_double)]),
     "cgb_ipc_export": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p]),
     "cgb_ipc_open": (C.c_int, [ctx_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "cgb_ipc_close": (C.c_int, [ctx_p, C.c_void_p]),

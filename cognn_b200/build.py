@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcognn_b200.so")
-SOURCES = ["capi.cu", "gather.cu", "matmul.cu", "matmul_tc.cu", "elementwise.cu", "prg.cu", "ingest.cu"]
+SOURCES = ["capi.cu", "gather.cu", "matmul.cu", "matmul_tc.cu", "elementwise.cu", "prg.cu", "ingest.cu", "exchange.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -11,8 +11,8 @@ static thread_local std::string g_last_error;
 
 int cgb_scratch_reserve(cgb_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->scratch_bytes) return CGB_OK;
-    CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->scratch) cudaFree(ctx->scratch);
+    // retired, not freed: launches in flight and captured CUDA graphs may still hold the old address (freed with the context)
+    if (ctx->scratch) ctx->retired.push_back(ctx->scratch);
     ctx->scratch = nullptr;
     ctx->scratch_bytes = 0;
     size_t want = bytes + bytes / 4;
@@ -28,6 +28,13 @@ int cgb_scratch_reserve(cgb_ctx* ctx, size_t bytes) {
 }
 
 extern "C" {
+
+int cgb_ctx_set_matmul_impl(cgb_ctx* ctx, int impl) {
+    CGB_REQUIRE(ctx, impl >= -1 && impl <= 2, "cgb_ctx_set_matmul_impl: -1 (environment / auto), 0 auto, 1 imad, 2 tc");
+    ctx->matmul_impl = impl;
+    return CGB_OK;
+}
+const char* cgb_ctx_last_kernel(cgb_ctx* ctx) { return ctx ? ctx->last_kernel : ""; }
 
 const char* cgb_version(void) { return "cognn_b200 0.1 (sm_100a)"; }
 
@@ -82,6 +89,8 @@ int cgb_ctx_destroy(cgb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->tc_planes) cudaFree(ctx->tc_planes);
+    for (void* p : ctx->retired) cudaFree(p);
     if (ctx->pipe.ready) {
         cudaStreamSynchronize(ctx->pipe.h2d);
         cudaStreamSynchronize(ctx->pipe.d2h);

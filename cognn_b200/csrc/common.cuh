@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/cognn_b200.h"
 
@@ -14,12 +15,19 @@ struct cgb_ctx {
     int num_sms = 148;
     std::string err;
     uint64_t launches = 0;
+    int matmul_impl = -1;  // -1: CGB_MATMUL_IMPL / auto; 0 auto, 1 integer pipe, 2 tensor pipe (cgb_ctx_set_matmul_impl)
+    const char* last_kernel = "";  // name of the gather / matmul kernel the last dispatch chose (bench.py reports it)
     // device word added to the stream id of every PRG launch (cgb_ctx_set_prg_stream_bias): lets a captured CUDA graph
     // draw fresh randomness at every replay
     const uint64_t* prg_bias = nullptr;
     // grow-only device scratch (split-K accumulators, Beaver temporaries)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // limb planes of the tensor-core matmul (grow-only, per context = per device and stream) and its per-device attribute flags
+    void* tc_planes = nullptr;
+    size_t tc_planes_bytes = 0;
+    bool tc_attr_set = false, tc_mc_attr_set = false;
+    std::vector<void*> retired;  // outgrown buffers, freed with the context (captured graphs may still reference them)
     // double-buffered staging for the pipelined host entry point (cgb_host_gather_sum_async)
     struct HostPipe {
         cudaStream_t h2d = nullptr, d2h = nullptr;
@@ -61,6 +69,7 @@ struct cgb_csr {
     uint32_t chunk_ctr_len = 0;
     uint64_t* d_piece = nullptr;        // 2 * n_chunks x D: [head pieces | tail pieces] (grow-only)
     size_t piece_words = 0;
+    std::vector<void*> retired;         // outgrown scratch buffers, freed with the handle (graphs may still reference them)
 };
 // edges per chunk of the edge-balanced schedule = 1 << chunk_shift, chosen per CSR when it is built: 64 keeps small graphs
 // (one wave of groups or less) short, 128 halves the per-chunk prologues and boundary pieces of big ones (100M edges,
@@ -124,7 +133,7 @@ __device__ __forceinline__ u64 ld_nc_u64(const u64* p) {
 // L2-coherent load (partials written by other CTAs in the same launch)
 __device__ __forceinline__ u64 ld_cg_u64(const u64* p) {
     u64 r;
-    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");  // ordered after the __threadfence before it
     return r;
 }
 __device__ __forceinline__ void st_cs_v2(u64* p, u64 a, u64 b) {

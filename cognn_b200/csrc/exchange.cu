@@ -1,0 +1,166 @@
+// exchange.cu -- the mirror-update exchange of one GAS iteration between parties that sit on different GPUs of one box.
+//
+// Replaces CommSync::sendShareVecVec / recvShareVecVec (include/comm_sync.h:245-277) for the update blocks of
+// ss_vertex_centric_algo_kernel.h:835 -> 1067/1090 and the GatherComp additions that consume them
+// (optimize-gcn/gcn.h:456-463).  Design:
+//
+//   * the producer gathers its block for party t in COMPACT form (cgb_gather_sum_compact: one row per destination that
+//     has an edge from the producer -- that list is the PosVec both sides hold since preprocessing, ssk.h:507-516), into
+//     a staging buffer the consumer has mapped with CUDA IPC;
+//   * it then raises a flag in the CONSUMER's memory (cgb_flag_signal: one thread, fence + st.release.sys over NVLink);
+//   * the consumer's stream waits for the flag (cgb_flag_wait) and runs cgb_scatter_add_rows, which PULLS the rows
+//     straight out of the producer's staging buffer over NVLink and adds them into its vertex rows:
+//     v[idx[k], :] += block[k, :].  The block is never copied into local HBM first and never re-read by a separate sum.
+//
+// The wait is either a stream memory operation (cuStreamWaitValue32: no SM is occupied while waiting) or a one-thread
+// kernel with a BOUNDED spin that reports a timeout instead of hanging.  Flags only grow (the value is the step number),
+// so a late waiter never misses a signal.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+// ---- flags -------------------------------------------------------------------------------------------------------------
+__global__ void flag_signal_kernel(uint32_t* flag, uint32_t value) {
+    __threadfence_system();  // everything this stream wrote before (own HBM or peer memory) is visible system-wide first
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+
+// bounded spin: ~2 s at 1 us per poll, then the error word is raised and the kernel returns (the caller's result is wrong
+// and reported as such, but nothing hangs)
+__global__ void flag_wait_kernel(const uint32_t* flag, uint32_t value, uint32_t* err, uint32_t max_polls) {
+    uint32_t v = 0;
+    for (uint32_t i = 0; i < max_polls; ++i) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - value) >= 0) return;
+        __nanosleep(1000);
+    }
+    if (err) atomicExch(err, 1u);
+}
+
+typedef CUresult (*wait_value32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+wait_value32_fn resolve_wait_value32() {
+    static wait_value32_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return (wait_value32_fn)p;
+    }();
+    return fn;
+}
+
+// ---- pull + add of a compact block ---------------------------------------------------------------------------------------
+// One group of LANES lanes per row, 16 bytes per lane and column tile; every thread first issues its U remote loads (rows
+// k, k + stride, ...), then the local read-modify-writes, so a CTA keeps U x 16 B x threads in flight against the ~2 us
+// NVLink round trip.  `src` may be peer memory; it is read exactly once, with plain (coherent) loads.
+constexpr int SA_THREADS = 256;
+constexpr int SA_U = 8;
+
+__device__ __forceinline__ ulonglong2 ld_once_v2(const u64* p) {
+    ulonglong2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+    return r;
+}
+
+// D even, 16-byte aligned rows
+__global__ void __launch_bounds__(SA_THREADS) scatter_add_rows_v2_kernel(const uint32_t* __restrict__ idx, uint64_t n,
+                                                                         const u64* src, u64* __restrict__ v, uint32_t D,
+                                                                         int assign) {
+    // work item = (row k, 16-byte slot s), s < D/2; items are laid out so that consecutive threads read consecutive slots
+    const uint64_t slots = D / 2;
+    const uint64_t total = n * slots;
+    const uint64_t stride = (uint64_t)gridDim.x * SA_THREADS;
+    uint64_t i = (uint64_t)blockIdx.x * SA_THREADS + threadIdx.x;
+    for (; i < total; i += SA_U * stride) {
+        ulonglong2 r[SA_U];
+        uint32_t row[SA_U];
+#pragma unroll
+        for (int u = 0; u < SA_U; ++u) {
+            const uint64_t it = i + (uint64_t)u * stride;
+            if (it < total) {
+                r[u] = ld_once_v2(src + 2 * it);  // src is dense n x D: item it <-> words [2 it, 2 it + 2)
+                row[u] = __ldg(idx + it / slots);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SA_U; ++u) {
+            const uint64_t it = i + (uint64_t)u * stride;
+            if (it < total) {
+                u64* dst = v + (size_t)row[u] * D + 2 * (it % slots);
+                ulonglong2 o = assign ? make_ulonglong2(0, 0) : *reinterpret_cast<const ulonglong2*>(dst);
+                o.x += r[u].x;
+                o.y += r[u].y;
+                *reinterpret_cast<ulonglong2*>(dst) = o;
+            }
+        }
+    }
+}
+
+// any D / alignment: one u64 per item
+__global__ void __launch_bounds__(SA_THREADS) scatter_add_rows_v1_kernel(const uint32_t* __restrict__ idx, uint64_t n,
+                                                                         const u64* src, u64* __restrict__ v, uint32_t D,
+                                                                         int assign) {
+    const uint64_t total = n * D;
+    const uint64_t stride = (uint64_t)gridDim.x * SA_THREADS;
+    for (uint64_t it = (uint64_t)blockIdx.x * SA_THREADS + threadIdx.x; it < total; it += stride) {
+        u64 r;
+        asm volatile("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(src + it) : "memory");
+        u64* dst = v + (size_t)__ldg(idx + it / D) * D + it % D;
+        *dst = assign ? r : *dst + r;
+    }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int cgb_flag_signal(cgb_ctx* ctx, uint32_t* d_flag, uint32_t value) {
+    CGB_REQUIRE(ctx, d_flag, "cgb_flag_signal: null flag");
+    flag_signal_kernel<<<1, 1, 0, ctx->stream>>>(d_flag, value);
+    CGB_CHECK_LAUNCH(ctx, "flag_signal_kernel");
+    return CGB_OK;
+}
+
+int cgb_flag_wait(cgb_ctx* ctx, const uint32_t* d_flag, uint32_t value, int mode, uint32_t* d_err) {
+    CGB_REQUIRE(ctx, d_flag, "cgb_flag_wait: null flag");
+    if (mode == 0) {  // stream memory operation: the stream stalls in hardware, no SM is held
+        wait_value32_fn fn = resolve_wait_value32();
+        CGB_REQUIRE(ctx, fn != nullptr, "cgb_flag_wait: cuStreamWaitValue32 unavailable (use mode 1)");
+        CUresult r = fn((CUstream)ctx->stream, (CUdeviceptr)(uintptr_t)d_flag, value, CU_STREAM_WAIT_VALUE_GEQ);
+        if (r != CUDA_SUCCESS) return cgb_fail(ctx, CGB_ERR_CUDA, "cuStreamWaitValue32", std::to_string((int)r).c_str());
+        return CGB_OK;
+    }
+    flag_wait_kernel<<<1, 1, 0, ctx->stream>>>(d_flag, value, d_err, 2000000u);
+    CGB_CHECK_LAUNCH(ctx, "flag_wait_kernel");
+    return CGB_OK;
+}
+
+int cgb_scatter_add_rows(cgb_ctx* ctx, const uint32_t* d_idx, uint64_t n, const uint64_t* d_src, uint64_t* d_v, uint32_t D,
+                         int assign, uint32_t n_ctas) {
+    CGB_REQUIRE(ctx, (d_idx && d_src && d_v) || n == 0, "cgb_scatter_add_rows: null argument");
+    CGB_REQUIRE(ctx, D > 0, "cgb_scatter_add_rows: D must be positive");
+    if (n == 0) return CGB_OK;
+    const bool vec = D % 2 == 0 && aligned16(d_src) && aligned16(d_v);
+    const uint64_t items = vec ? n * (D / 2) : n * (uint64_t)D;
+    const uint64_t per_cta = (uint64_t)SA_THREADS * (vec ? SA_U : 1);
+    uint64_t want = (items + per_cta - 1) / per_cta;
+    const uint64_t cap = n_ctas ? n_ctas : (uint64_t)ctx->num_sms * 4;
+    if (want > cap) want = cap;
+    if (vec)
+        scatter_add_rows_v2_kernel<<<(unsigned)want, SA_THREADS, 0, ctx->stream>>>(d_idx, n, (const u64*)d_src, (u64*)d_v, D,
+                                                                                   assign);
+    else
+        scatter_add_rows_v1_kernel<<<(unsigned)want, SA_THREADS, 0, ctx->stream>>>(d_idx, n, (const u64*)d_src, (u64*)d_v, D,
+                                                                                   assign);
+    CGB_CHECK_LAUNCH(ctx, "scatter_add_rows_kernel");
+    return CGB_OK;
+}
+
+}  // extern "C"

@@ -224,6 +224,10 @@ struct ChunkArgs {
     int n_blk;
     u64* blk_base[CGB_MAX_BLOCKS];
     uint32_t blk_off[CGB_MAX_BLOCKS + 1];
+    // compact output: row k of y is the k-th NON-EMPTY destination row (nz_row[k]); rows without edges are not written at
+    // all.  This is the mirror-update block a party sends to another party: which destinations of the receiver have an edge
+    // from the sender is public to both (sendPosVec / recvPosVec, ssk.h:507-516), so empty rows need not cross NVLink
+    uint32_t compact;
 };
 
 __device__ __forceinline__ u64* out_row(const ChunkArgs& a, uint32_t row) {
@@ -235,10 +239,11 @@ __device__ __forceinline__ u64* out_row(const ChunkArgs& a, uint32_t row) {
 }
 
 // A row segment cut by a chunk boundary has been stored as a "piece"; count the arrival and, if this was the last
-// piece of the row, fold them.  Rare relative to the edge loop, so kept out of line.
+// piece of the row, fold them.  `k` is the row's index in nz_row (its output row in compact mode).
 template <int VEC, int LANES>
-__device__ __forceinline__ void piece_arrive_body(const ChunkArgs& a, uint32_t row, uint32_t ct, uint32_t col0, bool active,
+__device__ __forceinline__ void piece_arrive_body(const ChunkArgs& a, uint32_t k, uint32_t ct, uint32_t col0, bool active,
                                                   int lane, unsigned mask) {
+    const uint32_t row = __ldg(a.nz_row + k);
     __threadfence();
     __syncwarp(mask);
     const uint32_t rb = __ldg(a.rowptr + row), re = __ldg(a.rowptr + row + 1);
@@ -250,7 +255,8 @@ __device__ __forceinline__ void piece_arrive_body(const ChunkArgs& a, uint32_t r
     if (prev == c2 - c1) {  // last of the c2 - c1 + 1 pieces
         __threadfence();
         if (active) {
-            const size_t o = (size_t)row * a.D + col0;
+            const uint32_t orow = a.compact ? k : row;
+            const size_t o = (size_t)orow * a.D + col0;
             Acc<VEC> sum;
             sum.zero();
             if (a.delta) sum.load_nc(a.delta + o);
@@ -261,20 +267,25 @@ __device__ __forceinline__ void piece_arrive_body(const ChunkArgs& a, uint32_t r
                 p.load_cg(a.piece_head + (size_t)cc * a.D + col0);
                 sum.add(p);
             }
-            sum.store_cs(out_row(a, row) + col0);
+            sum.store_cs(out_row(a, orow) + col0);
         }
         if (lane == 0) *ctr = 0;  // ready for the next launch
     }
 }
 
+// out-of-line form for the cp.async variant (kept for A/B runs)
 template <int VEC, int LANES>
-__device__ __noinline__ void piece_arrive(const ChunkArgs& a, uint32_t row, uint32_t ct, uint32_t col0, bool active, int lane,
+__device__ __noinline__ void piece_arrive(const ChunkArgs& a, uint32_t k, uint32_t ct, uint32_t col0, bool active, int lane,
                                           unsigned mask) {
-    piece_arrive_body<VEC, LANES>(a, row, ct, col0, active, lane, mask);
+    piece_arrive_body<VEC, LANES>(a, k, ct, col0, active, lane, mask);
 }
 
 // IPL: column indices each lane holds per batch (a batch is LANES * IPL edges; narrow 256-bit groups of 2 or 4 lanes keep
 // 8 edges per batch this way, so U can stay above the lane count)
+//
+// The piece arrivals run after the edge loop from values recomputed out of chunk_nz, in ONE inlined copy of the fold, so no
+// accumulator is live across it and nothing about a finished row is carried through the loop.  (Round 1 carried `head_row`
+// to the end and called an out-of-line fold; the IPL = 2 instantiation then returned wrong columns 1..3 for cut rows.)
 template <int VEC, int LANES, int U, int BLOCK, int OCC_THREADS, int IPL = 1>
 __global__ void __launch_bounds__(BLOCK, OCC_THREADS / BLOCK)
 gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
@@ -283,7 +294,7 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
     const int lane = threadIdx.x & (LANES - 1);
     const unsigned mask = group_mask<LANES>(threadIdx.x & 31);
     const uint64_t gid = (uint64_t)blockIdx.x * GROUPS + threadIdx.x / LANES;
-    const uint64_t total = ((uint64_t)a.n_chunks + a.n_empty) * a.n_ct;
+    const uint64_t total = ((uint64_t)a.n_chunks + (a.compact ? 0u : a.n_empty)) * a.n_ct;
     if (gid >= total) return;
     const uint32_t item = (uint32_t)(gid / a.n_ct);
     const uint32_t ct = (uint32_t)(gid - (uint64_t)item * a.n_ct);
@@ -307,8 +318,7 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
     const uint32_t cn = __ldg(a.chunk_nz + c);
     uint32_t k = cn & ~CGB_END_FLAG;
     bool head_open = (cn & CGB_END_FLAG) != 0;
-    bool open = false, have_head = false;
-    uint32_t head_row = 0;
+    bool open = false;
     Acc<VEC> acc;
     acc.zero();
     uint32_t my[IPL], nxt[IPL];
@@ -342,21 +352,19 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
                         acc.add(v[u]);
                         open = true;
                         if (id[u] & CGB_END_FLAG) {
-                            const uint32_t row = __ldg(a.nz_row + k);
                             if (!head_open) {  // the row lies inside this chunk: store it
                                 if (active) {
-                                    const size_t o = (size_t)row * a.D + col0;
+                                    const uint32_t orow = a.compact ? k : __ldg(a.nz_row + k);
+                                    const size_t o = (size_t)orow * a.D + col0;
                                     if (a.delta) {
                                         Acc<VEC> d;
                                         d.load_nc(a.delta + o);
                                         acc.add(d);
                                     }
-                                    acc.store_cs(out_row(a, row) + col0);
+                                    acc.store_cs(out_row(a, orow) + col0);
                                 }
-                            } else {  // end of a row that began in an earlier chunk: leave a head piece
+                            } else {  // end of a row that began in an earlier chunk: leave a head piece (arrival counted below)
                                 if (active) acc.store(a.piece_head + (size_t)c * a.D + col0);
-                                head_row = row;
-                                have_head = true;
                             }
                             acc.zero();
                             head_open = false;
@@ -380,21 +388,18 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
 #pragma unroll
         for (int i = 0; i < IPL; ++i) my[i] = nxt[i];
     }
-    // The 256-bit instantiations keep a few registers spilled around the main loop; with the piece fold out of line
-    // (a call, as below) the IPL = 2 variant returned wrong columns 1..3 of every lane for rows cut by a chunk boundary
-    // (accumulator halves restored from the stack after the call), so they inline it.
-    if constexpr (VEC == 4) {
-        if (have_head) piece_arrive_body<VEC, LANES>(a, head_row, ct, col0, active, lane, mask);
-        if (open) {
-            if (active) acc.store((head_open ? a.piece_head : a.piece_tail) + (size_t)c * a.D + col0);
-            piece_arrive_body<VEC, LANES>(a, __ldg(a.nz_row + k), ct, col0, active, lane, mask);
-        }
-        return;
-    }
-    if (have_head) piece_arrive<VEC, LANES>(a, head_row, ct, col0, active, lane, mask);
-    if (open) {  // the chunk ends inside a row
-        if (active) acc.store((head_open ? a.piece_head : a.piece_tail) + (size_t)c * a.D + col0);
-        piece_arrive<VEC, LANES>(a, __ldg(a.nz_row + k), ct, col0, active, lane, mask);
+    if (open && active)  // the chunk ends inside a row
+        acc.store((head_open ? a.piece_head : a.piece_tail) + (size_t)c * a.D + col0);
+    // Piece arrivals, after the edge loop, when no accumulator is live any more.  Which rows were cut is recomputed from
+    // chunk_nz instead of being carried through the loop: the head row (index kh) left a piece here iff the chunk began
+    // inside it and it ended here (k moved past it); the row open at the end (index k) left the other one.
+    const uint32_t cn2 = __ldg(a.chunk_nz + c);  // re-read (L1 hit): cheaper than a register held through the loop
+    const uint32_t kh = cn2 & ~CGB_END_FLAG;
+    const bool head_done = (cn2 & CGB_END_FLAG) != 0 && k > kh;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool doit = pass == 0 ? head_done : open;
+        if (doit) piece_arrive_body<VEC, LANES>(a, pass == 0 ? kh : k, ct, col0, active, lane, mask);
     }
 }
 
@@ -493,7 +498,7 @@ __global__ void __launch_bounds__(BLOCK) gather_chunk_async_kernel(const __grid_
                         }
                     } else {
                         if (active) acc.store(a.piece_head + (size_t)c * a.D + col0);
-                        head_row = row;
+                        head_row = k;
                         have_head = true;
                     }
                     acc.zero();
@@ -554,7 +559,7 @@ __global__ void __launch_bounds__(BLOCK) gather_chunk_async_kernel(const __grid_
     if (have_head) piece_arrive<VEC, LANES>(a, head_row, ct, col0, active, lane, mask);
     if (open) {  // the chunk ends inside a row
         if (active) acc.store((head_open ? a.piece_head : a.piece_tail) + (size_t)c * a.D + col0);
-        piece_arrive<VEC, LANES>(a, __ldg(a.nz_row + k), ct, col0, active, lane, mask);
+        piece_arrive<VEC, LANES>(a, k, ct, col0, active, lane, mask);
     }
 }
 
@@ -824,6 +829,7 @@ int cgb_csr_destroy(cgb_ctx* ctx, cgb_csr* c) {
     cudaFree(c->d_slice_count); cudaFree(c->d_long_id); cudaFree(c->d_counters); cudaFree(c->d_partial);
     cudaFree(c->d_colf); cudaFree(c->d_nz_row); cudaFree(c->d_empty_row); cudaFree(c->d_chunk_nz);
     cudaFree(c->d_chunk_ctr); cudaFree(c->d_piece);
+    for (void* p : c->retired) cudaFree(p);
     delete c;
     return CGB_OK;
 }
@@ -833,7 +839,7 @@ const uint32_t* cgb_csr_rowptr(const cgb_csr* c) { return c ? c->d_rowptr : null
 const uint32_t* cgb_csr_col(const cgb_csr* c) { return c ? c->d_col : nullptr; }
 
 static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, const uint64_t* d_delta, uint64_t* d_y,
-                       uint32_t D, int n_blk, uint64_t* const* blk_base, const uint32_t* blk_off) {
+                       uint32_t D, int n_blk, uint64_t* const* blk_base, const uint32_t* blk_off, bool compact = false) {
     cgb_csr* csr = const_cast<cgb_csr*>(csr_c);
     CGB_REQUIRE(ctx, csr && d_x && (d_y || n_blk > 0) && D > 0, "cgb_gather_sum: null argument");
     CGB_REQUIRE(ctx, (const void*)d_x != (const void*)d_y, "cgb_gather_sum: y must not alias x");
@@ -852,10 +858,12 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
     if (!use_row_schedule()) {
         CGB_REQUIRE(ctx, csr->n_src_rows < CGB_END_FLAG, "cgb_gather_sum: source rows must fit 31 bits");
         if (csr->n_chunks) {
+            // grow-only scratch of the CSR handle.  An outgrown buffer is RETIRED, not freed: a captured CUDA graph or a launch
+            // still in flight may hold its address; everything is released in cgb_csr_destroy.  (A handle serves one stream at
+            // a time -- see the contract in include/cognn_b200.h.)
             size_t need = 2 * (size_t)csr->n_chunks * D;
             if (need > csr->piece_words) {
-                CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                cudaFree(csr->d_piece);
+                if (csr->d_piece) csr->retired.push_back(csr->d_piece);
                 csr->d_piece = nullptr;
                 csr->piece_words = 0;
                 CGB_CHECK_CUDA(ctx, cudaMalloc((void**)&csr->d_piece, need * sizeof(u64)));
@@ -863,8 +871,7 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
             }
             uint32_t need_ctr = csr->n_chunks * s.n_ct;
             if (need_ctr > csr->chunk_ctr_len) {
-                CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                cudaFree(csr->d_chunk_ctr);
+                if (csr->d_chunk_ctr) csr->retired.push_back(csr->d_chunk_ctr);
                 csr->d_chunk_ctr = nullptr;
                 csr->chunk_ctr_len = 0;
                 CGB_CHECK_CUDA(ctx, cudaMalloc((void**)&csr->d_chunk_ctr, need_ctr * sizeof(uint32_t)));
@@ -888,13 +895,15 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
             a.blk_off[t] = blk_off[t];
         }
         if (n_blk) a.blk_off[n_blk] = blk_off[n_blk];
-        const uint64_t total = ((uint64_t)csr->n_chunks + csr->n_empty) * s.n_ct;
-        // tuning knobs (round 1 experiments): CGB_GATHER_IMPL=async -> cp.async staged variant (CGB_GATHER_NBUF=2|3);
-        // CGB_GATHER_U8=1 -> 8 register loads in flight per lane at 32 warps/SM;
-        // CGB_GATHER_OCC=1024|1280|1536|2048 -> register cap for that many resident threads per SM (U = 4)
+        a.compact = compact ? 1u : 0u;
+        const uint64_t total = ((uint64_t)csr->n_chunks + (compact ? 0u : csr->n_empty)) * s.n_ct;
+        if (total == 0) return CGB_OK;
+        // A/B knobs kept from the round-1 experiments (DESIGN.md section 5 has the measurements): CGB_GATHER_IMPL=async -> cp.async
+        // staged variant (CGB_GATHER_NBUF=2|3); CGB_GATHER_VEC=2 -> 128-bit kernels; CGB_GATHER_IPL=1 -> one index word per lane
         static const bool use_async = getenv("CGB_GATHER_IMPL") && std::string(getenv("CGB_GATHER_IMPL")) == "async";
         static const int nbuf = getenv("CGB_GATHER_NBUF") ? atoi(getenv("CGB_GATHER_NBUF")) : 2;
         if (use_async) {
+            CGB_REQUIRE(ctx, !compact, "cgb_gather_sum_compact: not available with CGB_GATHER_IMPL=async");
             int rc = dispatch_shape(s, [&](auto V, auto L, auto U_) {
                 constexpr int BLOCK = 128;
                 constexpr int VV = decltype(V)::value, LL = decltype(L)::value, UU = decltype(U_)::value;
@@ -914,42 +923,27 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
             });
             CGB_REQUIRE(ctx, rc == 0, "cgb_gather_sum: no kernel for this shape");
             CGB_CHECK_LAUNCH(ctx, "gather_chunk_async_kernel");
+            ctx->last_kernel = "gather_chunk_async_kernel";
             return CGB_OK;
         }
-        static const int use_u8 = getenv("CGB_GATHER_U8") ? 1 : 0;
-        static const int occ = getenv("CGB_GATHER_OCC") ? atoi(getenv("CGB_GATHER_OCC")) : 1536;
         if (vec4) {
-            static const int occ4 = getenv("CGB_GATHER_OCC") ? atoi(getenv("CGB_GATHER_OCC")) : 1024;
-            static const int u4 = getenv("CGB_GATHER_U") ? atoi(getenv("CGB_GATHER_U")) : 4;
             int rc4 = dispatch_shape4(s, [&](auto V, auto L, auto U_) {
                 constexpr int BLOCK = 128;
                 constexpr int VV = decltype(V)::value, LL = decltype(L)::value;
                 constexpr int GROUPS = BLOCK / LL;
                 constexpr int UU = decltype(U_)::value;
                 constexpr int UH = UU >= 4 ? 4 : UU;
-                constexpr int U2 = UU >= 2 ? 2 : UU;
                 const unsigned blocks = (unsigned)((total + GROUPS - 1) / GROUPS);
                 static const int ipl = getenv("CGB_GATHER_IPL") ? atoi(getenv("CGB_GATHER_IPL")) : 2;
-                if (ipl == 2 && LL <= 4) {  // 8 (LANES = 4) or 4 (LANES = 2) edges per batch
+                if (LL <= 4 && ipl == 2) {  // 8 (LANES = 4) or 4 (LANES = 2) edges per batch, 4 row loads in flight per lane
                     constexpr int B2 = LL * 2;
-                    constexpr int U8 = B2 >= 8 ? 8 : B2;
                     constexpr int U4 = B2 >= 4 ? 4 : B2;
-                    if (u4 == 8) {
-                        if (occ4 >= 1024) gather_chunk_kernel<VV, LL, U8, BLOCK, 1024, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
-                        else if (occ4 >= 768) gather_chunk_kernel<VV, LL, U8, BLOCK, 768, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
-                        else gather_chunk_kernel<VV, LL, U8, BLOCK, 640, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
-                    } else {
-                        if (occ4 >= 1280) gather_chunk_kernel<VV, LL, U4, BLOCK, 1280, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
-                        else if (occ4 >= 1024) gather_chunk_kernel<VV, LL, U4, BLOCK, 1024, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
-                        else gather_chunk_kernel<VV, LL, U4, BLOCK, 896, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
-                    }
-                } else if (u4 == 2) {
-                    if (occ4 >= 1536) gather_chunk_kernel<VV, LL, U2, BLOCK, 1536><<<blocks, BLOCK, 0, ctx->stream>>>(a);
-                    else gather_chunk_kernel<VV, LL, U2, BLOCK, 1024><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                    gather_chunk_kernel<VV, LL, U4, BLOCK, 1024, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                    ctx->last_kernel = LL == 4 ? "gather_chunk_kernel<VEC=4,LANES=4,U=4,128,1024,IPL=2> (256-bit row loads)"
+                                               : "gather_chunk_kernel<VEC=4,LANES=2,U=4,128,1024,IPL=2> (256-bit row loads)";
                 } else {
-                    if (occ4 >= 1536) gather_chunk_kernel<VV, LL, UH, BLOCK, 1536><<<blocks, BLOCK, 0, ctx->stream>>>(a);
-                    else if (occ4 >= 1280) gather_chunk_kernel<VV, LL, UH, BLOCK, 1280><<<blocks, BLOCK, 0, ctx->stream>>>(a);
-                    else gather_chunk_kernel<VV, LL, UH, BLOCK, 1024><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                    gather_chunk_kernel<VV, LL, UH, BLOCK, 1024><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                    ctx->last_kernel = "gather_chunk_kernel<VEC=4,LANES>=8,U=4,128,1024,IPL=1> (256-bit row loads)";
                 }
             });
             CGB_REQUIRE(ctx, rc4 == 0, "cgb_gather_sum: no 256-bit kernel for this shape");
@@ -963,28 +957,26 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
             constexpr int UU = decltype(U_)::value;
             constexpr int UH = UU >= 8 ? 4 : UU;
             const unsigned blocks = (unsigned)((total + GROUPS - 1) / GROUPS);
-            if (use_u8) gather_chunk_kernel<VV, LL, UU, BLOCK, 1024><<<blocks, BLOCK, 0, ctx->stream>>>(a);
-            else if (occ == 1024) gather_chunk_kernel<VV, LL, UH, BLOCK, 1024><<<blocks, BLOCK, 0, ctx->stream>>>(a);
-            else if (occ == 1536) gather_chunk_kernel<VV, LL, UH, BLOCK, 1536><<<blocks, BLOCK, 0, ctx->stream>>>(a);
-            else if (occ == 2048) gather_chunk_kernel<VV, LL, UH, BLOCK, 2048><<<blocks, BLOCK, 0, ctx->stream>>>(a);
-            else gather_chunk_kernel<VV, LL, UH, BLOCK, 1280><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+            gather_chunk_kernel<VV, LL, UH, BLOCK, 1536><<<blocks, BLOCK, 0, ctx->stream>>>(a);
         });
         CGB_REQUIRE(ctx, rc == 0, "cgb_gather_sum: no kernel for this shape");
         CGB_CHECK_LAUNCH(ctx, "gather_chunk_kernel");
+        ctx->last_kernel = "gather_chunk_kernel<VEC<=2,...,128,1536,IPL=1> (128-/64-bit row loads)";
         return CGB_OK;
     }
+    CGB_REQUIRE(ctx, !compact, "cgb_gather_sum_compact: needs the edge-balanced schedule");
     if (csr->n_slices) {
         size_t need = (size_t)csr->n_slices * D;
         if (need > csr->partial_words || !is_aligned16(csr->d_partial)) {
-            CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            cudaFree(csr->d_partial);
+            if (csr->d_partial) csr->retired.push_back(csr->d_partial);
+            csr->d_partial = nullptr;
             CGB_CHECK_CUDA(ctx, cudaMalloc((void**)&csr->d_partial, need * sizeof(u64)));
             csr->partial_words = need;
         }
         uint32_t need_ctr = csr->n_long_rows * s.n_ct;
         if (need_ctr > csr->counters_len) {
-            CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            cudaFree(csr->d_counters);
+            if (csr->d_counters) csr->retired.push_back(csr->d_counters);
+            csr->d_counters = nullptr;
             CGB_CHECK_CUDA(ctx, cudaMalloc((void**)&csr->d_counters, need_ctr * sizeof(uint32_t)));
             CGB_CHECK_CUDA(ctx, cudaMemsetAsync(csr->d_counters, 0, need_ctr * sizeof(uint32_t), ctx->stream));
             csr->counters_len = need_ctr;
@@ -1007,6 +999,7 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
     });
     CGB_REQUIRE(ctx, rc == 0, "cgb_gather_sum: no kernel for this shape");
     CGB_CHECK_LAUNCH(ctx, "gather_sum_kernel");
+    ctx->last_kernel = "gather_sum_kernel (row schedule)";
     return CGB_OK;
 }
 
@@ -1023,6 +1016,15 @@ int cgb_gather_sum_blocks(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x,
                 "cgb_gather_sum_blocks: offsets must span the rows");
     return gather_impl(ctx, csr, d_x, d_delta, nullptr, D, (int)n_blocks, d_block_base, block_row_offsets);
 }
+
+int cgb_gather_sum_compact(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x, const uint64_t* d_delta, uint64_t* d_y,
+                           uint32_t D) {
+    CGB_REQUIRE(ctx, csr, "cgb_gather_sum_compact: null argument");
+    if (csr->n_nz == 0) return CGB_OK;
+    return gather_impl(ctx, csr, d_x, d_delta, d_y, D, 0, nullptr, nullptr, true);
+}
+uint32_t cgb_csr_num_nonempty_rows(const cgb_csr* c) { return c ? c->n_nz : 0; }
+const uint32_t* cgb_csr_nonempty_rows(const cgb_csr* c) { return c ? c->d_nz_row : nullptr; }
 
 // Pipelined host entry point: slot s = step & 1 owns a device staging area; the H2D of step i+1 runs on its own stream
 // while step i computes and step i-1... copies back (PCIe is full duplex), so host-buffer throughput approaches

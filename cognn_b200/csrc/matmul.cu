@@ -163,6 +163,9 @@ int run_matmul(cgb_ctx* ctx, MatmulArgs a) {
     // pipe selection (DESIGN.md "Matmul design"): CGB_MATMUL_IMPL = imad | tc | auto
     {
         const char* impl = getenv("CGB_MATMUL_IMPL");
+        if (ctx->matmul_impl == 1) impl = "imad";  // cgb_ctx_set_matmul_impl overrides the environment
+        else if (ctx->matmul_impl == 2) impl = "tc";
+        else if (ctx->matmul_impl == 0) impl = nullptr;
         bool tc = false;
         if (impl && !strcmp(impl, "tc")) tc = a.K >= 1;
         else if (impl && !strcmp(impl, "imad")) tc = false;
@@ -218,6 +221,8 @@ int run_matmul(cgb_ctx* ctx, MatmulArgs a) {
     else if (BN == 16) launch_cfg<128, 16, 16, 4, 2>(ctx, a);
     else launch_cfg<256, 8, 16, 8, 1>(ctx, a);
     CGB_CHECK_LAUNCH(ctx, "matmul_kernel");
+    ctx->last_kernel = BN == 64 ? "matmul_kernel<128,64,16,8,4> (IMAD.WIDE u64 tiles)"
+                                : (BN == 16 ? "matmul_kernel<128,16,16,4,2> (IMAD.WIDE u64 tiles)" : "matmul_kernel<256,8,16,8,1> (IMAD.WIDE u64 tiles)");
     if (needs_finish) {
         const uint64_t n = (uint64_t)a.M * a.N;
         // accumulate + finish: C = trunc(T + Z + (accumulate ? C : 0)) is only needed without accumulate here
@@ -279,3 +284,61 @@ int cgb_beaver_matmul_finish(cgb_ctx* ctx, const uint64_t* d_E, const uint64_t* 
 }
 
 }  // extern "C"
+
+// ---- pipe-ceiling probe: independent u64 multiply-adds in registers, no memory traffic (the denominator of the integer-pipe
+// fraction bench.py reports; MEASURED_PEAKS.json only has HBM and bf16) ------------------------------------------------------
+namespace {
+template <int TM, int TN>
+__global__ void __launch_bounds__(256) imad_probe_kernel(u64* out, int iters, u64 seed) {
+    u64 acc[TM][TN], fa[TM], fb[TN];
+    const u64 t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) fa[i] = seed * (t + i + 1);
+#pragma unroll
+    for (int j = 0; j < TN; ++j) fb[j] = (seed ^ 0x9E3779B97F4A7C15ull) * (t + 7 * j + 3);
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] += fa[i] * fb[j];
+#pragma unroll
+        for (int i = 0; i < TM; ++i) fa[i] += (u64)it;  // operands change every iteration: nothing can be hoisted
+    }
+    u64 s = 0;
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) s ^= acc[i][j];
+    out[t] = s;
+}
+}  // namespace
+
+extern "C" int cgb_probe_imad_peak(cgb_ctx* ctx, double* u64_mac_per_s) {
+    CGB_REQUIRE(ctx, u64_mac_per_s, "cgb_probe_imad_peak: null argument");
+    CGB_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int blocks = ctx->num_sms * 8, threads = 256, iters = 4096;
+    int rc = cgb_scratch_reserve(ctx, (size_t)blocks * threads * sizeof(u64));
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    CGB_CHECK_CUDA(ctx, cudaEventCreate(&e0));
+    CGB_CHECK_CUDA(ctx, cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CGB_CHECK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        imad_probe_kernel<8, 4><<<blocks, threads, 0, ctx->stream>>>((u64*)ctx->scratch, iters, 0x1234567ull + rep);
+        CGB_CHECK_LAUNCH(ctx, "imad_probe_kernel");
+        CGB_CHECK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        CGB_CHECK_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CGB_CHECK_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms > 0.f) best = std::max(best, (double)blocks * threads * iters * 32.0 / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *u64_mac_per_s = best;
+    return CGB_OK;
+}

@@ -278,6 +278,57 @@ __global__ void __launch_bounds__(192, 1) matmul_tc_kernel(const __grid_constant
     }
 }
 
+// ---- pipe-ceiling probe ------------------------------------------------------------------------------------------------
+// The same 12 tcgen05.mma per k-step as matmul_tc_kernel (36 limb products, M = 128, N = 64..256, K = 32), issued back to back
+// on whatever the (zeroed) shared memory holds: no TMA, no epilogue.  One CTA per SM.  Its rate is the denominator of the
+// tensor-pipe fraction bench.py reports for the limb matmul: what the instruction mix could reach if operands were free.
+__global__ void __launch_bounds__(64, 1) tc_pipe_probe_kernel(uint32_t n_ksteps) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t done_bar;
+    __shared__ uint32_t tmem_base_smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t i = threadIdx.x; i < (A_STAGE_BYTES + B_STAGE_BYTES) / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&done_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_smem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA's async proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+    if (warp == 0 && lane == 0) {
+        const uint32_t idesc0 = (2u << 4) | ((uint32_t)(TC_BM >> 4) << 24);
+        const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + A_STAGE_BYTES);
+        for (uint32_t ks = 0; ks < n_ksteps; ++ks) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint64_t da = smem_desc(a0 + i * A_PLANE_BYTES, TC_BM * 16, 128);
+#pragma unroll
+                for (int j0 = 0; j0 + i < 8; j0 += 4) {
+                    const int planes = (8 - i - j0) < 4 ? (8 - i - j0) : 4;
+                    const uint32_t n = (uint32_t)planes * TC_BN;
+                    const uint64_t db = smem_desc(b0 + (uint32_t)j0 * TC_BN * 16, 8 * TC_BN * 16, 128);
+                    tc_mma_i8(tmem_base + (uint32_t)(i + j0) * TC_BN, da, db, idesc0 | ((n >> 3) << 17), (ks > 0 || i > 0) ? 1u : 0u);
+                }
+            }
+        }
+        tc_commit(smem_u32(&done_bar));
+        mbar_wait(smem_u32(&done_bar), 0);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 #ifdef CGB_EXPERIMENTAL_TC_MC
 // ---- EXPERIMENTAL, NOT PART OF THE PRODUCT BUILD (compile with -DCGB_EXPERIMENTAL_TC_MC) ------------------------------------
 // Next step named in DESIGN.md section 8: the kernel above keeps the tensor pipe 54 % busy because each 128x64 tile pulls
@@ -439,19 +490,17 @@ static int tc_chunk(cgb_ctx* ctx, const u64* const A[2], const u64* const B[2], 
     const uint32_t Mpad = (M + TC_BM - 1) / TC_BM * TC_BM, Npad = (N + TC_BN - 1) / TC_BN * TC_BN;
     const size_t a_bytes = (size_t)(Mpad / TC_BM) * n_ksteps * A_STAGE_BYTES;
     const size_t b_bytes = (size_t)(Npad / TC_BN) * n_ksteps * B_STAGE_BYTES;
-    // planes live in their own grow-only buffer (ctx->scratch may hold V + F of the caller)
-    static thread_local struct { void* p; size_t n; int dev; } planes = {nullptr, 0, -1};
+    // planes live in a grow-only buffer of the CONTEXT (ctx->scratch may hold V + F of the caller); an outgrown buffer is
+    // retired until the context is destroyed, because a captured CUDA graph may still hold its address
     const size_t need = ((a_bytes + 255) & ~(size_t)255) + b_bytes;
-    if (need > planes.n || planes.dev != ctx->device) {
-        CGB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (planes.p) cudaFree(planes.p);
-        planes.p = nullptr;
-        planes.n = 0;
-        CGB_CHECK_CUDA(ctx, cudaMalloc(&planes.p, need));
-        planes.n = need;
-        planes.dev = ctx->device;
+    if (need > ctx->tc_planes_bytes) {
+        if (ctx->tc_planes) ctx->retired.push_back(ctx->tc_planes);
+        ctx->tc_planes = nullptr;
+        ctx->tc_planes_bytes = 0;
+        CGB_CHECK_CUDA(ctx, cudaMalloc(&ctx->tc_planes, need));
+        ctx->tc_planes_bytes = need;
     }
-    uint8_t* dA = (uint8_t*)planes.p;
+    uint8_t* dA = (uint8_t*)ctx->tc_planes;
     uint8_t* dB = dA + ((a_bytes + 255) & ~(size_t)255);
     for (int p = 0; p < n_pairs; ++p) {
         const uint64_t ta = (uint64_t)Mpad * ks_pair * 2, tb = (uint64_t)Npad * ks_pair * 2;
@@ -461,10 +510,9 @@ static int tc_chunk(cgb_ctx* ctx, const u64* const A[2], const u64* const B[2], 
         limb_split_cols_kernel<<<(unsigned)((tb + 255) / 256), 256, 0, ctx->stream>>>(B[p], dB, K, N, Npad, p * ks_pair, n_ksteps, ks_pair);
         CGB_CHECK_LAUNCH(ctx, "limb_split_cols_kernel");
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->tc_attr_set) {  // a per-device attribute: set once per context, not once per process
         CGB_CHECK_CUDA(ctx, cudaFuncSetAttribute(matmul_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-        attr_set = true;
+        ctx->tc_attr_set = true;
     }
     TcArgs a;
     a.A = dA; a.B = dB; a.Z = Z; a.C = C; a.M = M; a.N = N; a.n_ksteps = n_ksteps;
@@ -473,10 +521,9 @@ static int tc_chunk(cgb_ctx* ctx, const u64* const A[2], const u64* const B[2], 
 #ifdef CGB_EXPERIMENTAL_TC_MC
     static const bool use_mc = getenv("CGB_MATMUL_IMPL") && std::string(getenv("CGB_MATMUL_IMPL")) == "tc_mc";
     if (use_mc && grid.x % TC_MC == 0) {  // whole clusters of four N-tiles only (N a multiple of 256)
-        static bool mc_attr_set = false;
-        if (!mc_attr_set) {
+        if (!ctx->tc_mc_attr_set) {
             CGB_CHECK_CUDA(ctx, cudaFuncSetAttribute(matmul_tc_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-            mc_attr_set = true;
+            ctx->tc_mc_attr_set = true;
         }
         matmul_tc_mc_kernel<<<grid, 192, TC_SMEM_BYTES, ctx->stream>>>(a);
         CGB_CHECK_LAUNCH(ctx, "matmul_tc_mc_kernel");
@@ -485,6 +532,35 @@ static int tc_chunk(cgb_ctx* ctx, const u64* const A[2], const u64* const B[2], 
 #endif
     matmul_tc_kernel<<<grid, 192, TC_SMEM_BYTES, ctx->stream>>>(a);
     CGB_CHECK_LAUNCH(ctx, "matmul_tc_kernel");
+    ctx->last_kernel = "matmul_tc_kernel (tcgen05 kind::i8 limbs, TMEM diagonals) + limb_split_{rows,cols}_kernel";
+    return CGB_OK;
+}
+
+// u8 x u8 limb MACs per second the tensor pipe sustains on the kernel's own MMA mix with free operands (synchronises)
+extern "C" int cgb_probe_tensor_i8_peak(cgb_ctx* ctx, double* limb_mac_per_s) {
+    CGB_REQUIRE(ctx, limb_mac_per_s, "cgb_probe_tensor_i8_peak: null argument");
+    CGB_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t smem = A_STAGE_BYTES + B_STAGE_BYTES + 1024;
+    CGB_CHECK_CUDA(ctx, cudaFuncSetAttribute(tc_pipe_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    CGB_CHECK_CUDA(ctx, cudaEventCreate(&e0));
+    CGB_CHECK_CUDA(ctx, cudaEventCreate(&e1));
+    const uint32_t n_ksteps = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CGB_CHECK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        tc_pipe_probe_kernel<<<ctx->num_sms, 64, smem, ctx->stream>>>(n_ksteps);
+        CGB_CHECK_LAUNCH(ctx, "tc_pipe_probe_kernel");
+        CGB_CHECK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        CGB_CHECK_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CGB_CHECK_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        const double macs = (double)ctx->num_sms * n_ksteps * 36.0 * TC_BM * TC_BN * TC_BK;
+        if (rep > 0 && ms > 0.f) best = std::max(best, macs / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *limb_mac_per_s = best;
     return CGB_OK;
 }
 

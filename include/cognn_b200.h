@@ -54,7 +54,8 @@ typedef enum cgb_status {
 } cgb_status;
 
 typedef struct cgb_ctx cgb_ctx; /* device + stream + scratch */
-typedef struct cgb_csr cgb_csr; /* device-resident CSR-by-destination + balanced work list */
+typedef struct cgb_csr cgb_csr; /* device-resident CSR-by-destination + balanced work list; carries grow-only scratch for
+                                   the gather, so one handle serves ONE stream at a time (create one per stream otherwise) */
 
 /* ---- library / context ---------------------------------------------------------------------------------- */
 const char* cgb_version(void);
@@ -114,6 +115,30 @@ int cgb_gather_sum(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x, const 
  * block_row_offsets are HOST arrays (n_blocks <= 16).  Completion on the peer needs a cross-rank barrier afterwards. */
 int cgb_gather_sum_blocks(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x, const uint64_t* d_delta, uint32_t D,
                           uint32_t n_blocks, uint64_t* const* d_block_base, const uint32_t* block_row_offsets);
+/* COMPACT form of the same gather: row k of d_y is the k-th destination row that HAS an edge (cgb_csr_nonempty_rows()[k],
+ * ascending); rows without edges are not written.  d_y (and d_delta, if given) are cgb_csr_num_nonempty_rows() x D.  This is
+ * the mirror-update block one party hands to another (ssk.h:835 -> 1067/1090): which destinations of the receiver have an
+ * edge from the sender is public to both sides (sendPosVec / recvPosVec, ssk.h:507-516), so only those rows cross NVLink.
+ * The consumer adds the block with cgb_scatter_add_rows. */
+int cgb_gather_sum_compact(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x, const uint64_t* d_delta, uint64_t* d_y,
+                           uint32_t D);
+uint32_t cgb_csr_num_nonempty_rows(const cgb_csr* csr);
+const uint32_t* cgb_csr_nonempty_rows(const cgb_csr* csr); /* device pointer, ascending row ids */
+/* v[idx[k], :] (+)= src[k, :] for k < n: the GatherComp addition (gcn.h:456-463) of one received compact block.  d_src may
+ * be PEER memory (the producer's staging buffer mapped with cgb_ipc_open): the rows are pulled over NVLink and added in one
+ * pass, never landing in local memory first.  idx must not repeat (it is a PosVec: distinct destination rows); assign != 0
+ * stores instead of adding.  n_ctas = 0 picks the grid. */
+int cgb_scatter_add_rows(cgb_ctx* ctx, const uint32_t* d_idx, uint64_t n, const uint64_t* d_src, uint64_t* d_v, uint32_t D,
+                         int assign, uint32_t n_ctas);
+/* Cross-GPU arrival flags in place of the TCP recv that blocks ssk.h:1090: cgb_flag_signal stores `value` to a 4-byte flag
+ * (usually in the consumer's memory, mapped with cgb_ipc_open) after everything enqueued before it on this context's stream is
+ * visible system-wide; cgb_flag_wait holds this context's stream until *d_flag >= value (wrap-safe signed difference).
+ * mode 0: stream memory operation (cuStreamWaitValue32, no SM occupied); mode 1: one-thread kernel polling for at most ~2 s,
+ * then *d_err (optional device word) is set to 1 and the stream continues -- a lost peer cannot hang the GPU. */
+int cgb_flag_signal(cgb_ctx* ctx, uint32_t* d_flag, uint32_t value);
+int cgb_flag_wait(cgb_ctx* ctx, const uint32_t* d_flag, uint32_t value, int mode, uint32_t* d_err);
+/* name of the kernel the last cgb_gather_sum* / cgb_matmul dispatch of this context chose (static string) */
+const char* cgb_ctx_last_kernel(cgb_ctx* ctx);
 /* CUDA IPC plumbing for the peer buffers (one process per GPU): d_ptr must come from cgb_malloc; handle is 64 bytes */
 int cgb_ipc_export(cgb_ctx* ctx, void* d_ptr, void* out_handle64);
 int cgb_ipc_open(cgb_ctx* ctx, const void* handle64, void** d_peer_out);
@@ -173,6 +198,15 @@ int cgb_matmul(cgb_ctx* ctx, const uint64_t* d_A, const uint64_t* d_B, uint64_t*
 int cgb_beaver_matmul_finish(cgb_ctx* ctx, const uint64_t* d_E, const uint64_t* d_F, const uint64_t* d_U,
                              const uint64_t* d_V, const uint64_t* d_Z, uint64_t* d_C, uint32_t M, uint32_t K,
                              uint32_t N, int share, int f);
+
+/* Pipe selection of cgb_matmul / cgb_beaver_matmul_finish for this context: -1 = CGB_MATMUL_IMPL from the environment or auto
+ * (default), 0 = auto by shape, 1 = integer pipe (IMAD tiles), 2 = tensor pipe (tcgen05 int8 limbs).  Same bits either way. */
+int cgb_ctx_set_matmul_impl(cgb_ctx* ctx, int impl);
+/* Pipe ceilings measured on this device (synchronise; a few ms each): u64 multiply-adds per second of the integer pipe on
+ * register operands, and u8 x u8 limb MACs per second of the tensor pipe on the limb kernel's own tcgen05.mma mix with
+ * operands already in shared memory.  bench.py divides the matmul rates by these. */
+int cgb_probe_imad_peak(cgb_ctx* ctx, double* u64_mac_per_s);
+int cgb_probe_tensor_i8_peak(cgb_ctx* ctx, double* limb_mac_per_s);
 
 /* ---- (3) fused elementwise: truncation, masking / opening, scaling ---------------------------------------- */
 int cgb_add(cgb_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint64_t n);

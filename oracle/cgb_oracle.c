@@ -199,7 +199,8 @@ void orc_gather_sum_csr(const uint32_t* rowptr, const uint32_t* col, const uint6
 #pragma omp parallel for schedule(dynamic, 256)
     for (size_t v = 0; v < n_rows; ++v) {
         uint64_t* yr = y + v * D;
-        if (delta) memcpy(yr, delta + v * D, D * sizeof(uint64_t));
+        if (delta == y) { /* in place: y already holds delta (accumulation of the blocks of several source parties) */ }
+        else if (delta) memcpy(yr, delta + v * D, D * sizeof(uint64_t));
         else memset(yr, 0, D * sizeof(uint64_t));
         for (uint32_t e = rowptr[v]; e < rowptr[v + 1]; ++e) {
             const uint64_t* xr = x + (size_t)col[e] * D;

@@ -225,13 +225,19 @@ def transpose(x):
     return out
 
 
-def gather_sum_csr(rowptr, col, x, delta=None):
+def gather_sum_csr(rowptr, col, x, delta=None, out=None):
+    """y = delta + A x.  `out` (n_rows x D uint64, C-contiguous) avoids the allocation; with delta is out the sum is
+    accumulated in place."""
     rowptr, col, x = _u32(rowptr), _u32(col), _u64(x)
     n_rows = rowptr.size - 1
     D = x.shape[1]
     if delta is not None:
         delta = _u64(delta)
-    y = np.zeros((n_rows, D), dtype=np.uint64)
+    if out is None:
+        y = np.zeros((n_rows, D), dtype=np.uint64)
+    else:
+        y = out
+        assert y.dtype == np.uint64 and y.flags.c_contiguous and y.shape == (n_rows, D)
     lib().orc_gather_sum_csr(_p(rowptr), _p(col), _p(x), _p(delta), _p(y), C.c_size_t(n_rows), C.c_size_t(D))
     return y
 

@@ -85,3 +85,68 @@ def test_synthetic_partition_is_balanced():
         assert int(rowptr[-1]) == col.numel() == E // 2 and bool((rowptr[1:] >= rowptr[:-1]).all())
         tot += col.numel()
     assert tot == E
+
+
+def _pull_worker(rank, world, port, n_local, E, D, out_dir):
+    """The pull exchange of bench.py with its device pieces replaced by the oracle: compact blocks (rows of destinations that
+    have an edge), the PosVec exchange (bench.exchange_index_lists), arrival order (bench.pull_orders), scatter-add."""
+    import bench
+    from oracle import pyoracle as po
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rowptr, col = bench.build_party_csr(torch, n_local, E, world, rank, 42, "cpu")
+        g = torch.Generator().manual_seed(43 + rank)
+        x = torch.randint(-2**63, 2**63 - 1, (n_local, D), dtype=torch.int64, generator=g)
+        rp, cl, xh = rowptr.numpy().view(np.uint32), col.numpy().view(np.uint32), x.numpy().view(np.uint64)
+        dense = po.gather_sum_csr(rp, cl, xh)  # (world * n_local) x D
+        # reference: plain all-to-all of the dense blocks + sums
+        y = torch.from_numpy(dense.view(np.int64))
+        want = torch.empty((n_local, D), dtype=torch.int64)
+        bench.exchange_and_sum(dist, y, torch.empty_like(y), want, world, n_local, D, lambda a, b, o: torch.add(a, b, out=o))
+        # pull form
+        deg = np.diff(rp.astype(np.int64))
+        nz, blocks = [], []
+        for t in range(world):
+            rows = np.nonzero(deg[t * n_local:(t + 1) * n_local])[0]
+            nz.append(torch.from_numpy(rows.astype(np.int32)))
+            blocks.append(torch.from_numpy(dense[t * n_local + rows].view(np.int64)))
+        nz_from, sizes = bench.exchange_index_lists(torch, dist, nz, rank, world)
+        assert [int(l.numel()) for l in nz_from] == [sizes[s][rank] for s in range(world)]
+        v = y[rank * n_local:(rank + 1) * n_local].clone()  # own block, dense
+        prod, cons = bench.pull_orders(rank, world)
+        assert sorted(prod) == sorted(cons) == [t for t in range(world) if t != rank]
+        reqs = [dist.isend(blocks[t].contiguous(), t) for t in prod]
+        for s in cons:
+            blk = torch.empty((sizes[s][rank], D), dtype=torch.int64)
+            dist.recv(blk, s)
+            v[nz_from[s].long()] += blk
+        for r in reqs:
+            r.wait()
+        open(os.path.join(out_dir, f"pull{rank}"), "w").write("1" if torch.equal(v, want) else "0")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 3])
+def test_pull_exchange_host_logic_gloo(tmp_path, world):
+    port = 29900 + os.getpid() % 300 + world
+    mp.spawn(_pull_worker, args=(world, port, 400, 6000, 16, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert (tmp_path / f"pull{r}").read_text() == "1"
+
+
+def test_pull_orders_pair_up():
+    """Party s gathers its block for party t as its ((t - s) mod P)-th remote block, and t pulls the block of s at the same
+    position: the j-th wait of a consumer is for a block that was its producer's j-th."""
+    import bench
+
+    for P in (2, 3, 4, 8):
+        for s in range(P):
+            prod, _ = bench.pull_orders(s, P)
+            for j, t in enumerate(prod):
+                _, cons = bench.pull_orders(t, P)
+                assert cons[j] == s

@@ -269,3 +269,90 @@ print("ok")
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("D", [1, 2, 7, 16, 40, 64])
+def test_gather_sum_compact_and_scatter_add(cgb, oracle, D):
+    """The compact mirror-update block (one row per destination that has an edge) and its consumer: scattering / adding it
+    into the vertex rows reproduces the dense gather, with and without the offline correlation delta."""
+    import torch
+
+    rng = np.random.default_rng(400 + D)
+    n_dst, n_src = 2300, 1700
+    rowptr, col = power_law_csr(rng, n_dst, n_src, 30000)
+    deg = np.diff(rowptr.astype(np.int64))
+    nz = np.nonzero(deg)[0]
+    assert 0 < nz.size < n_dst
+    x = rand_u64(rng, n_src, D)
+    csr = cgb.csr_create(to_dev(rowptr), to_dev(col), n_src)
+    assert csr.n_nonempty == nz.size
+    assert np.array_equal(to_np(csr.nonempty_rows()).astype(np.int64), nz)
+    dense = oracle.gather_sum_csr(rowptr, col, x)
+    delta_c = rand_u64(rng, nz.size, D)
+    for dl in (None, delta_c):
+        got = cgb.gather_sum_compact(csr, to_dev(x), None if dl is None else to_dev(dl))
+        want = dense[nz] + (0 if dl is None else dl)
+        for _ in range(2):  # second launch: arrival counters reset themselves
+            assert np.array_equal(to_np(got), want)
+            got = cgb.gather_sum_compact(csr, to_dev(x), None if dl is None else to_dev(dl))
+    # consumer side: v += block (GatherComp addition), and the assign form
+    block = cgb.gather_sum_compact(csr, to_dev(x))
+    base = rand_u64(rng, n_dst, D)
+    v = to_dev(base)
+    cgb.scatter_add_rows(csr.nonempty_rows(), block, v)
+    assert np.array_equal(to_np(v), base + dense)
+    v = to_dev(base)
+    cgb.scatter_add_rows(csr.nonempty_rows(), block, v, assign=True)
+    want = base.copy()
+    want[nz] = dense[nz]
+    assert np.array_equal(to_np(v), want)
+    # raw-address source (what a peer's staging buffer looks like) and a tiny grid
+    v = to_dev(base)
+    cgb.scatter_add_rows(csr.nonempty_rows(), int(block.data_ptr()), v, n=nz.size, n_ctas=3)
+    assert np.array_equal(to_np(v), base + dense)
+    torch.cuda.synchronize()
+    csr.destroy()
+
+
+def test_gather_sum_compact_edge_cases(cgb, oracle):
+    import torch
+
+    rng = np.random.default_rng(11)
+    # no edges at all; one row; rows cut by chunk boundaries with empty rows in between
+    for degs in ([0, 0, 0], [5], [0, 64, 0, 65, 200, 0, 0, 1, 63, 500, 0]):
+        rowptr = np.zeros(len(degs) + 1, dtype=np.uint32)
+        rowptr[1:] = np.cumsum(degs)
+        col = rng.integers(0, 40, size=int(rowptr[-1])).astype(np.uint32)
+        x = rand_u64(rng, 40, 16)
+        dcol = to_dev(col) if col.size else torch.empty(0, dtype=torch.int32, device="cuda")
+        csr = cgb.csr_create(to_dev(rowptr), dcol, 40)
+        nz = np.nonzero(np.array(degs))[0]
+        assert csr.n_nonempty == nz.size
+        got = cgb.gather_sum_compact(csr, to_dev(x))
+        assert got.shape[0] == nz.size
+        if nz.size:
+            assert np.array_equal(to_np(got), oracle.gather_sum_csr(rowptr, col, x)[nz])
+        csr.destroy()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_flags_signal_then_wait(cgb, mode):
+    """cgb_flag_signal / cgb_flag_wait on one stream: a wait for a value already signalled (or exceeded) passes; the polling
+    form gives up on a flag nobody raises and reports it instead of hanging."""
+    import time
+
+    import torch
+
+    flag = torch.zeros(4, dtype=torch.int32, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    cgb.flag_signal(flag.data_ptr(), 3)
+    cgb.flag_wait(flag.data_ptr(), 3, mode, err.data_ptr())
+    cgb.flag_wait(flag.data_ptr(), 2, mode, err.data_ptr())  # flags only grow: an older value is satisfied too
+    marker = torch.ones(1, device="cuda")  # enqueued behind the waits on the same (current) stream
+    torch.cuda.synchronize()
+    assert int(flag[0]) == 3 and int(err[0]) == 0 and float(marker[0]) == 1.0
+    if mode == 1:
+        t0 = time.time()
+        cgb.flag_wait(flag.data_ptr() + 4, 1, 1, err.data_ptr())
+        torch.cuda.synchronize()
+        assert int(err[0]) == 1 and time.time() - t0 < 30.0

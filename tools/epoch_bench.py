@@ -32,7 +32,7 @@ def main():
                     "them records the graphs and is left out of the minimum")
     ap.add_argument("--inter", type=float, default=None, help="fraction of inter-party edges (block partition)")
     ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle epoch")
-    ap.add_argument("--check", action="store_true", help="compare the final weight shares with the CPU oracle")
+    ap.add_argument("--check", action="store_true", help="compare every hosted share (X, W, z, g) with the epoch oracle after 3 epochs")
     args = ap.parse_args()
 
     import torch
@@ -108,14 +108,45 @@ def main():
         o.run(iters)
         rec["cpu_oracle"] = {"epoch_s": time.perf_counter() - t0, "setup_s": t_setup, "cores": po.num_threads(),
                              "kind": "port (python-orchestrated C kernels, includes dealer work)"}
-        if args.check and world == 1:
+    if args.check:
+        # a fresh engine for exactly `check_iters` iterations (eager first epoch + captured + replayed graphs), every share this
+        # rank hosts against the epoch oracle: share 0 of its own party and share 1 of its predecessor (all of them on loopback)
+        from oracle import epoch as oep
+
+        check_iters = iters * (3 if args.mode == "train" else 1)
+        if world > 1:
+            uid2 = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                import ctypes
+
+                buf = (ctypes.c_char * 128)()
+                assert eng.load_host().cge_nccl_unique_id(buf) == 0
+                uid2 = torch.frombuffer(bytearray(bytes(buf)), dtype=torch.uint8).clone()
+            dist.broadcast(uid2, 0)
+            e2 = eng.Engine(T, g["cfg"], device=local_rank, rank=rank, nccl_uid=bytes(uid2.numpy().tobytes()))
+            hosted = [(rank, 0), ((rank - 1) % T, 1)]
+        else:
             e2 = eng.Engine(T, g["cfg"], device=local_rank)
-            e2.load(g["edges"], g["tid"], g["feats"], g["labels"])
-            e2.run(iters)
-            ok = all(np.array_equal(e2.download(p, r, n), (o.own if r == 0 else o.hlp)[p]["W"][int(n[1])])
-                     for p in range(T) for r in (0, 1) for n in ("W0", "W1"))
-            rec["bit_exact_vs_oracle"] = bool(ok)
-            e2.close()
+            hosted = [(p, r) for p in range(T) for r in (0, 1)]
+        e2.load(g["edges"], g["tid"], g["feats"], g["labels"])
+        e2.run(check_iters)
+        o = oep.EpochOracle(g["edges"], g["tid"], T, g["feats"], g["labels"], g["cfg"])
+        o.run(check_iters)
+        bad = 0
+        names = ("X", "W0", "W1", "z0", "z1") + (("g",) if args.mode == "train" else ())
+        for p, r in hosted:
+            side = (o.own if r == 0 else o.hlp)[p]
+            for n in names:
+                want = side["X"] if n == "X" else side["g"] if n == "g" else side["W" if n[0] == "W" else "z"][int(n[1])]
+                bad += int(not np.array_equal(e2.download(p, r, n), want))
+        if world > 1:
+            t = torch.tensor([bad], dtype=torch.int64)
+            dist.all_reduce(t)
+            bad = int(t.item())
+        rec["bit_exact_vs_oracle"] = bad == 0
+        rec["checked"] = {"iterations": check_iters, "tensors_per_share": list(names), "shares": 2 * T, "mismatches": bad,
+                          "graph_replays": e2.graph_replays}
+        e2.close()
     if rank == 0:
         print(json.dumps(rec), flush=True)
     e.close()
