@@ -240,7 +240,7 @@ __device__ __forceinline__ u64* out_row(const ChunkArgs& a, uint32_t row) {
 
 // A row segment cut by a chunk boundary has been stored as a "piece"; count the arrival and, if this was the last
 // piece of the row, fold them.  `k` is the row's index in nz_row (its output row in compact mode).
-template <int VEC, int LANES>
+template <int VEC, int LANES, bool COMPACT = false>
 __device__ __forceinline__ void piece_arrive_body(const ChunkArgs& a, uint32_t k, uint32_t ct, uint32_t col0, bool active,
                                                   int lane, unsigned mask) {
     const uint32_t row = __ldg(a.nz_row + k);
@@ -255,7 +255,7 @@ __device__ __forceinline__ void piece_arrive_body(const ChunkArgs& a, uint32_t k
     if (prev == c2 - c1) {  // last of the c2 - c1 + 1 pieces
         __threadfence();
         if (active) {
-            const uint32_t orow = a.compact ? k : row;
+            const uint32_t orow = COMPACT ? k : row;
             const size_t o = (size_t)orow * a.D + col0;
             Acc<VEC> sum;
             sum.zero();
@@ -283,10 +283,7 @@ __device__ __noinline__ void piece_arrive(const ChunkArgs& a, uint32_t k, uint32
 // IPL: column indices each lane holds per batch (a batch is LANES * IPL edges; narrow 256-bit groups of 2 or 4 lanes keep
 // 8 edges per batch this way, so U can stay above the lane count)
 //
-// The piece arrivals run after the edge loop from values recomputed out of chunk_nz, in ONE inlined copy of the fold, so no
-// accumulator is live across it and nothing about a finished row is carried through the loop.  (Round 1 carried `head_row`
-// to the end and called an out-of-line fold; the IPL = 2 instantiation then returned wrong columns 1..3 for cut rows.)
-template <int VEC, int LANES, int U, int BLOCK, int OCC_THREADS, int IPL = 1>
+template <int VEC, int LANES, int U, int BLOCK, int OCC_THREADS, int IPL = 1, bool COMPACT = false>
 __global__ void __launch_bounds__(BLOCK, OCC_THREADS / BLOCK)
 gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
     constexpr int BATCH = LANES * IPL;
@@ -294,7 +291,7 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
     const int lane = threadIdx.x & (LANES - 1);
     const unsigned mask = group_mask<LANES>(threadIdx.x & 31);
     const uint64_t gid = (uint64_t)blockIdx.x * GROUPS + threadIdx.x / LANES;
-    const uint64_t total = ((uint64_t)a.n_chunks + (a.compact ? 0u : a.n_empty)) * a.n_ct;
+    const uint64_t total = ((uint64_t)a.n_chunks + (COMPACT ? 0u : a.n_empty)) * a.n_ct;
     if (gid >= total) return;
     const uint32_t item = (uint32_t)(gid / a.n_ct);
     const uint32_t ct = (uint32_t)(gid - (uint64_t)item * a.n_ct);
@@ -318,7 +315,8 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
     const uint32_t cn = __ldg(a.chunk_nz + c);
     uint32_t k = cn & ~CGB_END_FLAG;
     bool head_open = (cn & CGB_END_FLAG) != 0;
-    bool open = false;
+    bool open = false, have_head = false;
+    uint32_t head_k = 0;
     Acc<VEC> acc;
     acc.zero();
     uint32_t my[IPL], nxt[IPL];
@@ -354,7 +352,7 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
                         if (id[u] & CGB_END_FLAG) {
                             if (!head_open) {  // the row lies inside this chunk: store it
                                 if (active) {
-                                    const uint32_t orow = a.compact ? k : __ldg(a.nz_row + k);
+                                    const uint32_t orow = COMPACT ? k : __ldg(a.nz_row + k);
                                     const size_t o = (size_t)orow * a.D + col0;
                                     if (a.delta) {
                                         Acc<VEC> d;
@@ -365,6 +363,8 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
                                 }
                             } else {  // end of a row that began in an earlier chunk: leave a head piece (arrival counted below)
                                 if (active) acc.store(a.piece_head + (size_t)c * a.D + col0);
+                                head_k = k;
+                                have_head = true;
                             }
                             acc.zero();
                             head_open = false;
@@ -388,18 +388,13 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
 #pragma unroll
         for (int i = 0; i < IPL; ++i) my[i] = nxt[i];
     }
-    if (open && active)  // the chunk ends inside a row
-        acc.store((head_open ? a.piece_head : a.piece_tail) + (size_t)c * a.D + col0);
-    // Piece arrivals, after the edge loop, when no accumulator is live any more.  Which rows were cut is recomputed from
-    // chunk_nz instead of being carried through the loop: the head row (index kh) left a piece here iff the chunk began
-    // inside it and it ended here (k moved past it); the row open at the end (index k) left the other one.
-    const uint32_t cn2 = __ldg(a.chunk_nz + c);  // re-read (L1 hit): cheaper than a register held through the loop
-    const uint32_t kh = cn2 & ~CGB_END_FLAG;
-    const bool head_done = (cn2 & CGB_END_FLAG) != 0 && k > kh;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        const bool doit = pass == 0 ? head_done : open;
-        if (doit) piece_arrive_body<VEC, LANES>(a, pass == 0 ? kh : k, ct, col0, active, lane, mask);
+    // Piece arrivals after the edge loop, always INLINED (two copies): round 1 found that with the fold out of line (a call)
+    // the IPL = 2 instantiation returned wrong columns 1..3 for rows cut by a chunk boundary -- the accumulator is live across
+    // the first call.  No instantiation of this kernel calls out of line any more.
+    if (have_head) piece_arrive_body<VEC, LANES, COMPACT>(a, head_k, ct, col0, active, lane, mask);
+    if (open) {  // the chunk ends inside a row
+        if (active) acc.store((head_open ? a.piece_head : a.piece_tail) + (size_t)c * a.D + col0);
+        piece_arrive_body<VEC, LANES, COMPACT>(a, k, ct, col0, active, lane, mask);
     }
 }
 
@@ -938,11 +933,13 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
                 if (LL <= 4 && ipl == 2) {  // 8 (LANES = 4) or 4 (LANES = 2) edges per batch, 4 row loads in flight per lane
                     constexpr int B2 = LL * 2;
                     constexpr int U4 = B2 >= 4 ? 4 : B2;
-                    gather_chunk_kernel<VV, LL, U4, BLOCK, 1024, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                    if (compact) gather_chunk_kernel<VV, LL, U4, BLOCK, 1024, 2, true><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                    else gather_chunk_kernel<VV, LL, U4, BLOCK, 1024, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
                     ctx->last_kernel = LL == 4 ? "gather_chunk_kernel<VEC=4,LANES=4,U=4,128,1024,IPL=2> (256-bit row loads)"
                                                : "gather_chunk_kernel<VEC=4,LANES=2,U=4,128,1024,IPL=2> (256-bit row loads)";
                 } else {
-                    gather_chunk_kernel<VV, LL, UH, BLOCK, 1024><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                    if (compact) gather_chunk_kernel<VV, LL, UH, BLOCK, 1024, 1, true><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                    else gather_chunk_kernel<VV, LL, UH, BLOCK, 1024><<<blocks, BLOCK, 0, ctx->stream>>>(a);
                     ctx->last_kernel = "gather_chunk_kernel<VEC=4,LANES>=8,U=4,128,1024,IPL=1> (256-bit row loads)";
                 }
             });
@@ -957,7 +954,8 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
             constexpr int UU = decltype(U_)::value;
             constexpr int UH = UU >= 8 ? 4 : UU;
             const unsigned blocks = (unsigned)((total + GROUPS - 1) / GROUPS);
-            gather_chunk_kernel<VV, LL, UH, BLOCK, 1536><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+            if (compact) gather_chunk_kernel<VV, LL, UH, BLOCK, 1536, 1, true><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+            else gather_chunk_kernel<VV, LL, UH, BLOCK, 1536><<<blocks, BLOCK, 0, ctx->stream>>>(a);
         });
         CGB_REQUIRE(ctx, rc == 0, "cgb_gather_sum: no kernel for this shape");
         CGB_CHECK_LAUNCH(ctx, "gather_chunk_kernel");

@@ -251,8 +251,11 @@ class EpochOracle:
 
     # ---- iterations ------------------------------------------------------------------------------------------------
     def run(self, n_iters):
+        """Runs the next n_iters GAS iterations (like the engine's run(): a second call continues where the first stopped)."""
         T, f = self.T, self.f
-        for it in range(n_iters):
+        start = getattr(self, "iters_done", 0)
+        self.iters_done = start + n_iters
+        for it in range(start, start + n_iters):
             ph = it % 6
             if ph == 0:  # ssk.h:695, 938: back to the first layer
                 for p in range(T):
