@@ -82,14 +82,19 @@ def csr_from_edges(torch, src, out_row, n_src, n_rows):
     return rowptr.int(), col
 
 
-def build_party_csr(torch, n_local, n_edges, n_parties, rank, seed, device):
+def build_party_csr(torch, n_local, n_edges, n_parties, rank, seed, device, own_first=False):
     """CSR-by-destination of the edges party `rank` owns.  Sources are its local vertices (row index 0..n_local),
-    destinations are global vertices grouped by owner: output row of global vertex v = (v % P) * n_local + v // P."""
+    destinations are global vertices grouped by owner: output row of global vertex v = (v % P) * n_local + v // P.
+    own_first: the owner blocks are rotated so that the party's own block comes first and the block of party rank + j is the
+    j-th (the order in which the fused step completes and signals them)."""
     n_global = n_local * n_parties
     src, dst = rmat_edges(torch, n_global, n_edges, seed + 1000 * rank, device)
     src = src % n_local  # the party's own vertices (local row index)
-    out_row = (dst % n_parties) * n_local + dst // n_parties
-    del dst
+    owner = dst % n_parties
+    if own_first:
+        owner = (owner - rank) % n_parties
+    out_row = owner * n_local + dst // n_parties
+    del dst, owner
     return csr_from_edges(torch, src, out_row, n_local, n_global)
 
 
@@ -124,13 +129,20 @@ class RawCuda:
 # ------------------------------------------------------------------------------------------------------------
 # N > 1: the pull exchange
 # ------------------------------------------------------------------------------------------------------------
-FLAG_BYTES = 4096  # ready[P] | ack[P] | err at the start of every rank's exported allocation
+FLAG_BYTES = 4096  # ready[P * S] | ack[P * S] | err at the start of every rank's exported allocation (P * S <= 256)
 
 
 def pull_orders(rank, P):
     """Producer order (destination of the j-th remote gather) and consumer order (source whose block is pulled j-th): the
     block for party rank+j is gathered j-th, so the block FROM party rank-j is that party's j-th too and arrives j-th."""
     return [(rank + j) % P for j in range(1, P)], [(rank - j) % P for j in range(1, P)]
+
+
+def sub_blocks(P):
+    """Row ranges each remote block is cut into (as fractions of the destination party's rows).  A pull can only start when its
+    block is complete, so with few parties the blocks are cut finer: the pull of one piece overlaps the gather of the next and
+    only the last piece's pull is exposed (2 parties: 4 pieces of the one remote block; 8 parties: the 7 blocks as they are)."""
+    return max(1, 8 // P)
 
 
 def exchange_index_lists(torch, dist, my_lists, rank, P):
@@ -156,68 +168,90 @@ def exchange_index_lists(torch, dist, my_lists, rank, P):
 def setup_pull(torch, dist, ctx, rowptr, col, rank, P, n_local, D, dev):
     import cognn_b200
 
-    csrs = []
-    for t in range(P):
-        lo, hi = t * n_local, (t + 1) * n_local
+    S = sub_blocks(P)
+    cuts = [n_local * u // S for u in range(S + 1)]
+
+    def sub_csr(lo, hi):
         e0, e1 = int(rowptr[lo]), int(rowptr[hi])
-        csrs.append(ctx.csr_create((rowptr[lo:hi + 1] - rowptr[lo]).int().contiguous(), col[e0:e1].contiguous(), n_local))
-    nz_mine = [csrs[t].nonempty_rows() for t in range(P)]
-    nz_from, sizes = exchange_index_lists(torch, dist, nz_mine, rank, P)  # the PosVec exchange of preprocessing
-    # one exported allocation per rank: flags, then two staging buffers (step parity) per remote destination
+        return ctx.csr_create((rowptr[lo:hi + 1] - rowptr[lo]).int().contiguous(), col[e0:e1].contiguous(), n_local)
+
+    own_csr = sub_csr(rank * n_local, (rank + 1) * n_local)
+    csrs = {(t, u): sub_csr(t * n_local + cuts[u], t * n_local + cuts[u + 1]) for t in range(P) if t != rank for u in range(S)}
+    # PosVec of preprocessing: per destination party the rows (of THAT party) that receive an edge from me, piece by piece
+    empty = torch.empty(0, dtype=torch.int32, device=dev)
+    nz_mine = [empty if t == rank else torch.cat([csrs[(t, u)].nonempty_rows() + cuts[u] for u in range(S)]) for t in range(P)]
+    counts_mine = [[0] * S if t == rank else [csrs[(t, u)].n_nonempty for u in range(S)] for t in range(P)]
+    nz_from, _ = exchange_index_lists(torch, dist, nz_mine, rank, P)
+    all_counts = [None] * P
+    dist.all_gather_object(all_counts, counts_mine)  # all_counts[s][t][u]: rows of piece u of the block s -> t
+    # one exported allocation per rank: flags, then two staging buffers (step parity) per remote piece
     offs, cur = {}, FLAG_BYTES
     for b in range(2):
-        for t in range(P):
-            if t != rank:
-                offs[(b, t)] = cur
-                cur += (csrs[t].n_nonempty * D * 8 + 255) & ~255
+        for (t, u), c in csrs.items():
+            offs[(b, t, u)] = cur
+            cur += (c.n_nonempty * D * 8 + 255) & ~255
     base = ctx.malloc(max(cur, FLAG_BYTES))
     ctx.check(ctx.lib.cgb_memset(ctx.handle, base, 0, FLAG_BYTES))
     ctx.sync()
     everyone = [None] * P
     dist.all_gather_object(everyone, (ctx.ipc_export(base), offs))
     peer_base = [base if s == rank else ctx.ipc_open(everyone[s][0]) for s in range(P)]
-    side = torch.cuda.Stream(device=dev)
+    side = torch.cuda.Stream(device=dev, priority=-1)  # pull CTAs are placed ahead of the queued gather CTAs
     with torch.cuda.stream(side):
         ctx_side = cognn_b200.Context(dev.index)
+    # per source s and piece u: the slice of nz_from[s] that belongs to the piece
+    nz_piece = {}
+    for s in range(P):
+        if s == rank:
+            continue
+        o = 0
+        for u in range(S):
+            n = all_counts[s][rank][u]
+            nz_piece[(s, u)] = (nz_from[s][o:o + n].contiguous(), n)
+            o += n
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    return {"csrs": csrs, "nz_from": nz_from, "sizes": sizes, "base": base, "offs": offs, "peer_base": peer_base,
+    return {"S": S, "own_csr": own_csr, "csrs": csrs, "nz_piece": nz_piece, "base": base, "offs": offs, "peer_base": peer_base,
             "peer_offs": [everyone[s][1] for s in range(P)], "side": side, "ctx_side": ctx_side, "step": 0,
             "wait_mode": 1 if os.environ.get("CGB_FLAG_WAIT", "memop") == "spin" else 0,
-            "t0": ev(), "own": ev(), "gat": [ev() for _ in range(P)], "add": [ev() for _ in range(P)], "end": ev(),
-            "err": torch.as_tensor(RawCuda(base + 8 * P, (1,), "<i4"), device=dev),
-            "bytes_out": sum(csrs[t].n_nonempty for t in range(P) if t != rank) * D * 8,
-            "rows_out": [csrs[t].n_nonempty for t in range(P)]}
+            "pull_ctas": int(os.environ.get("CGB_PULL_CTAS", "48")),
+            "t0": ev(), "own": ev(), "gat": {k: ev() for k in csrs}, "add": {k: ev() for k in nz_piece}, "end": ev(),
+            "err": torch.as_tensor(RawCuda(base + 8 * P * S, (1,), "<i4"), device=dev),
+            "bytes_out": sum(c.n_nonempty for c in csrs.values()) * D * 8,
+            "rows_out": {k: c.n_nonempty for k, c in csrs.items()}}
 
 
 def pull_step(torch, ctx, x, v, pl, rank, P, D):
-    """One step: own block gathered densely into v; every remote block gathered in compact form into a staging buffer its
-    consumer has mapped, flag raised in the consumer's memory; meanwhile the side stream waits for the other parties' flags in
-    arrival order and pulls + adds their blocks (cgb_scatter_add_rows over NVLink).  No collective, no dense block copy."""
+    """One step: own block gathered densely into v; every remote block gathered piece by piece in compact form into staging
+    buffers its consumer has mapped, a flag raised in the consumer's memory after each piece; meanwhile the side stream waits
+    for the other parties' flags in arrival order and pulls + adds their pieces (cgb_scatter_add_rows over NVLink).  No
+    collective, no dense block copy, nothing lands in local memory before it is added."""
     pl["step"] += 1
     i = pl["step"]
-    b = i & 1
+    b, S = i & 1, pl["S"]
     main, side, cs = torch.cuda.current_stream(), pl["side"], pl["ctx_side"]
     prod, cons = pull_orders(rank, P)
-    ready = lambda r, slot: pl["peer_base"][r] + 4 * slot          # noqa: E731  ready[slot] in rank r's memory
-    ack = lambda r, slot: pl["peer_base"][r] + 4 * (P + slot)      # noqa: E731
-    err = pl["base"] + 8 * P
+    ready = lambda r, src, u: pl["peer_base"][r] + 4 * (src * S + u)            # noqa: E731  ready[src, u] in rank r's memory
+    ack = lambda r, dst, u: pl["peer_base"][r] + 4 * (P * S + dst * S + u)      # noqa: E731  ack[dst, u] in rank r's memory
+    err = pl["base"] + 8 * P * S
     pl["t0"].record(main)
-    ctx.gather_sum(pl["csrs"][rank], x, None, out=v)  # every row of v is written (zeros where no local edge ends)
+    ctx.gather_sum(pl["own_csr"], x, None, out=v)  # every row of v is written (zeros where no local edge ends)
     pl["own"].record(main)
     side.wait_event(pl["own"])
     for t in prod:
-        if i > 2:  # the buffer of this parity was read by t two steps ago: its ack must have arrived
-            ctx.flag_wait(ack(rank, t), i - 2, pl["wait_mode"], err)
-        ctx.gather_sum_compact(pl["csrs"][t], x, out_ptr=pl["base"] + pl["offs"][(b, t)])
-        ctx.flag_signal(ready(t, rank), i)
-        pl["gat"][t].record(main)
+        for u in range(S):
+            if i > 2:  # the buffer of this parity was read by t two steps ago: its ack must have arrived
+                ctx.flag_wait(ack(rank, t, u), i - 2, pl["wait_mode"], err)
+            ctx.gather_sum_compact(pl["csrs"][(t, u)], x, out_ptr=pl["base"] + pl["offs"][(b, t, u)])
+            ctx.flag_signal(ready(t, rank, u), i)
+            pl["gat"][(t, u)].record(main)
     with torch.cuda.stream(side):
         for s in cons:
-            cs.flag_wait(ready(rank, s), i, pl["wait_mode"], err)
-            cs.scatter_add_rows(pl["nz_from"][s], pl["peer_base"][s] + pl["peer_offs"][s][(b, rank)], v,
-                                n=pl["sizes"][s][rank], D=D)
-            cs.flag_signal(ack(s, rank), i)
-            pl["add"][s].record(side)
+            for u in range(S):
+                idx, n = pl["nz_piece"][(s, u)]
+                cs.flag_wait(ready(rank, s, u), i, pl["wait_mode"], err)
+                cs.scatter_add_rows(idx, pl["peer_base"][s] + pl["peer_offs"][s][(b, rank, u)], v, n=n, D=D, n_ctas=pl["pull_ctas"])
+                cs.flag_signal(ack(s, rank, u), i)
+                pl["add"][(s, u)].record(side)
         pl["end"].record(side)
     main.wait_event(pl["end"])
     return v
@@ -225,13 +259,120 @@ def pull_step(torch, ctx, x, v, pl, rank, P, D):
 
 def pull_phases(pl, rank, P):
     """Timeline of the LAST step on this rank (ms after the step's start), read after a synchronize."""
-    t0 = pl["t0"]
+    t0, S = pl["t0"], pl["S"]
     prod, cons = pull_orders(rank, P)
     return {"own_gather_done": round(t0.elapsed_time(pl["own"]), 3),
-            "remote_gather_done": [round(t0.elapsed_time(pl["gat"][t]), 3) for t in prod],
-            "block_added": [round(t0.elapsed_time(pl["add"][s]), 3) for s in cons],
-            "step_done": round(t0.elapsed_time(pl["end"]), 3),
-            "rows_sent_per_block": [pl["rows_out"][t] for t in prod], "nvlink_bytes_out": pl["bytes_out"]}
+            "remote_gather_done": [round(t0.elapsed_time(pl["gat"][(t, u)]), 3) for t in prod for u in range(S)],
+            "piece_added": [round(t0.elapsed_time(pl["add"][(s, u)]), 3) for s in cons for u in range(S)],
+            "step_done": round(t0.elapsed_time(pl["end"]), 3), "pieces_per_block": S,
+            "rows_sent_per_piece": [pl["rows_out"][(t, u)] for t in prod for u in range(S)], "nvlink_bytes_out": pl["bytes_out"]}
+
+
+def setup_fused(torch, dist, ctx, rank, P, n_local, n_edges, D, dev, v):
+    """The fused step (cgb_gather_sum_signal): ONE CSR over all of the party's out-edges with the destination blocks in the order
+    [own | rank+1 | rank+2 | ...], remote blocks cut into sub_blocks(P) row pieces; every piece has a staging buffer (two step
+    parities) its consumer has mapped and a flag in the consumer's memory that the gather kernel itself raises."""
+    import cognn_b200
+
+    S = sub_blocks(P)
+    cuts = [n_local * u // S for u in range(S + 1)]
+    rowptr, col = build_party_csr(torch, n_local, n_edges, P, rank, 42, dev, own_first=True)
+    csr = ctx.csr_create(rowptr, col, n_local)
+    del rowptr, col
+    nz = csr.nonempty_rows().long()
+    prod, cons = pull_orders(rank, P)
+    offsets, pieces = [0], []          # pieces[i] = (dest party t, piece u) of block i + 1
+    for j, t in enumerate(prod, start=1):
+        for u in range(S):
+            offsets.append(j * n_local + cuts[u])
+            pieces.append((t, u))
+    offsets.append(P * n_local)        # block 0 = own rows [0, n_local), then the remote pieces in signalling order
+    bounds = torch.searchsorted(nz, torch.tensor(offsets, device=dev))
+    bl = bounds.tolist()
+    counts_mine = [[0] * S for _ in range(P)]
+    nz_mine = [torch.empty(0, dtype=torch.int32, device=dev) for _ in range(P)]
+    for i, (t, u) in enumerate(pieces, start=1):
+        counts_mine[t][u] = bl[i + 1] - bl[i]
+    for j, t in enumerate(prod, start=1):  # rows of party t (its local index) that receive an edge from me: my PosVec for t
+        lo, hi = bl[1 + (j - 1) * S], bl[1 + j * S]
+        nz_mine[t] = (nz[lo:hi] - j * n_local).int()
+    nz_from, _ = exchange_index_lists(torch, dist, nz_mine, rank, P)
+    all_counts = [None] * P
+    dist.all_gather_object(all_counts, counts_mine)
+    offs, cur = {}, FLAG_BYTES
+    for b in range(2):
+        for (t, u) in pieces:
+            offs[(b, t, u)] = cur
+            cur += (counts_mine[t][u] * D * 8 + 255) & ~255
+    base = ctx.malloc(max(cur, FLAG_BYTES))
+    ctx.check(ctx.lib.cgb_memset(ctx.handle, base, 0, FLAG_BYTES))
+    ctx.sync()
+    everyone = [None] * P
+    dist.all_gather_object(everyone, (ctx.ipc_export(base), offs))
+    peer_base = [base if s == rank else ctx.ipc_open(everyone[s][0]) for s in range(P)]
+    side = torch.cuda.Stream(device=dev, priority=-1)  # pull CTAs are placed ahead of the queued gather CTAs
+    with torch.cuda.stream(side):
+        ctx_side = cognn_b200.Context(dev.index)
+    nz_piece = {}
+    for s in cons:
+        o = 0
+        for u in range(S):
+            n = all_counts[s][rank][u]
+            nz_piece[(s, u)] = (nz_from[s][o:o + n].contiguous(), n)
+            o += n
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    return {"S": S, "csr": csr, "offsets": offsets, "pieces": pieces, "nz_piece": nz_piece, "base": base, "offs": offs,
+            "peer_base": peer_base, "peer_offs": [everyone[s][1] for s in range(P)], "side": side, "ctx_side": ctx_side, "step": 0,
+            "wait_mode": 1 if os.environ.get("CGB_FLAG_WAIT", "memop") == "spin" else 0,
+            "pull_ctas": int(os.environ.get("CGB_PULL_CTAS", "64")),
+            "t0": ev(), "launched": ev(), "add": {k: ev() for k in nz_piece}, "own_seen": ev(), "end": ev(),
+            "err": torch.as_tensor(RawCuda(base + 8 * P * S, (1,), "<i4"), device=dev),
+            "bytes_out": sum(counts_mine[t][u] for (t, u) in pieces) * D * 8,
+            "rows_out": {k: counts_mine[k[0]][k[1]] for k in pieces}}
+
+
+def fused_step(torch, ctx, x, v, fz, rank, P, D):
+    """One step = ONE gather launch.  The kernel stores the own block densely into v and every remote piece in compact form into
+    its staging buffer and raises each block's flag the moment that block is complete; the side stream (high priority) waits for
+    the own block's flag, then for the other parties' flags in arrival order, and pulls + adds their pieces over NVLink."""
+    fz["step"] += 1
+    i = fz["step"]
+    b, S = i & 1, fz["S"]
+    main, side, cs = torch.cuda.current_stream(), fz["side"], fz["ctx_side"]
+    _, cons = pull_orders(rank, P)
+    ready = lambda r, src, u: fz["peer_base"][r] + 4 * (src * S + u)            # noqa: E731  ready[src, u] in rank r's memory
+    ack = lambda r, dst, u: fz["peer_base"][r] + 4 * (P * S + dst * S + u)      # noqa: E731  ack[dst, u] in rank r's memory
+    err = fz["base"] + 8 * P * S
+    fz["t0"].record(main)
+    if i > 2:  # the staging buffers of this parity were read two steps ago: those acks must have arrived
+        for (t, u) in fz["pieces"]:
+            ctx.flag_wait(ack(rank, t, u), i - 2, fz["wait_mode"], err)
+    bases = [v.data_ptr()] + [fz["base"] + fz["offs"][(b, t, u)] for (t, u) in fz["pieces"]]
+    flags = [ready(rank, rank, 0)] + [ready(t, rank, u) for (t, u) in fz["pieces"]]
+    ctx.gather_sum_signal(fz["csr"], x, fz["offsets"], bases, [False] + [True] * len(fz["pieces"]), flags, i)
+    fz["launched"].record(main)
+    with torch.cuda.stream(side):
+        cs.flag_wait(ready(rank, rank, 0), i, fz["wait_mode"], err)  # own rows are in v: the additions may start
+        fz["own_seen"].record(side)
+        for s in cons:
+            for u in range(S):
+                idx, n = fz["nz_piece"][(s, u)]
+                cs.flag_wait(ready(rank, s, u), i, fz["wait_mode"], err)
+                cs.scatter_add_rows(idx, fz["peer_base"][s] + fz["peer_offs"][s][(b, rank, u)], v, n=n, D=D, n_ctas=fz["pull_ctas"])
+                cs.flag_signal(ack(s, rank, u), i)
+                fz["add"][(s, u)].record(side)
+        fz["end"].record(side)
+    main.wait_event(fz["end"])
+    return v
+
+
+def fused_phases(fz, rank, P):
+    t0, S = fz["t0"], fz["S"]
+    _, cons = pull_orders(rank, P)
+    return {"gather_kernel_done": round(t0.elapsed_time(fz["launched"]), 3), "own_block_flag_seen": round(t0.elapsed_time(fz["own_seen"]), 3),
+            "piece_added": [round(t0.elapsed_time(fz["add"][(s, u)]), 3) for s in cons for u in range(S)],
+            "step_done": round(t0.elapsed_time(fz["end"]), 3), "pieces_per_block": S,
+            "rows_sent_per_piece": [fz["rows_out"][k] for k in fz["pieces"]], "nvlink_bytes_out": fz["bytes_out"]}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -527,9 +668,10 @@ def main():
     ap.add_argument("--no-epoch", action="store_true", help="skip the secure-GCN epoch record")
     ap.add_argument("--no-matmul", action="store_true", help="skip the Beaver matmul record (N = 1 only)")
     ap.add_argument("--no-uniform", action="store_true", help="skip the uniform-graph control of the roofline (N = 1 only)")
-    ap.add_argument("--exchange", default="pull", choices=["pull", "nccl"],
-                    help="N > 1: pull = compact blocks, arrival flags, consumer pulls + adds over NVLink (default); "
-                         "nccl = dense gather then all_to_all + sums")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "pull", "nccl"],
+                    help="N > 1: fused = ONE gather launch that stores compact blocks and raises per-block flags in the consumers' "
+                         "memory, consumers pull + add over NVLink (default); pull = the same with one gather launch per block and "
+                         "stream-ordered flags; nccl = dense gather then all_to_all + sums")
     args = ap.parse_args()
 
     import torch
@@ -574,7 +716,7 @@ def main():
     g = torch.Generator(device=dev).manual_seed(43 + rank)
     x = torch.randint(-2**63, 2**63 - 1, (n_local, D), dtype=torch.int64, device=dev, generator=g)
     add = lambda a, b, o: ctx.add(a, b, out=o)  # noqa: E731
-    exchange_impl, exchange_check, pl = None, None, None
+    exchange_impl, exchange_check, pl, fz = None, None, None, None
     if P == 1:
         csr = ctx.csr_create(rowptr, col, n_local)
         y = torch.empty((n_local, D), dtype=torch.int64, device=dev)
@@ -588,40 +730,55 @@ def main():
         ctx.gather_sum(csr, x, None, out=y)
         want_v = exchange_and_sum(dist, y, recv, torch.empty_like(v), P, n_local, D, add).clone()
         exchange_impl = args.exchange
-        if exchange_impl == "pull":
+        if exchange_impl in ("pull", "fused"):
             del recv, y
             csr.destroy()
             csr = y = recv = None
             torch.cuda.empty_cache()
             try:  # peer windows need CUDA IPC between the ranks' processes
-                pl = setup_pull(torch, dist, ctx, rowptr, col, rank, P, n_local, D, dev)
+                if exchange_impl == "pull":
+                    pl = setup_pull(torch, dist, ctx, rowptr, col, rank, P, n_local, D, dev)
+                else:
+                    del rowptr, col
+                    torch.cuda.empty_cache()
+                    fz = setup_fused(torch, dist, ctx, rank, P, n_local, E, D, dev, v)
                 ok = torch.ones(1, dtype=torch.int32, device=dev)
             except Exception as ex:  # noqa: BLE001
                 sys.stderr.write(f"[bench] rank {rank}: peer memory unavailable ({ex}); falling back to --exchange nccl\n")
                 ok = torch.zeros(1, dtype=torch.int32, device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if int(ok.item()) == 0:
-                exchange_impl, pl = "nccl", None
+                exchange_impl, pl, fz = "nccl", None, None
+                rowptr, col = build_party_csr(torch, n_local, E, P, rank, 42, dev)
                 csr = ctx.csr_create(rowptr, col, n_local)
                 y = torch.empty((n_local * P, D), dtype=torch.int64, device=dev)
                 recv = torch.empty_like(y)
-        if exchange_impl == "pull":
+        if exchange_impl in ("pull", "fused"):
             good = 1
             for _ in range(3):  # both staging parities and the ack path
-                pull_step(torch, ctx, x, v, pl, rank, P, D)
+                if exchange_impl == "pull":
+                    pull_step(torch, ctx, x, v, pl, rank, P, D)
+                else:
+                    fused_step(torch, ctx, x, v, fz, rank, P, D)
                 torch.cuda.synchronize()
                 good &= int(torch.equal(v, want_v))
-            good &= int(int(pl["err"].item()) == 0)
+            good &= int(int((pl or fz)["err"].item()) == 0)
             t = torch.tensor([good], dtype=torch.int32, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
             exchange_check = {"against": "dense gather + NCCL all_to_all_single + block sums of the same inputs", "steps": 3,
                               "ok": bool(int(t.item()))}
-            assert exchange_check["ok"], "pull exchange differs from the gather + all-to-all + sum path"
+            assert exchange_check["ok"], "fused / pull exchange differs from the gather + all-to-all + sum path"
             dist.barrier()
         config["exchange_impl"] = {
-            "pull": "one gather per destination party; remote blocks in compact form (rows of destinations that have an edge, the "
-                    "PosVec both sides hold) into IPC-mapped staging, arrival flag raised in the consumer's memory; the consumer's "
-                    "side stream waits per block and pulls + adds it over NVLink (cgb_scatter_add_rows); no collective in the step",
+            "fused": "ONE gather launch per step over all out-edges (cgb_gather_sum_signal): own block stored densely, remote blocks "
+                     "(cut into max(1, 8 // parties) row pieces) in compact form (rows of destinations that have an edge, the PosVec "
+                     "both sides hold) into IPC-mapped staging; the kernel itself raises each piece's arrival flag in the consumer's "
+                     "memory when the piece is complete; the consumer's side stream waits per piece and pulls + adds it over NVLink "
+                     "(cgb_scatter_add_rows) while the producer is still gathering; no collective in the step",
+            "pull": "one gather per destination party (remote blocks cut into max(1, 8 // parties) row pieces); remote pieces in compact "
+                    "form (rows of destinations that have an edge, the PosVec both sides hold) into IPC-mapped staging, arrival flag "
+                    "raised in the consumer's memory; the consumer's side stream waits per piece and pulls + adds it over NVLink "
+                    "(cgb_scatter_add_rows); no collective in the step",
             "nccl": "dense gather, NCCL all_to_all_single of the N_p x D blocks, cgb_add sums"}[exchange_impl]
 
     step_no = [0]
@@ -632,6 +789,8 @@ def main():
             ctx.gather_sum(csr, x, None, out=y)
         elif exchange_impl == "pull":
             pull_step(torch, ctx, x, v, pl, rank, P, D)
+        elif exchange_impl == "fused":
+            fused_step(torch, ctx, x, v, fz, rank, P, D)
         else:
             ctx.gather_sum(csr, x, None, out=y)
             exchange_and_sum(dist, y, recv, v, P, n_local, D, add)
@@ -649,7 +808,7 @@ def main():
     sampler.start()
     time.sleep(0.25)
     barrier()
-    all_ctx = [ctx] + ([pl["ctx_side"]] if pl else [])
+    all_ctx = [ctx] + ([(pl or fz)["ctx_side"]] if (pl or fz) else [])
     launches0 = sum(c.launches for c in all_ctx)
     t_wall0 = time.time()
     torch.cuda.profiler.start()  # ncu --profile-from-start off captures exactly the timed region
@@ -669,6 +828,26 @@ def main():
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / K
     kernel_name = ctx.last_kernel
     phases = None
+    if fz is not None:
+        if int(fz["err"].item()) != 0:
+            raise RuntimeError("a flag wait timed out inside the timed region")
+        allp = [None] * P
+        dist.all_gather_object(allp, fused_phases(fz, rank, P))
+        phases = {"per_rank_last_step_timeline_ms": allp}
+        # the gather launch on its own (no flags, no pulls running beside it), for the roofline of the dominant kernel
+        scr = [torch.empty((max(1, fz["rows_out"][k]), D), dtype=torch.int64, device=dev) for k in fz["pieces"]]
+        bases = [v.data_ptr()] + [t.data_ptr() for t in scr]
+        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        ctx.gather_sum_signal(fz["csr"], x, fz["offsets"], bases, [False] + [True] * len(scr), [0] * len(bases), 0)
+        ka.record()
+        for _ in range(reps):
+            ctx.gather_sum_signal(fz["csr"], x, fz["offsets"], bases, [False] + [True] * len(scr), [0] * len(bases), 0)
+        kb.record()
+        torch.cuda.synchronize()
+        kernel_ms = ka.elapsed_time(kb) / reps
+        kernel_name = "gather_chunk_signal_kernel<VEC=4,LANES=4,U=4,128,1024,IPL=2> (256-bit row loads, per-block completion flags)"
+        del scr
     if pl is not None:
         if int(pl["err"].item()) != 0:
             raise RuntimeError("a flag wait timed out inside the timed region")
@@ -676,15 +855,14 @@ def main():
         dist.all_gather_object(allp, pull_phases(pl, rank, P))
         phases = {"per_rank_last_step_timeline_ms": allp}
         # the P gather launches of one step on their own (no waits, no pulls), for the roofline of the dominant kernel
-        scratch = torch.empty((max(pl["rows_out"]), D), dtype=torch.int64, device=dev)
+        scratch = torch.empty((max(pl["rows_out"].values()), D), dtype=torch.int64, device=dev)
         ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 3
         ka.record()
         for _ in range(reps):
-            ctx.gather_sum(pl["csrs"][rank], x, None, out=v)
-            for t in range(P):
-                if t != rank:
-                    ctx.gather_sum_compact(pl["csrs"][t], x, out=scratch[: pl["rows_out"][t]])
+            ctx.gather_sum(pl["own_csr"], x, None, out=v)
+            for k, c in pl["csrs"].items():
+                ctx.gather_sum_compact(c, x, out=scratch[: pl["rows_out"][k]])
         kb.record()
         torch.cuda.synchronize()
         kernel_ms = ka.elapsed_time(kb) / reps
@@ -697,11 +875,12 @@ def main():
     value = E * P / (ms_per_step * 1e-3)
 
     peak, peak_src = measured_peak_hbm()
-    n_out_rows = n_local if P == 1 else (n_local + sum(pl["rows_out"][t] for t in range(P) if t != rank) if pl else n_local * P)
+    n_out_rows = n_local if P == 1 else (n_local + sum((pl or fz)["rows_out"].values()) if (pl or fz) else n_local * P)
+    n_launch = 1 + len(pl["csrs"]) if pl else 1
     alg = algorithmic_bytes(n_out_rows, E, D)
     achieved = alg / (kernel_ms * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic(E, D, P)
-    roofline = {"bound": "hbm", "kernel": kernel_name + (f" x {P} launches per step" if P > 1 else ""),
+    roofline = {"bound": "hbm", "kernel": kernel_name + (f" x {n_launch} launches per step" if n_launch > 1 else ""),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": kernel_ms,
                 "frac_of_8TBs_nominal": achieved / 8000.0,

@@ -125,6 +125,18 @@ class Context:
                                                    C.c_void_p(int(out_ptr)), D))
         return out
 
+    def gather_sum_signal(self, csr, x, offsets, bases, compact, flags, value):
+        """One launch; block b = rows [offsets[b], offsets[b+1]) -> bases[b] (raw address; dense or compact[b]), flags[b] (raw
+        address or 0) raised with `value` when the block is complete."""
+        n = len(bases)
+        D = x.shape[1]
+        offs = (C.c_uint32 * (n + 1))(*[int(o) for o in offsets])
+        bs = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in bases])
+        cm = (C.c_uint8 * n)(*[1 if c else 0 for c in compact])
+        fl = (C.c_void_p * n)(*[C.c_void_p(int(f)) if f else None for f in flags])
+        self.check(self.lib.cgb_gather_sum_signal(self.handle, csr.handle, _ptr(self._u64(x)), D, n, offs, bs, cm, fl,
+                                                  int(value) & 0xFFFFFFFF))
+
     def scatter_add_rows(self, idx, src, v, assign=False, n=None, D=None, n_ctas=0):
         """v[idx[k], :] (+)= src[k, :].  `src` may be a raw device address (int; e.g. a peer's staging buffer) with n given."""
         D = v.shape[1] if D is None else D

@@ -50,6 +50,8 @@ SIGNATURES = {
     "cgb_gather_sum": (C.c_int, [ctx_p, csr_p, u64p, u64p, u64p, C.c_uint32]),
     "cgb_gather_sum_blocks": (C.c_int, [ctx_p, csr_p, u64p, u64p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "cgb_gather_sum_compact": (C.c_int, [ctx_p, csr_p, u64p, u64p, u64p, C.c_uint32]),
+    "cgb_gather_sum_signal": (C.c_int, [ctx_p, csr_p, u64p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_uint32]),
     "cgb_csr_num_nonempty_rows": (C.c_uint32, [csr_p]),
     "cgb_csr_nonempty_rows": (C.c_void_p, [csr_p]),
     "cgb_scatter_add_rows": (C.c_int, [ctx_p, u32p, C.c_uint64, u64p, u64p, C.c_uint32, C.c_int, C.c_uint32]),

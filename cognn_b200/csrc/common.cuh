@@ -70,6 +70,8 @@ struct cgb_csr {
     uint64_t* d_piece = nullptr;        // 2 * n_chunks x D: [head pieces | tail pieces] (grow-only)
     size_t piece_words = 0;
     std::vector<void*> retired;         // outgrown scratch buffers, freed with the handle (graphs may still reference them)
+    std::vector<uint32_t> h_nz_row;     // host copy of d_nz_row (block bookkeeping of cgb_gather_sum_signal)
+    uint32_t* d_sig_done = nullptr;     // per-block completion counters of cgb_gather_sum_signal (self-resetting)
 };
 // edges per chunk of the edge-balanced schedule = 1 << chunk_shift, chosen per CSR when it is built: 64 keeps small graphs
 // (one wave of groups or less) short, 128 halves the per-chunk prologues and boundary pieces of big ones (100M edges,

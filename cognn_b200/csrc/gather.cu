@@ -238,12 +238,43 @@ __device__ __forceinline__ u64* out_row(const ChunkArgs& a, uint32_t row) {
     return a.blk_base[t] + (size_t)(row - a.blk_off[t]) * a.D;
 }
 
+// ---- signalling mode (cgb_gather_sum_signal) ---------------------------------------------------------------------------
+// The output rows are cut into up to CGB_MAX_SIG contiguous blocks (mirror-update blocks for the other parties, or pieces of
+// them, and the party's own block).  Each block has its own destination buffer, dense (row - first row of the block) or compact
+// (position among the block's non-empty rows), and a FLAG: every CTA counts the rows it completes per block, and the CTA
+// that brings a block's count to its total raises the flag (st.release.sys, usually into the CONSUMER's memory over NVLink)
+// while the rest of the grid is still gathering the later blocks.  The transfer of block t (the consumer pulls it as soon
+// as it sees the flag) therefore overlaps the gather of blocks t+1.. inside ONE launch.
+#define CGB_MAX_SIG 32
+struct SigArgs {
+    uint32_t n_sig;
+    uint32_t compact_mask;            // bit b: block b is stored in compact form
+    uint32_t off[CGB_MAX_SIG + 1];    // first row of each block (ascending), off[n_sig] = n_rows
+    uint32_t k0[CGB_MAX_SIG];         // number of non-empty rows before the block
+    uint32_t total[CGB_MAX_SIG];      // (row, column tile) stores that complete the block
+    u64* base[CGB_MAX_SIG];
+    uint32_t* flag[CGB_MAX_SIG];      // may be null (no signal), may be peer memory
+    uint32_t* done;                   // CGB_MAX_SIG device counters, self-resetting
+    uint32_t value;
+};
+
+__device__ __forceinline__ uint32_t sig_block_of(const SigArgs& g, uint32_t row, uint32_t b) {
+#pragma unroll 1
+    while (b + 1 < g.n_sig && row >= g.off[b + 1]) ++b;
+    return b;
+}
+__device__ __forceinline__ u64* sig_row_ptr(const SigArgs& g, uint32_t b, uint32_t row, uint32_t k, uint32_t D) {
+    const uint32_t idx = ((g.compact_mask >> b) & 1u) ? (k - g.k0[b]) : (row - g.off[b]);
+    return g.base[b] + (size_t)idx * D;
+}
+
 // A row segment cut by a chunk boundary has been stored as a "piece"; count the arrival and, if this was the last
-// piece of the row, fold them.  `k` is the row's index in nz_row (its output row in compact mode).
-template <int VEC, int LANES, bool COMPACT = false>
-__device__ __forceinline__ void piece_arrive_body(const ChunkArgs& a, uint32_t k, uint32_t ct, uint32_t col0, bool active,
-                                                  int lane, unsigned mask) {
-    const uint32_t row = __ldg(a.nz_row + k);
+// piece of the row, fold them.  `orow` is the row's output index (the row itself, or its position among the non-empty rows in
+// compact mode).
+template <int VEC, int LANES, int MODE = 0>
+__device__ __forceinline__ void piece_arrive_body(const ChunkArgs& a, uint32_t row, uint32_t orow, uint32_t ct, uint32_t col0,
+                                                  bool active, int lane, unsigned mask, const SigArgs* g = nullptr,
+                                                  uint32_t* s_cnt = nullptr) {
     __threadfence();
     __syncwarp(mask);
     const uint32_t rb = __ldg(a.rowptr + row), re = __ldg(a.rowptr + row + 1);
@@ -255,7 +286,6 @@ __device__ __forceinline__ void piece_arrive_body(const ChunkArgs& a, uint32_t k
     if (prev == c2 - c1) {  // last of the c2 - c1 + 1 pieces
         __threadfence();
         if (active) {
-            const uint32_t orow = COMPACT ? k : row;
             const size_t o = (size_t)orow * a.D + col0;
             Acc<VEC> sum;
             sum.zero();
@@ -267,7 +297,15 @@ __device__ __forceinline__ void piece_arrive_body(const ChunkArgs& a, uint32_t k
                 p.load_cg(a.piece_head + (size_t)cc * a.D + col0);
                 sum.add(p);
             }
-            sum.store_cs(out_row(a, orow) + col0);
+            if constexpr (MODE == 2) {  // orow carries the row's index among the non-empty rows
+                const uint32_t b = sig_block_of(*g, row, 0);
+                sum.store_cs(sig_row_ptr(*g, b, row, orow, a.D) + col0);
+            } else {
+                sum.store_cs(out_row(a, orow) + col0);
+            }
+        }
+        if constexpr (MODE == 2) {
+            if (lane == 0) atomicAdd(&s_cnt[sig_block_of(*g, row, 0)], 1u);
         }
         if (lane == 0) *ctr = 0;  // ready for the next launch
     }
@@ -275,17 +313,18 @@ __device__ __forceinline__ void piece_arrive_body(const ChunkArgs& a, uint32_t k
 
 // out-of-line form for the cp.async variant (kept for A/B runs)
 template <int VEC, int LANES>
-__device__ __noinline__ void piece_arrive(const ChunkArgs& a, uint32_t k, uint32_t ct, uint32_t col0, bool active, int lane,
+__device__ __noinline__ void piece_arrive(const ChunkArgs& a, uint32_t row, uint32_t ct, uint32_t col0, bool active, int lane,
                                           unsigned mask) {
-    piece_arrive_body<VEC, LANES>(a, k, ct, col0, active, lane, mask);
+    piece_arrive_body<VEC, LANES>(a, row, row, ct, col0, active, lane, mask);
 }
 
 // IPL: column indices each lane holds per batch (a batch is LANES * IPL edges; narrow 256-bit groups of 2 or 4 lanes keep
 // 8 edges per batch this way, so U can stay above the lane count)
 //
-template <int VEC, int LANES, int U, int BLOCK, int OCC_THREADS, int IPL = 1, bool COMPACT = false>
-__global__ void __launch_bounds__(BLOCK, OCC_THREADS / BLOCK)
-gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
+// MODE 0: rows stored at their index (or into the blk_* windows); 1: compact (COMPACT); 2: signalling blocks (SigArgs)
+template <int VEC, int LANES, int U, int BLOCK, int IPL, int MODE>
+__device__ __forceinline__ void gather_chunk_body(const ChunkArgs& a, const SigArgs* g, uint32_t* s_cnt) {
+    constexpr bool COMPACT = MODE == 1;
     constexpr int BATCH = LANES * IPL;
     constexpr int GROUPS = BLOCK / LANES;
     const int lane = threadIdx.x & (LANES - 1);
@@ -299,8 +338,20 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
     const bool active = col0 < a.D;
 
     if (item >= a.n_chunks) {  // a row without edges: y = delta (or 0)
+        const uint32_t row = __ldg(a.empty_row + (item - a.n_chunks));
+        if constexpr (MODE == 2) {  // dense blocks get their zero rows (and count them); compact blocks have no such row
+            const uint32_t b = sig_block_of(*g, row, 0);
+            if (!((g->compact_mask >> b) & 1u)) {
+                if (active) {
+                    Acc<VEC> v;
+                    v.zero();
+                    v.store_cs(sig_row_ptr(*g, b, row, 0, a.D) + col0);
+                }
+                if (lane == 0) atomicAdd(&s_cnt[b], 1u);
+            }
+            return;
+        }
         if (active) {
-            const uint32_t row = __ldg(a.empty_row + (item - a.n_chunks));
             const size_t o = (size_t)row * a.D + col0;
             Acc<VEC> v;
             v.zero();
@@ -316,7 +367,8 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
     uint32_t k = cn & ~CGB_END_FLAG;
     bool head_open = (cn & CGB_END_FLAG) != 0;
     bool open = false, have_head = false;
-    uint32_t head_k = 0;
+    uint32_t head_row = 0, head_k = 0;
+    uint32_t sb = 0;  // MODE 2: block of the last row stored (rows ascend inside a chunk)
     Acc<VEC> acc;
     acc.zero();
     uint32_t my[IPL], nxt[IPL];
@@ -350,9 +402,14 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
                         acc.add(v[u]);
                         open = true;
                         if (id[u] & CGB_END_FLAG) {
+                            const uint32_t row = __ldg(a.nz_row + k);
                             if (!head_open) {  // the row lies inside this chunk: store it
-                                if (active) {
-                                    const uint32_t orow = COMPACT ? k : __ldg(a.nz_row + k);
+                                if constexpr (MODE == 2) {
+                                    sb = sig_block_of(*g, row, sb);
+                                    if (active) acc.store_cs(sig_row_ptr(*g, sb, row, k, a.D) + col0);
+                                    if (lane == 0) atomicAdd(&s_cnt[sb], 1u);
+                                } else if (active) {
+                                    const uint32_t orow = COMPACT ? k : row;
                                     const size_t o = (size_t)orow * a.D + col0;
                                     if (a.delta) {
                                         Acc<VEC> d;
@@ -363,7 +420,8 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
                                 }
                             } else {  // end of a row that began in an earlier chunk: leave a head piece (arrival counted below)
                                 if (active) acc.store(a.piece_head + (size_t)c * a.D + col0);
-                                head_k = k;
+                                head_row = row;
+                                if constexpr (MODE != 0) head_k = k;
                                 have_head = true;
                             }
                             acc.zero();
@@ -391,10 +449,44 @@ gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
     // Piece arrivals after the edge loop, always INLINED (two copies): round 1 found that with the fold out of line (a call)
     // the IPL = 2 instantiation returned wrong columns 1..3 for rows cut by a chunk boundary -- the accumulator is live across
     // the first call.  No instantiation of this kernel calls out of line any more.
-    if (have_head) piece_arrive_body<VEC, LANES, COMPACT>(a, head_k, ct, col0, active, lane, mask);
+    if (have_head) piece_arrive_body<VEC, LANES, MODE>(a, head_row, MODE != 0 ? head_k : head_row, ct, col0, active, lane, mask, g, s_cnt);
     if (open) {  // the chunk ends inside a row
         if (active) acc.store((head_open ? a.piece_head : a.piece_tail) + (size_t)c * a.D + col0);
-        piece_arrive_body<VEC, LANES, COMPACT>(a, k, ct, col0, active, lane, mask);
+        const uint32_t row = __ldg(a.nz_row + k);
+        piece_arrive_body<VEC, LANES, MODE>(a, row, MODE != 0 ? k : row, ct, col0, active, lane, mask, g, s_cnt);
+    }
+}
+
+template <int VEC, int LANES, int U, int BLOCK, int OCC_THREADS, int IPL = 1, bool COMPACT = false>
+__global__ void __launch_bounds__(BLOCK, OCC_THREADS / BLOCK)
+gather_chunk_kernel(const __grid_constant__ ChunkArgs a) {
+    gather_chunk_body<VEC, LANES, U, BLOCK, IPL, COMPACT ? 1 : 0>(a, nullptr, nullptr);
+}
+
+// The fused compute + signalling form: the same edge loop, then every CTA adds its per-block row counts to the global counters
+// and the one that completes a block raises that block's flag.
+template <int VEC, int LANES, int U, int BLOCK, int OCC_THREADS, int IPL = 1>
+__global__ void __launch_bounds__(BLOCK, OCC_THREADS / BLOCK)
+gather_chunk_signal_kernel(const __grid_constant__ ChunkArgs a, const __grid_constant__ SigArgs g) {
+    __shared__ uint32_t s_cnt[CGB_MAX_SIG];
+    if (threadIdx.x < CGB_MAX_SIG) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    gather_chunk_body<VEC, LANES, U, BLOCK, IPL, 2>(a, &g, s_cnt);
+    __threadfence();  // this thread's rows are visible device-wide before its CTA reports them
+    __syncthreads();
+    if (threadIdx.x < g.n_sig) {
+        const uint32_t b = threadIdx.x, cnt = s_cnt[b];
+        if (cnt) {
+            __threadfence();
+            const uint32_t prev = atomicAdd(g.done + b, cnt);
+            if (prev + cnt == g.total[b]) {  // this CTA completed block b
+                atomicExch(g.done + b, 0u);  // ready for the next launch
+                if (g.flag[b]) {
+                    __threadfence_system();
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(g.flag[b]), "r"(g.value) : "memory");
+                }
+            }
+        }
     }
 }
 
@@ -493,7 +585,7 @@ __global__ void __launch_bounds__(BLOCK) gather_chunk_async_kernel(const __grid_
                         }
                     } else {
                         if (active) acc.store(a.piece_head + (size_t)c * a.D + col0);
-                        head_row = k;
+                        head_row = row;
                         have_head = true;
                     }
                     acc.zero();
@@ -554,7 +646,7 @@ __global__ void __launch_bounds__(BLOCK) gather_chunk_async_kernel(const __grid_
     if (have_head) piece_arrive<VEC, LANES>(a, head_row, ct, col0, active, lane, mask);
     if (open) {  // the chunk ends inside a row
         if (active) acc.store((head_open ? a.piece_head : a.piece_tail) + (size_t)c * a.D + col0);
-        piece_arrive<VEC, LANES>(a, k, ct, col0, active, lane, mask);
+        piece_arrive<VEC, LANES>(a, __ldg(a.nz_row + k), ct, col0, active, lane, mask);
     }
 }
 
@@ -730,6 +822,7 @@ int build_chunks(cgb_ctx* ctx, cgb_csr* c, const uint32_t* h_rowptr) {
     };
     int rc;
     if ((rc = upload(&c->d_nz_row, nz))) return rc;
+    c->h_nz_row = nz;
     if ((rc = upload(&c->d_empty_row, empty))) return rc;
     if ((rc = upload(&c->d_chunk_nz, chunk_nz))) return rc;
     if (c->n_edges) {
@@ -823,7 +916,7 @@ int cgb_csr_destroy(cgb_ctx* ctx, cgb_csr* c) {
     cudaFree(c->d_slice_row); cudaFree(c->d_slice_begin); cudaFree(c->d_slice_first);
     cudaFree(c->d_slice_count); cudaFree(c->d_long_id); cudaFree(c->d_counters); cudaFree(c->d_partial);
     cudaFree(c->d_colf); cudaFree(c->d_nz_row); cudaFree(c->d_empty_row); cudaFree(c->d_chunk_nz);
-    cudaFree(c->d_chunk_ctr); cudaFree(c->d_piece);
+    cudaFree(c->d_chunk_ctr); cudaFree(c->d_piece); cudaFree(c->d_sig_done);
     for (void* p : c->retired) cudaFree(p);
     delete c;
     return CGB_OK;
@@ -834,19 +927,24 @@ const uint32_t* cgb_csr_rowptr(const cgb_csr* c) { return c ? c->d_rowptr : null
 const uint32_t* cgb_csr_col(const cgb_csr* c) { return c ? c->d_col : nullptr; }
 
 static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, const uint64_t* d_delta, uint64_t* d_y,
-                       uint32_t D, int n_blk, uint64_t* const* blk_base, const uint32_t* blk_off, bool compact = false) {
+                       uint32_t D, int n_blk, uint64_t* const* blk_base, const uint32_t* blk_off, bool compact = false,
+                       const SigArgs* sig = nullptr) {
     cgb_csr* csr = const_cast<cgb_csr*>(csr_c);
-    CGB_REQUIRE(ctx, csr && d_x && (d_y || n_blk > 0) && D > 0, "cgb_gather_sum: null argument");
+    CGB_REQUIRE(ctx, csr && d_x && (d_y || n_blk > 0 || sig) && D > 0, "cgb_gather_sum: null argument");
     CGB_REQUIRE(ctx, (const void*)d_x != (const void*)d_y, "cgb_gather_sum: y must not alias x");
     if (csr->n_rows == 0) return CGB_OK;
     bool al = is_aligned16(d_x) && is_aligned16(d_delta) && is_aligned16(d_y);
     for (int t = 0; t < n_blk; ++t) al = al && is_aligned16(blk_base[t]);
+    if (sig)
+        for (uint32_t t = 0; t < sig->n_sig; ++t) al = al && is_aligned16(sig->base[t]);
     Shape s = pick_shape(D, al);
     // CGB_GATHER_VEC=4|2: 256-bit accesses when the shape allows (D % 4 == 0, 32-byte aligned bases), else 128 / 64 bit
     static const int want_vec = getenv("CGB_GATHER_VEC") ? atoi(getenv("CGB_GATHER_VEC")) : CGB_GATHER_DEFAULT_VEC;
     static const bool async_impl = getenv("CGB_GATHER_IMPL") && std::string(getenv("CGB_GATHER_IMPL")) == "async";
     bool al32 = is_aligned32(d_x) && is_aligned32(d_delta) && is_aligned32(d_y);
     for (int t = 0; t < n_blk; ++t) al32 = al32 && is_aligned32(blk_base[t]);
+    if (sig)
+        for (uint32_t t = 0; t < sig->n_sig; ++t) al32 = al32 && is_aligned32(sig->base[t]);
     const bool vec4 = want_vec == 4 && D % 4 == 0 && al32 && !use_row_schedule() && !async_impl;
     if (vec4) s = pick_shape4(D);
     CGB_REQUIRE(ctx, n_blk == 0 || !use_row_schedule(), "cgb_gather_sum_blocks: needs the edge-balanced schedule");
@@ -897,8 +995,13 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
         // staged variant (CGB_GATHER_NBUF=2|3); CGB_GATHER_VEC=2 -> 128-bit kernels; CGB_GATHER_IPL=1 -> one index word per lane
         static const bool use_async = getenv("CGB_GATHER_IMPL") && std::string(getenv("CGB_GATHER_IMPL")) == "async";
         static const int nbuf = getenv("CGB_GATHER_NBUF") ? atoi(getenv("CGB_GATHER_NBUF")) : 2;
+        SigArgs g;
+        if (sig) {
+            g = *sig;
+            for (uint32_t t = 0; t < g.n_sig; ++t) g.total[t] *= s.n_ct;  // one store per (row, column tile)
+        }
         if (use_async) {
-            CGB_REQUIRE(ctx, !compact, "cgb_gather_sum_compact: not available with CGB_GATHER_IMPL=async");
+            CGB_REQUIRE(ctx, !compact && !sig, "cgb_gather_sum_compact / _signal: not available with CGB_GATHER_IMPL=async");
             int rc = dispatch_shape(s, [&](auto V, auto L, auto U_) {
                 constexpr int BLOCK = 128;
                 constexpr int VV = decltype(V)::value, LL = decltype(L)::value, UU = decltype(U_)::value;
@@ -933,12 +1036,14 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
                 if (LL <= 4 && ipl == 2) {  // 8 (LANES = 4) or 4 (LANES = 2) edges per batch, 4 row loads in flight per lane
                     constexpr int B2 = LL * 2;
                     constexpr int U4 = B2 >= 4 ? 4 : B2;
-                    if (compact) gather_chunk_kernel<VV, LL, U4, BLOCK, 1024, 2, true><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                    if (sig) gather_chunk_signal_kernel<VV, LL, U4, BLOCK, 1024, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a, g);
+                    else if (compact) gather_chunk_kernel<VV, LL, U4, BLOCK, 1024, 2, true><<<blocks, BLOCK, 0, ctx->stream>>>(a);
                     else gather_chunk_kernel<VV, LL, U4, BLOCK, 1024, 2><<<blocks, BLOCK, 0, ctx->stream>>>(a);
                     ctx->last_kernel = LL == 4 ? "gather_chunk_kernel<VEC=4,LANES=4,U=4,128,1024,IPL=2> (256-bit row loads)"
                                                : "gather_chunk_kernel<VEC=4,LANES=2,U=4,128,1024,IPL=2> (256-bit row loads)";
                 } else {
-                    if (compact) gather_chunk_kernel<VV, LL, UH, BLOCK, 1024, 1, true><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+                    if (sig) gather_chunk_signal_kernel<VV, LL, UH, BLOCK, 1024, 1><<<blocks, BLOCK, 0, ctx->stream>>>(a, g);
+                    else if (compact) gather_chunk_kernel<VV, LL, UH, BLOCK, 1024, 1, true><<<blocks, BLOCK, 0, ctx->stream>>>(a);
                     else gather_chunk_kernel<VV, LL, UH, BLOCK, 1024><<<blocks, BLOCK, 0, ctx->stream>>>(a);
                     ctx->last_kernel = "gather_chunk_kernel<VEC=4,LANES>=8,U=4,128,1024,IPL=1> (256-bit row loads)";
                 }
@@ -954,7 +1059,8 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
             constexpr int UU = decltype(U_)::value;
             constexpr int UH = UU >= 8 ? 4 : UU;
             const unsigned blocks = (unsigned)((total + GROUPS - 1) / GROUPS);
-            if (compact) gather_chunk_kernel<VV, LL, UH, BLOCK, 1536, 1, true><<<blocks, BLOCK, 0, ctx->stream>>>(a);
+            if (sig) gather_chunk_signal_kernel<VV, LL, UH, BLOCK, 1536, 1><<<blocks, BLOCK, 0, ctx->stream>>>(a, g);
+            else if (compact) gather_chunk_kernel<VV, LL, UH, BLOCK, 1536, 1, true><<<blocks, BLOCK, 0, ctx->stream>>>(a);
             else gather_chunk_kernel<VV, LL, UH, BLOCK, 1536><<<blocks, BLOCK, 0, ctx->stream>>>(a);
         });
         CGB_REQUIRE(ctx, rc == 0, "cgb_gather_sum: no kernel for this shape");
@@ -962,7 +1068,7 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
         ctx->last_kernel = "gather_chunk_kernel<VEC<=2,...,128,1536,IPL=1> (128-/64-bit row loads)";
         return CGB_OK;
     }
-    CGB_REQUIRE(ctx, !compact, "cgb_gather_sum_compact: needs the edge-balanced schedule");
+    CGB_REQUIRE(ctx, !compact && !sig, "cgb_gather_sum_compact / _signal: need the edge-balanced schedule");
     if (csr->n_slices) {
         size_t need = (size_t)csr->n_slices * D;
         if (need > csr->partial_words || !is_aligned16(csr->d_partial)) {
@@ -1020,6 +1126,47 @@ int cgb_gather_sum_compact(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x
     CGB_REQUIRE(ctx, csr, "cgb_gather_sum_compact: null argument");
     if (csr->n_nz == 0) return CGB_OK;
     return gather_impl(ctx, csr, d_x, d_delta, d_y, D, 0, nullptr, nullptr, true);
+}
+int cgb_gather_sum_signal(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, uint32_t D, uint32_t n_blocks,
+                          const uint32_t* block_row_offsets, uint64_t* const* d_block_base, const uint8_t* block_compact,
+                          uint32_t* const* d_block_flag, uint32_t flag_value) {
+    cgb_csr* csr = const_cast<cgb_csr*>(csr_c);
+    CGB_REQUIRE(ctx, csr && d_x && block_row_offsets && d_block_base && block_compact, "cgb_gather_sum_signal: null argument");
+    CGB_REQUIRE(ctx, n_blocks >= 1 && n_blocks <= CGB_MAX_SIG, "cgb_gather_sum_signal: 1..32 blocks");
+    CGB_REQUIRE(ctx, block_row_offsets[0] == 0 && block_row_offsets[n_blocks] == csr->n_rows,
+                "cgb_gather_sum_signal: offsets must span the rows");
+    if (csr->n_rows == 0) return CGB_OK;
+    if (!csr->d_sig_done) {
+        CGB_CHECK_CUDA(ctx, cudaMalloc((void**)&csr->d_sig_done, CGB_MAX_SIG * sizeof(uint32_t)));
+        CGB_CHECK_CUDA(ctx, cudaMemsetAsync(csr->d_sig_done, 0, CGB_MAX_SIG * sizeof(uint32_t), ctx->stream));
+    }
+    SigArgs g;
+    memset(&g, 0, sizeof(g));
+    g.n_sig = n_blocks;
+    g.done = csr->d_sig_done;
+    g.value = flag_value;
+    const std::vector<uint32_t>& nz = csr->h_nz_row;
+    for (uint32_t b = 0; b <= n_blocks; ++b) {
+        CGB_REQUIRE(ctx, b == 0 || block_row_offsets[b] >= block_row_offsets[b - 1], "cgb_gather_sum_signal: offsets must ascend");
+        g.off[b] = block_row_offsets[b];
+    }
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        const uint32_t k_lo = (uint32_t)(std::lower_bound(nz.begin(), nz.end(), g.off[b]) - nz.begin());
+        const uint32_t k_hi = (uint32_t)(std::lower_bound(nz.begin(), nz.end(), g.off[b + 1]) - nz.begin());
+        g.k0[b] = k_lo;
+        if (block_compact[b]) g.compact_mask |= 1u << b;
+        g.total[b] = block_compact[b] ? (k_hi - k_lo) : (g.off[b + 1] - g.off[b]);
+        g.base[b] = (u64*)d_block_base[b];
+        g.flag[b] = d_block_flag ? d_block_flag[b] : nullptr;
+        CGB_REQUIRE(ctx, g.base[b] || g.total[b] == 0, "cgb_gather_sum_signal: null block buffer");
+    }
+    // a block without any row to store completes trivially: raise its flag from the stream
+    for (uint32_t b = 0; b < n_blocks; ++b)
+        if (g.total[b] == 0 && g.flag[b]) {
+            int rc = cgb_flag_signal(ctx, g.flag[b], flag_value);
+            if (rc) return rc;
+        }
+    return gather_impl(ctx, csr, d_x, nullptr, nullptr, D, 0, nullptr, nullptr, false, &g);
 }
 uint32_t cgb_csr_num_nonempty_rows(const cgb_csr* c) { return c ? c->n_nz : 0; }
 const uint32_t* cgb_csr_nonempty_rows(const cgb_csr* c) { return c ? c->d_nz_row : nullptr; }

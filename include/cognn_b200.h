@@ -122,6 +122,19 @@ int cgb_gather_sum_blocks(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x,
  * The consumer adds the block with cgb_scatter_add_rows. */
 int cgb_gather_sum_compact(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x, const uint64_t* d_delta, uint64_t* d_y,
                            uint32_t D);
+/* The fused gather + exchange step: ONE launch over all of the party's out-edges whose output rows are cut into n_blocks
+ * contiguous blocks (block b = rows [offsets[b], offsets[b+1]); the party's own block and the mirror-update blocks for the other
+ * parties, or row pieces of them).  Block b is stored at d_block_base[b] -- densely (row - offsets[b]) or, if
+ * block_compact[b], in the compact form of cgb_gather_sum_compact (position among the block's non-empty rows) -- and the moment
+ * its last row has been stored, while the grid is still gathering the later blocks, the kernel raises d_block_flag[b]
+ * (value flag_value, st.release.sys; the flag is usually in the CONSUMER's memory, mapped with cgb_ipc_open; NULL = no signal).
+ * The consumer waits with cgb_flag_wait and pulls the block with cgb_scatter_add_rows, so the NVLink transfer of block b
+ * overlaps the gather of blocks b+1... inside one kernel; this replaces the blocking sendShareVecVec / recvShareVecVec pairs of
+ * ssk.h:1090-1100.  All arrays are HOST arrays (n_blocks <= 32).  Buffers of compact blocks hold
+ * (number of non-empty rows of the block) x D words. */
+int cgb_gather_sum_signal(cgb_ctx* ctx, const cgb_csr* csr, const uint64_t* d_x, uint32_t D, uint32_t n_blocks,
+                          const uint32_t* block_row_offsets, uint64_t* const* d_block_base, const uint8_t* block_compact,
+                          uint32_t* const* d_block_flag, uint32_t flag_value);
 uint32_t cgb_csr_num_nonempty_rows(const cgb_csr* csr);
 const uint32_t* cgb_csr_nonempty_rows(const cgb_csr* csr); /* device pointer, ascending row ids */
 /* v[idx[k], :] (+)= src[k, :] for k < n: the GatherComp addition (gcn.h:456-463) of one received compact block.  d_src may

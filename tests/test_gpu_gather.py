@@ -356,3 +356,52 @@ def test_flags_signal_then_wait(cgb, mode):
         cgb.flag_wait(flag.data_ptr() + 4, 1, 1, err.data_ptr())
         torch.cuda.synchronize()
         assert int(err[0]) == 1 and time.time() - t0 < 30.0
+
+
+@pytest.mark.parametrize("D", [2, 16, 40, 64])
+def test_gather_sum_signal_blocks_and_flags(cgb, oracle, D):
+    """The fused gather + signalling launch: rows cut into dense and compact blocks (an empty block and an all-empty-rows block
+    included), every block in its own buffer, every flag raised exactly with the launch's value; repeated launches reuse the
+    self-resetting completion counters."""
+    import torch
+
+    rng = np.random.default_rng(500 + D)
+    n_dst, n_src = 2600, 1900
+    rowptr, col = power_law_csr(rng, n_dst, n_src, 36000)
+    deg = np.diff(rowptr.astype(np.int64)).copy()
+    # make rows [900, 1000) empty so that one block has no edge at all
+    keep = np.ones(n_dst, dtype=bool)
+    keep[900:1000] = False
+    e_keep = np.repeat(keep, deg)
+    col = col[e_keep]
+    deg[~keep] = 0
+    rowptr = np.zeros(n_dst + 1, dtype=np.uint32)
+    rowptr[1:] = np.cumsum(deg)
+    x = rand_u64(rng, n_src, D)
+    dense = oracle.gather_sum_csr(rowptr, col, x)
+    csr = cgb.csr_create(to_dev(rowptr), to_dev(col), n_src)
+    offsets = [0, 700, 700, 900, 1000, 1777, 2600]  # empty block, block of empty rows, ragged cuts
+    compact = [False, True, True, True, False, True]
+    nb = len(compact)
+    nz_in = [np.nonzero(deg[offsets[b]:offsets[b + 1]])[0] + offsets[b] for b in range(nb)]
+    bufs = [torch.full((max(1, (nz_in[b].size if compact[b] else offsets[b + 1] - offsets[b])), D), -1, dtype=torch.int64, device="cuda")
+            for b in range(nb)]
+    flags = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    for value in (1, 2, 7):
+        cgb.gather_sum_signal(csr, to_dev(x), offsets, [t.data_ptr() for t in bufs], compact,
+                              [flags.data_ptr() + 4 * b for b in range(nb)], value)
+        torch.cuda.synchronize()
+        assert flags.tolist() == [value] * nb
+        for b in range(nb):
+            got = to_np(bufs[b])
+            if compact[b]:
+                assert np.array_equal(got[:nz_in[b].size], dense[nz_in[b]]), (b, value)
+            else:
+                assert np.array_equal(got[:offsets[b + 1] - offsets[b]], dense[offsets[b]:offsets[b + 1]]), (b, value)
+    # no flags requested: plain blocked output
+    for t in bufs:
+        t.fill_(-1)
+    cgb.gather_sum_signal(csr, to_dev(x), offsets, [t.data_ptr() for t in bufs], compact, [0] * nb, 9)
+    torch.cuda.synchronize()
+    assert np.array_equal(to_np(bufs[0])[:700], dense[:700]) and flags.tolist() == [7] * nb
+    csr.destroy()
