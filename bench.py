@@ -142,7 +142,8 @@ def sub_blocks(P):
     """Row ranges each remote block is cut into (as fractions of the destination party's rows).  A pull can only start when its
     block is complete, so with few parties the blocks are cut finer: the pull of one piece overlaps the gather of the next and
     only the last piece's pull is exposed (2 parties: 4 pieces of the one remote block; 8 parties: the 7 blocks as they are)."""
-    return max(1, 8 // P)
+    total = int(os.environ.get("CGB_PIECES_TOTAL", "8"))
+    return max(1, min(total // P, 31 // max(1, P - 1)))
 
 
 def exchange_index_lists(torch, dist, my_lists, rank, P):

@@ -55,43 +55,44 @@ wait_value32_fn resolve_wait_value32() {
 }
 
 // ---- pull + add of a compact block ---------------------------------------------------------------------------------------
-// One group of LANES lanes per row, 16 bytes per lane and column tile; every thread first issues its U remote loads (rows
-// k, k + stride, ...), then the local read-modify-writes, so a CTA keeps U x 16 B x threads in flight against the ~2 us
-// NVLink round trip.  `src` may be peer memory; it is read exactly once, with plain (coherent) loads.
+// Work item = one 16-byte slot of one row (row k, slot s < D / 2), consecutive threads take consecutive slots, so a warp reads
+// 512 contiguous bytes of the (possibly remote) block per instruction.  Every thread first issues its U remote loads (items
+// i, i + stride, ...), then the U local read-modify-writes, so a CTA keeps U x 16 B x 256 threads = 64 KB in flight against the
+// ~2 us NVLink round trip; 32-bit index arithmetic only (a 64-bit division per item made the first version ALU-bound at
+// 240 GB/s).  `src` may be peer memory; it is read exactly once, with plain (coherent) loads that bypass L1.
 constexpr int SA_THREADS = 256;
-constexpr int SA_U = 8;
+constexpr int SA_U = 16;
 
 __device__ __forceinline__ ulonglong2 ld_once_v2(const u64* p) {
     ulonglong2 r;
-    asm volatile("ld.global.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+    asm volatile("ld.global.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
     return r;
 }
 
-// D even, 16-byte aligned rows
-__global__ void __launch_bounds__(SA_THREADS) scatter_add_rows_v2_kernel(const uint32_t* __restrict__ idx, uint64_t n,
+// D even, 16-byte aligned rows, n * D / 2 < 2^32.  SHIFT >= 0: D / 2 == 1 << SHIFT (no division at all)
+template <int SHIFT>
+__global__ void __launch_bounds__(SA_THREADS) scatter_add_rows_v2_kernel(const uint32_t* __restrict__ idx, uint32_t total,
                                                                          const u64* src, u64* __restrict__ v, uint32_t D,
                                                                          int assign) {
-    // work item = (row k, 16-byte slot s), s < D/2; items are laid out so that consecutive threads read consecutive slots
-    const uint64_t slots = D / 2;
-    const uint64_t total = n * slots;
-    const uint64_t stride = (uint64_t)gridDim.x * SA_THREADS;
-    uint64_t i = (uint64_t)blockIdx.x * SA_THREADS + threadIdx.x;
-    for (; i < total; i += SA_U * stride) {
+    const uint32_t slots = D / 2;
+    const uint32_t stride = gridDim.x * SA_THREADS;
+    for (uint32_t i = blockIdx.x * SA_THREADS + threadIdx.x; i < total; i += SA_U * stride) {
         ulonglong2 r[SA_U];
         uint32_t row[SA_U];
 #pragma unroll
         for (int u = 0; u < SA_U; ++u) {
-            const uint64_t it = i + (uint64_t)u * stride;
-            if (it < total) {
-                r[u] = ld_once_v2(src + 2 * it);  // src is dense n x D: item it <-> words [2 it, 2 it + 2)
-                row[u] = __ldg(idx + it / slots);
+            const uint32_t it = i + (uint32_t)u * stride;
+            if (it < total && it >= i) {  // (it >= i: no 32-bit wrap)
+                r[u] = ld_once_v2(src + 2 * (size_t)it);  // src is dense n x D: item it <-> words [2 it, 2 it + 2)
+                row[u] = __ldg(idx + (SHIFT >= 0 ? (it >> SHIFT) : (it / slots)));
             }
         }
 #pragma unroll
         for (int u = 0; u < SA_U; ++u) {
-            const uint64_t it = i + (uint64_t)u * stride;
-            if (it < total) {
-                u64* dst = v + (size_t)row[u] * D + 2 * (it % slots);
+            const uint32_t it = i + (uint32_t)u * stride;
+            if (it < total && it >= i) {
+                const uint32_t s = SHIFT >= 0 ? (it & ((1u << SHIFT) - 1u)) : (it % slots);
+                u64* dst = v + (size_t)row[u] * D + 2 * s;
                 ulonglong2 o = assign ? make_ulonglong2(0, 0) : *reinterpret_cast<const ulonglong2*>(dst);
                 o.x += r[u].x;
                 o.y += r[u].y;
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(SA_THREADS) scatter_add_rows_v1_kernel(const u
     const uint64_t stride = (uint64_t)gridDim.x * SA_THREADS;
     for (uint64_t it = (uint64_t)blockIdx.x * SA_THREADS + threadIdx.x; it < total; it += stride) {
         u64 r;
-        asm volatile("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(src + it) : "memory");
+        asm volatile("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(src + it));
         u64* dst = v + (size_t)__ldg(idx + it / D) * D + it % D;
         *dst = assign ? r : *dst + r;
     }
@@ -147,16 +148,30 @@ int cgb_scatter_add_rows(cgb_ctx* ctx, const uint32_t* d_idx, uint64_t n, const 
     CGB_REQUIRE(ctx, (d_idx && d_src && d_v) || n == 0, "cgb_scatter_add_rows: null argument");
     CGB_REQUIRE(ctx, D > 0, "cgb_scatter_add_rows: D must be positive");
     if (n == 0) return CGB_OK;
-    const bool vec = D % 2 == 0 && aligned16(d_src) && aligned16(d_v);
+    const bool vec = D % 2 == 0 && aligned16(d_src) && aligned16(d_v) && n * (uint64_t)(D / 2) < 0xFFFFFFFFull;
     const uint64_t items = vec ? n * (D / 2) : n * (uint64_t)D;
     const uint64_t per_cta = (uint64_t)SA_THREADS * (vec ? SA_U : 1);
     uint64_t want = (items + per_cta - 1) / per_cta;
-    const uint64_t cap = n_ctas ? n_ctas : (uint64_t)ctx->num_sms * 4;
+    const uint64_t cap = n_ctas ? n_ctas : (uint64_t)ctx->num_sms * 2;
     if (want > cap) want = cap;
-    if (vec)
-        scatter_add_rows_v2_kernel<<<(unsigned)want, SA_THREADS, 0, ctx->stream>>>(d_idx, n, (const u64*)d_src, (u64*)d_v, D,
-                                                                                   assign);
-    else
+    if (vec) {
+        const uint32_t slots = D / 2, total = (uint32_t)items;
+        int shift = -1;
+        for (int sft = 0; sft < 12; ++sft)
+            if (slots == (1u << sft)) shift = sft;
+        const u64* src = (const u64*)d_src;
+        u64* v = (u64*)d_v;
+        switch (shift) {
+            case 0: scatter_add_rows_v2_kernel<0><<<(unsigned)want, SA_THREADS, 0, ctx->stream>>>(d_idx, total, src, v, D, assign); break;
+            case 1: scatter_add_rows_v2_kernel<1><<<(unsigned)want, SA_THREADS, 0, ctx->stream>>>(d_idx, total, src, v, D, assign); break;
+            case 2: scatter_add_rows_v2_kernel<2><<<(unsigned)want, SA_THREADS, 0, ctx->stream>>>(d_idx, total, src, v, D, assign); break;
+            case 3: scatter_add_rows_v2_kernel<3><<<(unsigned)want, SA_THREADS, 0, ctx->stream>>>(d_idx, total, src, v, D, assign); break;
+            case 4: scatter_add_rows_v2_kernel<4><<<(unsigned)want, SA_THREADS, 0, ctx->stream>>>(d_idx, total, src, v, D, assign); break;
+            case 5: scatter_add_rows_v2_kernel<5><<<(unsigned)want, SA_THREADS, 0, ctx->stream>>>(d_idx, total, src, v, D, assign); break;
+            case 6: scatter_add_rows_v2_kernel<6><<<(unsigned)want, SA_THREADS, 0, ctx->stream>>>(d_idx, total, src, v, D, assign); break;
+            default: scatter_add_rows_v2_kernel<-1><<<(unsigned)want, SA_THREADS, 0, ctx->stream>>>(d_idx, total, src, v, D, assign); break;
+        }
+    } else
         scatter_add_rows_v1_kernel<<<(unsigned)want, SA_THREADS, 0, ctx->stream>>>(d_idx, n, (const u64*)d_src, (u64*)d_v, D,
                                                                                    assign);
     CGB_CHECK_LAUNCH(ctx, "scatter_add_rows_kernel");

@@ -332,8 +332,13 @@ __device__ __forceinline__ void gather_chunk_body(const ChunkArgs& a, const SigA
     const uint64_t gid = (uint64_t)blockIdx.x * GROUPS + threadIdx.x / LANES;
     const uint64_t total = ((uint64_t)a.n_chunks + (COMPACT ? 0u : a.n_empty)) * a.n_ct;
     if (gid >= total) return;
-    const uint32_t item = (uint32_t)(gid / a.n_ct);
+    uint32_t item = (uint32_t)(gid / a.n_ct);
     const uint32_t ct = (uint32_t)(gid - (uint64_t)item * a.n_ct);
+    if constexpr (MODE == 2) {
+        // the rows without edges come FIRST in this mode (the first CTAs of the grid): a dense block is complete -- and its flag
+        // raised -- when its last chunk is, not when the tail of the grid gets to its zero rows
+        item = item < a.n_empty ? a.n_chunks + item : item - a.n_empty;
+    }
     const uint32_t col0 = ct * (VEC * LANES) + lane * VEC;
     const bool active = col0 < a.D;
 
