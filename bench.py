@@ -214,7 +214,7 @@ def setup_pull(torch, dist, ctx, rowptr, col, rank, P, n_local, D, dev):
     return {"S": S, "own_csr": own_csr, "csrs": csrs, "nz_piece": nz_piece, "base": base, "offs": offs, "peer_base": peer_base,
             "peer_offs": [everyone[s][1] for s in range(P)], "side": side, "ctx_side": ctx_side, "step": 0,
             "wait_mode": 1 if os.environ.get("CGB_FLAG_WAIT", "memop") == "spin" else 0,
-            "pull_ctas": int(os.environ.get("CGB_PULL_CTAS", "48")),
+            "pull_ctas": int(os.environ.get("CGB_PULL_CTAS", "128")),
             "t0": ev(), "own": ev(), "gat": {k: ev() for k in csrs}, "add": {k: ev() for k in nz_piece}, "end": ev(),
             "err": torch.as_tensor(RawCuda(base + 8 * P * S, (1,), "<i4"), device=dev),
             "bytes_out": sum(c.n_nonempty for c in csrs.values()) * D * 8,
@@ -325,7 +325,7 @@ def setup_fused(torch, dist, ctx, rank, P, n_local, n_edges, D, dev, v):
     return {"S": S, "csr": csr, "offsets": offsets, "pieces": pieces, "nz_piece": nz_piece, "base": base, "offs": offs,
             "peer_base": peer_base, "peer_offs": [everyone[s][1] for s in range(P)], "side": side, "ctx_side": ctx_side, "step": 0,
             "wait_mode": 1 if os.environ.get("CGB_FLAG_WAIT", "memop") == "spin" else 0,
-            "pull_ctas": int(os.environ.get("CGB_PULL_CTAS", "64")),
+            "pull_ctas": int(os.environ.get("CGB_PULL_CTAS", "128")),
             "t0": ev(), "launched": ev(), "add": {k: ev() for k in nz_piece}, "own_seen": ev(), "end": ev(),
             "err": torch.as_tensor(RawCuda(base + 8 * P * S, (1,), "<i4"), device=dev),
             "bytes_out": sum(counts_mine[t][u] for (t, u) in pieces) * D * 8,

@@ -256,6 +256,9 @@ struct SigArgs {
     uint32_t* flag[CGB_MAX_SIG];      // may be null (no signal), may be peer memory
     uint32_t* done;                   // CGB_MAX_SIG device counters, self-resetting
     uint32_t value;
+    // rows without edges exist in the output of DENSE blocks only: e_cum[b] = number of such rows in the dense blocks before b
+    // (e_cum[n_sig] = all of them); the zero rows of block b are empty_row[off[b] - k0[b] + i], i < e_cum[b + 1] - e_cum[b]
+    uint32_t e_cum[CGB_MAX_SIG + 1];
 };
 
 __device__ __forceinline__ uint32_t sig_block_of(const SigArgs& g, uint32_t row, uint32_t b) {
@@ -330,32 +333,35 @@ __device__ __forceinline__ void gather_chunk_body(const ChunkArgs& a, const SigA
     const int lane = threadIdx.x & (LANES - 1);
     const unsigned mask = group_mask<LANES>(threadIdx.x & 31);
     const uint64_t gid = (uint64_t)blockIdx.x * GROUPS + threadIdx.x / LANES;
-    const uint64_t total = ((uint64_t)a.n_chunks + (COMPACT ? 0u : a.n_empty)) * a.n_ct;
+    uint32_t n_empty_items = COMPACT ? 0u : a.n_empty;
+    if constexpr (MODE == 2) n_empty_items = g->e_cum[g->n_sig];  // only the dense blocks have rows without edges to write
+    const uint64_t total = ((uint64_t)a.n_chunks + n_empty_items) * a.n_ct;
     if (gid >= total) return;
     uint32_t item = (uint32_t)(gid / a.n_ct);
     const uint32_t ct = (uint32_t)(gid - (uint64_t)item * a.n_ct);
-    if constexpr (MODE == 2) {
-        // the rows without edges come FIRST in this mode (the first CTAs of the grid): a dense block is complete -- and its flag
-        // raised -- when its last chunk is, not when the tail of the grid gets to its zero rows
-        item = item < a.n_empty ? a.n_chunks + item : item - a.n_empty;
-    }
     const uint32_t col0 = ct * (VEC * LANES) + lane * VEC;
     const bool active = col0 < a.D;
+    if constexpr (MODE == 2) {
+        // the zero rows come FIRST in this mode (the first CTAs of the grid): a dense block is complete -- and its flag raised --
+        // when its last chunk is, not when the tail of the grid gets to its zero rows
+        if (item < n_empty_items) {
+            uint32_t b = 0;
+#pragma unroll 1
+            while (item >= g->e_cum[b + 1]) ++b;
+            const uint32_t row = __ldg(a.empty_row + (g->off[b] - g->k0[b]) + (item - g->e_cum[b]));
+            if (active) {
+                Acc<VEC> v;
+                v.zero();
+                v.store_cs(sig_row_ptr(*g, b, row, 0, a.D) + col0);
+            }
+            if (lane == 0) atomicAdd(&s_cnt[b], 1u);
+            return;
+        }
+        item -= n_empty_items;
+    }
 
     if (item >= a.n_chunks) {  // a row without edges: y = delta (or 0)
         const uint32_t row = __ldg(a.empty_row + (item - a.n_chunks));
-        if constexpr (MODE == 2) {  // dense blocks get their zero rows (and count them); compact blocks have no such row
-            const uint32_t b = sig_block_of(*g, row, 0);
-            if (!((g->compact_mask >> b) & 1u)) {
-                if (active) {
-                    Acc<VEC> v;
-                    v.zero();
-                    v.store_cs(sig_row_ptr(*g, b, row, 0, a.D) + col0);
-                }
-                if (lane == 0) atomicAdd(&s_cnt[b], 1u);
-            }
-            return;
-        }
         if (active) {
             const size_t o = (size_t)row * a.D + col0;
             Acc<VEC> v;
@@ -994,7 +1000,7 @@ static int gather_impl(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_x, 
         }
         if (n_blk) a.blk_off[n_blk] = blk_off[n_blk];
         a.compact = compact ? 1u : 0u;
-        const uint64_t total = ((uint64_t)csr->n_chunks + (compact ? 0u : csr->n_empty)) * s.n_ct;
+        const uint64_t total = ((uint64_t)csr->n_chunks + (sig ? sig->e_cum[sig->n_sig] : (compact ? 0u : csr->n_empty))) * s.n_ct;
         if (total == 0) return CGB_OK;
         // A/B knobs kept from the round-1 experiments (DESIGN.md section 5 has the measurements): CGB_GATHER_IMPL=async -> cp.async
         // staged variant (CGB_GATHER_NBUF=2|3); CGB_GATHER_VEC=2 -> 128-bit kernels; CGB_GATHER_IPL=1 -> one index word per lane
@@ -1161,6 +1167,7 @@ int cgb_gather_sum_signal(cgb_ctx* ctx, const cgb_csr* csr_c, const uint64_t* d_
         g.k0[b] = k_lo;
         if (block_compact[b]) g.compact_mask |= 1u << b;
         g.total[b] = block_compact[b] ? (k_hi - k_lo) : (g.off[b + 1] - g.off[b]);
+        g.e_cum[b + 1] = g.e_cum[b] + (block_compact[b] ? 0u : (g.off[b + 1] - g.off[b]) - (k_hi - k_lo));
         g.base[b] = (u64*)d_block_base[b];
         g.flag[b] = d_block_flag ? d_block_flag[b] : nullptr;
         CGB_REQUIRE(ctx, g.base[b] || g.total[b] == 0, "cgb_gather_sum_signal: null block buffer");
