@@ -33,6 +33,7 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -44,6 +45,8 @@
 #define SCALER_BIT_LENGTH CGB_SCALER_BITS
 #endif
 
+#ifndef TASK_H_
+// ---- stand-alone mode: the vocabulary of the reference's include/task/task.h:78-272 (GNNParam, share typedefs, PosVec) --------
 typedef std::vector<uint64_t> ShareVec;
 typedef std::vector<std::vector<double>> DoubleTensor;
 typedef std::vector<std::vector<uint64_t>> ShareTensor;
@@ -107,6 +110,32 @@ public:
     }
 };
 
+#else
+// ---- the reference's own task.h is in the translation unit (its operator headers are being compiled against this shim): it
+// declares these helpers and leaves their definitions to Task-Worker (absent); define them here, once, inline
+inline ShareTensor transpose(const ShareTensor& st) {
+    if (st.empty()) return ShareTensor();
+    ShareTensor out(st[0].size(), ShareVec(st.size()));
+    for (size_t i = 0; i < st.size(); ++i)
+        for (size_t j = 0; j < st[i].size(); ++j) out[j][i] = st[i][j];
+    return out;
+}
+inline ShareTensor toShareTensor(const ShareVec& sv) { return ShareTensor(1, sv); }
+inline ShareVec toShareVec(const ShareTensor& st) {
+    ShareVec v;
+    for (const auto& r : st) v.insert(v.end(), r.begin(), r.end());
+    return v;
+}
+#ifndef SCALER_BIT_LENGTH
+#define SCALER_BIT_LENGTH CGB_SCALER_BITS
+#endif
+inline ShareVec toShareVec(int hotIndex, int vecSize) {  // one-hot label in fixed point (gcn.h:575)
+    ShareVec v(vecSize, 0);
+    if (hotIndex >= 0 && hotIndex < vecSize) v[hotIndex] = 1ull << SCALER_BIT_LENGTH;
+    return v;
+}
+#endif  // TASK_H_
+
 enum class AggregationOp { ADD_AGG, MIN_AGG, MAX_AGG };
 
 namespace cognn_shim {
@@ -160,6 +189,8 @@ enum Kind : uint64_t { K_MM_U0 = 5, K_MM_U1, K_MM_V0, K_MM_V1, K_MM_Z0, K_RM_A0,
 inline uint64_t stream_id(uint64_t kind, uint64_t op, uint64_t owner, uint64_t sub) {
     return (kind << 48) | (op << 16) | (owner << 8) | sub;
 }
+// dealer streams of an (owner, helper) pair: 4 bits of sub-stream, 4 bits of helper id in the low byte (T <= 16)
+inline uint64_t pair_sub(uint64_t helper, uint64_t sub) { return ((helper & 15) << 4) | (sub & 15); }
 
 class Runtime {
 public:
@@ -170,15 +201,31 @@ public:
         for (auto& kv : ctxs) cgb_ctx_destroy(kv.second);
     }
     // the thread that will issue primitives for (coTid, party) registers its channel to the matching thread of coTid
-    void connect(uint64_t coTid, int party, Channel* ch) { chans[{coTid, party}] = ch; }
+    void connect(uint64_t coTid, int party, Channel* ch) {
+        std::lock_guard<std::mutex> l(mu);
+        chans[{coTid, party}] = ch;
+    }
+    void connect_owned(uint64_t coTid, int party, Channel* ch) {  // the runtime deletes the channel
+        connect(coTid, party, ch);
+        std::lock_guard<std::mutex> l(mu);
+        owned.emplace_back(ch);
+    }
     static Runtime*& current_ptr() {
         static thread_local Runtime* rt = nullptr;
         return rt;
     }
     static void bind_thread(Runtime* rt) { current_ptr() = rt; }
+    // one party per process (the reference's deployment: its engine spawns the ALICE / BOB threads itself, so nothing can bind
+    // them): the runtime every unbound thread falls back to
+    static Runtime*& process_ptr() {
+        static Runtime* rt = nullptr;
+        return rt;
+    }
+    static void bind_process(Runtime* rt) { process_ptr() = rt; }
     static Runtime& current() {
-        if (!current_ptr()) fatal("cognn_shim", "no Runtime bound to this thread (Runtime::bind_thread)");
-        return *current_ptr();
+        if (current_ptr()) return *current_ptr();
+        if (process_ptr()) return *process_ptr();
+        fatal("cognn_shim", "no Runtime bound to this thread or process (Runtime::bind_thread / bind_process)");
     }
     cgb_ctx* ctx(uint64_t coTid, int party) {
         std::lock_guard<std::mutex> l(mu);
@@ -191,13 +238,16 @@ public:
         return c;
     }
     Channel& chan(uint64_t coTid, int party) {
+        std::lock_guard<std::mutex> l(mu);
         auto it = chans.find({coTid, party});
         if (it == chans.end()) fatal("cognn_shim", "no channel connected for this (coTid, party)");
         return *it->second;
     }
-    uint64_t next_op(uint64_t owner, int share) {
+    // one counter per (owner, helper) pair and share: the ALICE thread of the owner and the BOB thread of the helper issue the
+    // same sequence of two-party primitives (ssk.h:702-704 / 926-928), other pairs run concurrently with their own sequence
+    uint64_t next_op(uint64_t owner, uint64_t helper, int share) {
         std::lock_guard<std::mutex> l(mu);
-        return ops[{owner, share}]++;
+        return ops[{owner * 256 + helper, share}]++;
     }
     int tileIndex, tileNum, device;
     uint32_t key[8];
@@ -207,6 +257,7 @@ private:
     std::map<std::pair<uint64_t, int>, cgb_ctx*> ctxs;
     std::map<std::pair<uint64_t, int>, Channel*> chans;
     std::map<std::pair<uint64_t, int>, uint64_t> ops;
+    std::vector<std::unique_ptr<Channel>> owned;
 };
 
 // ---- small RAII device buffer + host <-> device helpers -------------------------------------------------------------
@@ -263,14 +314,16 @@ inline void swap_msgs(Channel& ch, const Dev& mine, Dev& peer) {
 struct Call {  // common prologue of every two-party primitive
     Runtime& rt;
     int share;
-    uint64_t owner, op;
+    uint64_t owner, helper, op;
     cgb_ctx* c;
     Channel& ch;
     Call(uint64_t coTid, int party)
         : rt(Runtime::current()), share(party == 1 ? 0 : 1), owner(party == 1 ? (uint64_t)rt.tileIndex : coTid),
-          op(rt.next_op(owner, share)), c(rt.ctx(coTid, party)), ch(rt.chan(coTid, party)) {
+          helper(party == 1 ? coTid : (uint64_t)rt.tileIndex), op(rt.next_op(owner, helper, share)), c(rt.ctx(coTid, party)),
+          ch(rt.chan(coTid, party)) {
         if (party != 1 && party != 2) fatal("cognn_shim", "party must be sci::ALICE (1) or sci::BOB (2)");
     }
+    uint64_t sid(uint64_t kind, uint64_t sub = 0) const { return stream_id(kind, op, owner, pair_sub(helper, sub)); }
 };
 
 }  // namespace cognn_shim
@@ -278,13 +331,28 @@ struct Call {  // common prologue of every two-party primitive
 // ---------------------------------------------------------------------------------------------------------------------
 class CryptoUtil {
 public:
+    // the reference's main() configures a singleton (harness.cpp:119-121); the Paillier / FHE set-up it asks for belongs to the
+    // HE task queue that the secret-shared GCN path does not use ("not used", README.md:107)
+    static CryptoUtil& getInstance() {
+        static CryptoUtil inst;
+        return inst;
+    }
+    void tileIndexIs(size_t t) { tileIndex_ = t; }
+    size_t tileIndex() const { return tileIndex_; }
+    void setUpPaillierCipher() {}
+    void setUpFHECipher() {}
+
     static uint64_t encodeDoubleAsFixedPoint(double x) { return (uint64_t)(int64_t)(x * (double)(1ull << SCALER_BIT_LENGTH)); }
     static double decodeFixedPointAsDouble(uint64_t v) { return (double)(int64_t)v / (double)(1ull << SCALER_BIT_LENGTH); }
-    // s1 = next word of this thread's split stream, s0 = enc(x) - s1 (DESIGN.md "Frozen semantics")
+    // s1 = next word of the party's split stream, s0 = enc(x) - s1 (DESIGN.md "Frozen semantics").  The reference calls this
+    // from OpenMP workers (optimize-gcn/gcn.h:86-99 intoShareTensor): ONE process-wide pool under a mutex, refilled from
+    // consecutive PRG blocks of one stream, so no two calls -- on whatever thread -- ever draw the same mask word.
     static void intoShares(double x, uint64_t& s0, uint64_t& s1) {
-        static thread_local std::vector<uint64_t> pool;
-        static thread_local size_t pos = 0;
-        static thread_local uint64_t refill = 0;
+        static std::mutex mu;
+        static std::vector<uint64_t> pool;
+        static size_t pos = 0;
+        static uint64_t refill = 0;
+        std::lock_guard<std::mutex> l(mu);
         if (pos == pool.size()) {
             auto& rt = cognn_shim::Runtime::current();
             cgb_ctx* c = rt.ctx((uint64_t)-1, 1);
@@ -299,12 +367,104 @@ public:
         s0 = encodeDoubleAsFixedPoint(x) - s1;
     }
     static double mergeShareAsDouble(uint64_t s0, uint64_t s1) { return decodeFixedPointAsDouble(s0 + s1); }
+
+private:
+    size_t tileIndex_ = 0;
 };
 
 namespace sci {
 
 const int ALICE = 1;
 const int BOB = 2;
+
+// ---- plaintext helpers the operators use for the FedAvg sums and for the metrics the owner prints (gcn.h:603-632, 753-777) ----
+inline void plaintext_add_matrix_in_place(ShareVecVec& a, const ShareVecVec& b) {
+    if (a.size() != b.size()) cognn_shim::fatal("plaintext_add_matrix_in_place", "row count mismatch");
+    for (size_t i = 0; i < a.size(); ++i) {
+        if (a[i].size() != b[i].size()) cognn_shim::fatal("plaintext_add_matrix_in_place", "column count mismatch");
+        for (size_t j = 0; j < a[i].size(); ++j) a[i][j] += b[i][j];
+    }
+}
+inline ShareVecVec plaintext_add_matrix(const ShareVecVec& a, const ShareVecVec& b) {
+    ShareVecVec r = a;
+    plaintext_add_matrix_in_place(r, b);
+    return r;
+}
+inline double cross_entropy_loss(const DoubleTensor& y, const DoubleTensor& p) {  // mean over rows of -log p[label]
+    if (y.empty()) return 0.0;
+    double tot = 0.0;
+    for (size_t i = 0; i < y.size(); ++i)
+        for (size_t j = 0; j < y[i].size(); ++j)
+            if (y[i][j] != 0.0) tot -= y[i][j] * std::log(p[i][j] > 1e-30 ? p[i][j] : 1e-30);
+    return tot / (double)y.size();
+}
+inline size_t argmax_row(const std::vector<double>& r) {
+    size_t b = 0;
+    for (size_t j = 1; j < r.size(); ++j)
+        if (r[j] > r[b]) b = j;
+    return b;
+}
+inline double accuracy(const DoubleTensor& y, const DoubleTensor& p) {
+    if (y.empty()) return 0.0;
+    size_t hit = 0;
+    for (size_t i = 0; i < y.size(); ++i) hit += argmax_row(y[i]) == argmax_row(p[i]);
+    return (double)hit / (double)y.size();
+}
+inline double accuracy(const DoubleTensor& y, const DoubleTensor& p, const std::vector<bool>& mask) {  // rows with mask only
+    size_t hit = 0, n = 0;
+    for (size_t i = 0; i < y.size(); ++i)
+        if (mask[i]) {
+            ++n;
+            hit += argmax_row(y[i]) == argmax_row(p[i]);
+        }
+    return n ? (double)hit / (double)n : 0.0;
+}
+inline size_t count_true(const std::vector<bool>& v) {
+    size_t n = 0;
+    for (bool b : v) n += b;
+    return n;
+}
+template <typename T>
+inline void print_vector(const std::vector<T>& v, size_t limit = (size_t)-1) {
+    for (size_t i = 0; i < v.size() && i < limit; ++i) std::cout << v[i] << " ";
+    std::cout << std::endl;
+}
+template <typename T>
+inline void print_vector_of_vector(const std::vector<std::vector<T>>& m, size_t limit = (size_t)-1) {
+    for (size_t i = 0; i < m.size() && i < limit; ++i) print_vector(m[i]);
+}
+// GCN_LOG debugging aid of the reference: opens the shares towards ALICE and prints the fixed-point values (insecure by nature;
+// only compiled into debugging builds of the operator headers, -DGCN_LOG)
+inline void printShareVecVec(const ShareVecVec& m, uint64_t coTid, int party) {
+    auto& rt = cognn_shim::Runtime::current();
+    cognn_shim::Channel& ch = rt.chan(coTid, party);
+    size_t rows, cols;
+    std::vector<uint64_t> x = cognn_shim::flatten(m, &rows, &cols);
+    if (party == 2) {
+        ch.send(x);
+        return;
+    }
+    std::vector<uint64_t> other;
+    ch.recv(other);
+    static std::mutex mu;
+    static std::map<uint64_t, int> calls;
+    std::lock_guard<std::mutex> l(mu);
+    const int call = calls[coTid]++;
+    std::string out;
+    char buf[64];
+    for (size_t i = 0; i < rows; ++i) {
+        snprintf(buf, sizeof buf, "\n[svv peer=%llu call=%d row=%zu]", (unsigned long long)coTid, call, i);
+        out += buf;
+        for (size_t j = 0; j < cols; ++j) {
+            snprintf(buf, sizeof buf, " %.6f",
+                     (double)(int64_t)(x[i * cols + j] + (i * cols + j < other.size() ? other[i * cols + j] : 0)) / (double)(1ull << SCALER_BIT_LENGTH));
+            out += buf;
+        }
+    }
+    out += "\n";
+    fputs(out.c_str(), stdout);
+    fflush(stdout);
+}
 
 // C = trunc(A * B) on shares (Beaver triple from the dealer PRG; one message each way)
 inline void twoPartyGCNMatMul(const ShareVecVec& A, const ShareTensor& B, ShareVecVec& C, uint64_t coTid, int party) {
@@ -318,16 +478,16 @@ inline void twoPartyGCNMatMul(const ShareVecVec& A, const ShareTensor& B, ShareV
     dA.up(a);
     dB.up(b);
     if (k.share == 0) {
-        prg(c, k.rt.key, stream_id(K_MM_U0, k.op, k.owner, 0), U);
-        prg(c, k.rt.key, stream_id(K_MM_V0, k.op, k.owner, 0), V);
-        prg(c, k.rt.key, stream_id(K_MM_Z0, k.op, k.owner, 0), Z);
+        prg(c, k.rt.key, k.sid(K_MM_U0), U);
+        prg(c, k.rt.key, k.sid(K_MM_V0), V);
+        prg(c, k.rt.key, k.sid(K_MM_Z0), Z);
     } else {  // dealer emulation: Z1 = (U0+U1)(V0+V1) - Z0
         Dev U0(c, M * K), V0(c, K * N), Z0(c, M * N);
-        prg(c, k.rt.key, stream_id(K_MM_U0, k.op, k.owner, 0), U0);
-        prg(c, k.rt.key, stream_id(K_MM_V0, k.op, k.owner, 0), V0);
-        prg(c, k.rt.key, stream_id(K_MM_Z0, k.op, k.owner, 0), Z0);
-        prg(c, k.rt.key, stream_id(K_MM_U1, k.op, k.owner, 0), U);
-        prg(c, k.rt.key, stream_id(K_MM_V1, k.op, k.owner, 0), V);
+        prg(c, k.rt.key, k.sid(K_MM_U0), U0);
+        prg(c, k.rt.key, k.sid(K_MM_V0), V0);
+        prg(c, k.rt.key, k.sid(K_MM_Z0), Z0);
+        prg(c, k.rt.key, k.sid(K_MM_U1), U);
+        prg(c, k.rt.key, k.sid(K_MM_V1), V);
         ok(c, cgb_add(c, U0.p, U.p, U0.p, U0.n), "cgb_add");
         ok(c, cgb_add(c, V0.p, V.p, V0.p, V0.n), "cgb_add");
         ok(c, cgb_matmul(c, U0.p, V0.p, Z.p, M, K, N, 0, 0), "cgb_matmul");
@@ -344,7 +504,8 @@ inline void twoPartyGCNMatMul(const ShareVecVec& A, const ShareTensor& B, ShareV
 }
 
 namespace detail {
-// out = [trunc](x * s[row]) with s private to ALICE (BOB's scaler argument is ignored, it passes zeros: ssk.h:985-994)
+// out = [trunc](x * s[row]) with s = s_ALICE + s_BOB: in CoGNN-Opt the scaler is private to ALICE and BOB passes zeros
+// (ssk.h:985-994); in original-gcn BOB supplies the destination normaliser of mirror edges instead (ssk.h:1043)
 inline void rowmul(const ShareVecVec& in, const std::vector<uint64_t>& scaler, ShareVecVec& out, uint64_t coTid, int party, int f) {
     using namespace cognn_shim;
     Call k(coTid, party);
@@ -355,16 +516,16 @@ inline void rowmul(const ShareVecVec& in, const std::vector<uint64_t>& scaler, S
     Dev dx(c, rows * D), a(c, rows * D), b(c, rows), cc(c, rows * D), mine(c, rows * D + rows), peer(c, rows * D + rows), res(c, rows * D);
     dx.up(x);
     if (k.share == 0) {
-        prg(c, k.rt.key, stream_id(K_RM_A0, k.op, k.owner, 0), a);
-        prg(c, k.rt.key, stream_id(K_RM_B0, k.op, k.owner, 0), b);
-        prg(c, k.rt.key, stream_id(K_RM_C0, k.op, k.owner, 0), cc);
+        prg(c, k.rt.key, k.sid(K_RM_A0), a);
+        prg(c, k.rt.key, k.sid(K_RM_B0), b);
+        prg(c, k.rt.key, k.sid(K_RM_C0), cc);
     } else {
         Dev a0(c, rows * D), b0(c, rows), c0(c, rows * D), zm(c, rows * D), zv(c, rows);
-        prg(c, k.rt.key, stream_id(K_RM_A0, k.op, k.owner, 0), a0);
-        prg(c, k.rt.key, stream_id(K_RM_B0, k.op, k.owner, 0), b0);
-        prg(c, k.rt.key, stream_id(K_RM_C0, k.op, k.owner, 0), c0);
-        prg(c, k.rt.key, stream_id(K_RM_A1, k.op, k.owner, 0), a);
-        prg(c, k.rt.key, stream_id(K_RM_B1, k.op, k.owner, 0), b);
+        prg(c, k.rt.key, k.sid(K_RM_A0), a0);
+        prg(c, k.rt.key, k.sid(K_RM_B0), b0);
+        prg(c, k.rt.key, k.sid(K_RM_C0), c0);
+        prg(c, k.rt.key, k.sid(K_RM_A1), a);
+        prg(c, k.rt.key, k.sid(K_RM_B1), b);
         ok(c, cgb_add(c, a0.p, a.p, a0.p, a0.n), "cgb_add");
         ok(c, cgb_add(c, b0.p, b.p, b0.p, b0.n), "cgb_add");
         ok(c, cgb_memset(c, zm.p, 0, zm.n * 8), "memset");
@@ -380,8 +541,10 @@ inline void rowmul(const ShareVecVec& in, const std::vector<uint64_t>& scaler, S
         ok(c, cgb_sub(c, s.p, b.p, mine.p + rows * D, rows), "cgb_sub");
         cgb_ctx_sync(c);
     } else {
-        ok(c, cgb_memset(c, mine.p + rows * D, 0, rows * 8), "memset");
-        ok(c, cgb_sub(c, mine.p + rows * D, b.p, mine.p + rows * D, rows), "cgb_sub");
+        Dev s(c, rows);
+        s.up(scaler);
+        ok(c, cgb_sub(c, s.p, b.p, mine.p + rows * D, rows), "cgb_sub");
+        cgb_ctx_sync(c);
     }
     swap_msgs(k.ch, mine, peer);
     ok(c, cgb_add(c, mine.p, peer.p, mine.p, mine.n), "cgb_add");
@@ -398,8 +561,10 @@ inline void twoPartyGCNVectorScale(const ShareVecVec& in, const std::vector<uint
 // out = v + (cond ? u : 0); cond is private to ALICE (BOB passes all-true, ssk.h:1124-1126): MUX via a Beaver product
 inline void twoPartyGCNCondVectorAddition(const ShareVecVec& v, const ShareVecVec& u, const std::vector<bool>& cond, ShareVecVec& out,
                                           uint64_t coTid, int party) {
-    std::vector<uint64_t> sel(cond.size());
-    for (size_t i = 0; i < cond.size(); ++i) sel[i] = cond[i] ? 1 : 0;
+    // the selector is ALICE's alone: BOB's argument carries no information (all true, ssk.h:1124-1126) and must not be added in
+    std::vector<uint64_t> sel(cond.size(), 0);
+    if (party == ALICE)
+        for (size_t i = 0; i < cond.size(); ++i) sel[i] = cond[i] ? 1 : 0;
     ShareVecVec gated;
     detail::rowmul(u, sel, gated, coTid, party, -1);
     ShareVecVec r(v.size());
@@ -488,7 +653,7 @@ inline bool ideal_exchange(cognn_shim::Call& k, int party, const std::vector<uin
 inline void ideal_reshare(cognn_shim::Call& k, int party, int sub, const cognn_shim::Dev* plain, size_t rows, size_t cols, ShareVecVec& out) {
     using namespace cognn_shim;
     Dev r(k.c, rows * cols);
-    prg(k.c, k.rt.key, stream_id(K_RESHARE, k.op, k.owner, sub), r);
+    prg(k.c, k.rt.key, k.sid(K_RESHARE, sub), r);
     if (party == BOB) {
         unflatten(r.down(), rows, cols, out);
         return;
@@ -588,7 +753,54 @@ inline void twoPartyGCNBackwardNNWithoutAH(const ShareVecVec& in, const ShareVec
     if (!isFirstLayer) twoPartyGCNMatMul(dstVec, weightT, g, coTid, party);
     else g.clear();
 }
+
+// ---- the fused primitives of the UNOPTIMISED operators (original-gcn/gcn.h:459, 493, 586, 622; BASELINE configs[2]'s comparison
+// arm): compositions of the primitives above, so they inherit the same 2PC-residual stand-ins.  `normalizer` is passed empty
+// by the reference (original-gcn/gcn.h:451) and ignored.
+// z = AH * W, new_h = ReLU(z)
+inline void twoPartyGCNForwardNN(const ShareVecVec& ah, const ShareTensor& weight, const std::vector<uint64_t>& /*normalizer*/, ShareTensor& z,
+                                 ShareTensor& new_h, uint64_t coTid, int party) {
+    twoPartyGCNMatMul(ah, weight, z, coTid, party);
+    twoPartyGCNRelu(z, new_h, coTid, party);
+}
+// z = AH * W, p = softmax(z), p_minus_y = p - label
+inline void twoPartyGCNForwardNNPrediction(const ShareVecVec& ah, const ShareTensor& weight, const ShareVecVec& label,
+                                           const std::vector<uint64_t>& /*normalizer*/, ShareTensor& z, ShareTensor& p, ShareTensor& p_minus_y,
+                                           uint64_t coTid, int party) {
+    twoPartyGCNMatMul(ah, weight, z, coTid, party);
+    twoPartyGCNForwardNNPredictionWithoutWeight(z, label, p, p_minus_y, coTid, party);
+}
+// last layer, backward: d = AH^T * grad (weight gradient), g = grad * W^T (gradient towards the previous layer)
+inline void twoPartyGCNBackwardNNInit(const ShareVecVec& grad, const ShareTensor& ah_t, const ShareTensor& weightT,
+                                      const std::vector<uint64_t>& /*normalizer*/, ShareTensor& d, ShareTensor& g, uint64_t coTid, int party) {
+    ShareTensor d_new, g_new;
+    twoPartyGCNMatMul(ah_t, grad, d_new, coTid, party);
+    twoPartyGCNMatMul(grad, weightT, g_new, coTid, party);
+    d.swap(d_new);
+    g.swap(g_new);
+}
+// hidden layer, backward: v = grad (.) ReLU'(z), d = AH^T * v, g = v * W^T unless this is the first layer
+inline void twoPartyGCNBackwardNN(const ShareVecVec& grad, const ShareTensor& ah_t, const ShareTensor& z, const ShareTensor& weightT,
+                                  const std::vector<uint64_t>& /*normalizer*/, ShareTensor& d, ShareTensor& g, bool isFirstLayer, uint64_t coTid,
+                                  int party) {
+    ShareVecVec v;
+    ShareTensor g_new, d_new;
+    twoPartyGCNBackwardNNWithoutAH(grad, z, weightT, v, g_new, isFirstLayer, coTid, party);
+    twoPartyGCNMatMul(ah_t, v, d_new, coTid, party);
+    d.swap(d_new);
+    g.swap(g_new);
+}
 #endif  // COGNN_SHIM_IDEAL_NONLINEAR
+
+// the per-edge scale of the UNOPTIMISED Scatter (original-gcn/gcn.h:243-250): out = in * n0[row] * n1[row], two fixed-point
+// products; n0 (source out-degree normaliser) is ALICE's, n1 (destination in-degree normaliser) ALICE's for local edges and
+// BOB's for mirror edges (ssk.h:1041-1043) -- each side passes zeros for what it does not know
+inline void twoPartyGCNVectorScale(const ShareVecVec& in, const std::vector<uint64_t>& normalizer0, const std::vector<uint64_t>& normalizer1,
+                                   ShareVecVec& out, uint64_t coTid, int party) {
+    ShareVecVec tmp;
+    detail::rowmul(in, normalizer0, tmp, coTid, party, SCALER_BIT_LENGTH);
+    detail::rowmul(tmp, normalizer1, out, coTid, party, SCALER_BIT_LENGTH);
+}
 
 }  // namespace sci
 
@@ -608,9 +820,9 @@ inline ShareVecVec prefix_network_aggregate(const std::vector<uint64_t>& dstPos,
     if (party == sci::BOB) {
         Dev dx(c, E * D), m(c, E * D), s(c, E * D);
         dx.up(x);
-        ok(c, cgb_prg_mask_sub(c, k.rt.key, stream_id(K_OM_R, k.op, k.owner, 0), 0, dx.p, m.p, m.n), "cgb_prg_mask_sub");
+        ok(c, cgb_prg_mask_sub(c, k.rt.key, k.sid(K_OM_R), 0, dx.p, m.p, m.n), "cgb_prg_mask_sub");
         k.ch.send(m.down());
-        prg(c, k.rt.key, stream_id(K_OM_S, k.op, k.owner, 0), s);
+        prg(c, k.rt.key, k.sid(K_OM_S), s);
         unflatten(s.down(), E, D, result);
         return result;
     }
@@ -628,8 +840,8 @@ inline ShareVecVec prefix_network_aggregate(const std::vector<uint64_t>& dstPos,
     ok(c, cgb_h2d(c, dseg, segptr.data(), segptr.size() * 4), "cgb_h2d");
     dx.up(x);
     m.up(msg);
-    prg(c, k.rt.key, stream_id(K_OM_R, k.op, k.owner, 0), r);
-    prg(c, k.rt.key, stream_id(K_OM_S, k.op, k.owner, 0), s);
+    prg(c, k.rt.key, k.sid(K_OM_R), r);
+    prg(c, k.rt.key, k.sid(K_OM_S), s);
     const uint32_t n_seg = (uint32_t)segptr.size() - 1;
     ok(c, cgb_segsum(c, (const uint32_t*)dseg, n_seg, E, r.p, gr.p, (uint32_t)D, 1), "cgb_segsum");  // dealer: G r
     ok(c, cgb_sub(c, gr.p, s.p, gr.p, gr.n), "cgb_sub");                                              //         - s
@@ -650,9 +862,6 @@ inline void client_oblivious_mapper_online(const std::vector<uint64_t>& srcPos, 
     (void)preprocessId;  // the reference keys its offline correlation by (iter, preprocessId); here by the call counter
     Call k(coTid, sci::ALICE);
     const size_t n_src = srcPos.size(), n_dst = dstPos.size(), D = plainNumPerOperand;
-    size_t r_, c_;
-    std::vector<uint64_t> x = flatten(srcSvv, &r_, &c_);
-    if (r_ != n_src || (n_src && c_ != D)) fatal("client_oblivious_mapper_online", "source shape mismatch");
     std::unordered_map<uint64_t, uint32_t> first;
     for (size_t i = 0; i < n_src; ++i) first.emplace(srcPos[i], (uint32_t)i);  // duplicated sources: first occurrence
     std::vector<uint32_t> idx(n_dst);
@@ -663,9 +872,24 @@ inline void client_oblivious_mapper_online(const std::vector<uint64_t>& srcPos, 
             idx[j] = CGB_NO_ROW;
         } else idx[j] = it->second;
     }
+    if (getenv("COGNN_SHIM_TRACE"))
+        printf("[shim] OM client me=%d peer=%llu iter=%llu id=%u op=%llu n_src=%zu n_dst=%zu D=%zu\n", k.rt.tileIndex, (unsigned long long)coTid,
+               (unsigned long long)iter, preprocessId, (unsigned long long)k.op, n_src, n_dst, D);
     k.ch.send(std::vector<uint64_t>{(uint64_t)n_dst});  // the server learns the output size (as in the reference's preprocessing)
     std::vector<uint64_t> msg;
     k.ch.recv(msg);
+    // The client's own share is read only now, after the server's message: with more than two parties the ALICE threads of the
+    // non-primary peers call this on gs.localVertexSvv while the primary thread may still be inside PreScatterComp
+    // (ssk.h:734-763 has no barrier there); their servers answer only after the primary helper has forwarded its PreScatter result
+    // (ssk.h:981-1002), which orders the two in practice.
+    size_t r_, c_;
+    std::vector<uint64_t> x = flatten(srcSvv, &r_, &c_);
+    if (r_ != n_src || (n_src && c_ != D)) {
+        char emsg[200];
+        snprintf(emsg, sizeof emsg, "source shape mismatch: %zu positions, %zu x %zu shares, %zu columns expected (iter %llu, id %u, peer %llu)",
+                 n_src, r_, c_, D, (unsigned long long)iter, preprocessId, (unsigned long long)coTid);
+        fatal("client_oblivious_mapper_online", emsg);
+    }
     if (msg.size() != n_src * D) fatal("client_oblivious_mapper_online", "message size mismatch");
     cgb_ctx* c = k.c;
     Dev dx(c, n_src * D), m(c, n_src * D), r(c, n_src * D), s(c, n_dst * D), delta(c, n_dst * D), y(c, n_dst * D);
@@ -674,8 +898,8 @@ inline void client_oblivious_mapper_online(const std::vector<uint64_t>& srcPos, 
     if (n_dst) ok(c, cgb_h2d(c, didx, idx.data(), n_dst * 4), "cgb_h2d");
     dx.up(x);
     m.up(msg);
-    prg(c, k.rt.key, stream_id(K_OM_R, k.op, k.owner, 0), r);
-    prg(c, k.rt.key, stream_id(K_OM_S, k.op, k.owner, 0), s);
+    prg(c, k.rt.key, k.sid(K_OM_R), r);
+    prg(c, k.rt.key, k.sid(K_OM_S), s);
     if (D) {
         ok(c, cgb_expand_rows(c, (const uint32_t*)didx, n_dst, r.p, nullptr, delta.p, (uint32_t)D), "cgb_expand_rows");  // dealer: pi(r)
         ok(c, cgb_sub(c, delta.p, s.p, delta.p, delta.n), "cgb_sub");                                                   //         - s
@@ -697,11 +921,14 @@ inline void server_oblivious_mapper_online(const ShareVecVec& srcSvv, ShareVecVe
     std::vector<uint64_t> hdr;
     k.ch.recv(hdr);
     const size_t n_dst = hdr.empty() ? 0 : (size_t)hdr[0];
+    if (getenv("COGNN_SHIM_TRACE"))
+        printf("[shim] OM server me=%d owner=%llu iter=%llu id=%u op=%llu n_src=%zu n_dst=%zu D=%zu\n", k.rt.tileIndex, (unsigned long long)coTid,
+               (unsigned long long)iter, preprocessId, (unsigned long long)k.op, n_src, n_dst, D);
     cgb_ctx* c = k.c;
     Dev dx(c, n_src * D), m(c, n_src * D), s(c, n_dst * D);
     dx.up(x);
-    ok(c, cgb_prg_mask_sub(c, k.rt.key, stream_id(K_OM_R, k.op, k.owner, 0), 0, dx.p, m.p, m.n), "cgb_prg_mask_sub");
+    ok(c, cgb_prg_mask_sub(c, k.rt.key, k.sid(K_OM_R), 0, dx.p, m.p, m.n), "cgb_prg_mask_sub");
     k.ch.send(m.down());
-    prg(c, k.rt.key, stream_id(K_OM_S, k.op, k.owner, 0), s);
+    prg(c, k.rt.key, k.sid(K_OM_S), s);
     unflatten(s.down(), n_dst, D, dstSvv);
 }

@@ -1,0 +1,2 @@
+#pragma once
+#include "binary_oarchive.hpp"
