@@ -37,6 +37,8 @@ def _binaries():
 
 def run_until_complete(binary, g, T, iters, n_losses, mock, port_base, attempts=5, skip_if_never=False):
     last = None
+    # every pytest process gets its own port window (a killed earlier run may still hold listening sockets for a while)
+    port_base = 20000 + (os.getpid() * 7 % 120) * 300 + (port_base % 3000) // 10
     for a in range(attempts):
         rcs, out = refdrop.run(binary, g, T, iters, mock, port_base + 20 * a, timeout=25 if mock else 90)
         last = (rcs, out)
