@@ -27,7 +27,7 @@ def test_reference_code_runs_on_the_cuda_library_and_matches_oracle():
     g = small_graph(n=60, n_edges=220, F=10, C=4, T=2, seed=5)
     gd = refdrop.graph_dict(g["edges"], g["tid"], g["feats"], g["labels"], CFG)
     out = run_until_complete("gcn-optimize", gd, 2, 12, 2, False, 33000)
-    check_against_oracle(out, g, 2, 12, 1e-4)
+    check_against_oracle(out, g, 2, 12, 1e-3)
 
 
 @pytest.mark.timeout(900)
@@ -41,7 +41,7 @@ def test_reference_inference_and_original_operators_on_the_cuda_library():
     g = small_graph(n=60, n_edges=220, F=10, C=4, T=2, seed=6)
     gd = refdrop.graph_dict(g["edges"], g["tid"], g["feats"], g["labels"], CFG)
     out = run_until_complete("gcn-inference-optimize", gd, 2, 2, 1, False, 33300)
-    check_against_oracle(out, g, 2, 2, 1e-4)
+    check_against_oracle(out, g, 2, 2, 1e-3)
     if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "gcn-original")):
         out = run_until_complete("gcn-original", gd, 2, 4, 1, False, 33600)
         o = oep.EpochOracle(g["edges"], g["tid"], 2, g["feats"], g["labels"], CFG)

