@@ -242,7 +242,28 @@ int main(int argc, char* argv[]) {
             comm = make_nccl_comm((int)tileIndex, T, ctx, uid);
             if (tileIndex == 0) remove(idfile.c_str());
         }
-        const uint32_t key[8] = {45, 0, 0, 0, 0, 0, 0, 0};
+        // Master key of the dealer emulation.  Every party derives ALL correlated randomness (OM masks, Beaver triples, re-share
+        // masks) from it, so a run is only as private as this key is secret from ... nobody: it is a TEST configuration.  The key
+        // comes from COGNN_B200_KEY (eight 32-bit words, hex, comma separated; the same for all parties of a run) -- there is no
+        // compiled-in default any more -- and the binary refuses to start unless the caller acknowledges what it emulates.
+        uint32_t key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        {
+            const char* ack = getenv("COGNN_B200_ALLOW_INSECURE_EMULATION");
+            const char* ks = getenv("COGNN_B200_KEY");
+            printf("gcn-optimize-b200: INSECURE -- all correlated randomness comes from a trusted-dealer EMULATION keyed by COGNN_B200_KEY (every\n"
+                   "party can regenerate every mask), and ReLU / softmax / ReLU' run as ideal-functionality stand-ins on values opened to the\n"
+                   "owner.  Timing and functional parity only; no privacy.  (DESIGN.md section 1)\n");
+            if (!ack || std::string(ack) != "1") {
+                printf("refusing to run: set COGNN_B200_ALLOW_INSECURE_EMULATION=1 to acknowledge\n");
+                exit(-1);
+            }
+            unsigned long long v[8] = {0};
+            if (!ks || sscanf(ks, "%llx,%llx,%llx,%llx,%llx,%llx,%llx,%llx", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7]) != 8) {
+                printf("refusing to run: COGNN_B200_KEY must hold eight comma-separated 32-bit hex words (e.g. from /dev/urandom)\n");
+                exit(-1);
+            }
+            for (int i = 0; i < 8; ++i) key[i] = (uint32_t)v[i];
+        }
         SSGcnEngine engine(comm.get(), cfg, CGB_SCALER_BITS, key);
         engine.verbose = true;
         std::cout << tileIndex << " Initialize graph algo kernel" << std::endl;

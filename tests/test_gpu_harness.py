@@ -43,13 +43,19 @@ def test_cli_runs_reference_inputs(tmp_path, shape, T, iters):
     write_config(prefix + "_config.txt", g["cfg"])
     exe = hb.build_harness()
     env = dict(os.environ, COGNN_B200_PLANE="loopback")
+    # the binary refuses to run until the caller acknowledges the dealer emulation and supplies the master key
+    r = subprocess.run([exe, "-t", str(T), "-g", str(T), "-i", "0", "-m", "1", "-r", "1", prefix + ".edge.preprocessed",
+                        prefix + ".vertex.preprocessed", prefix + ".part.preprocessed", prefix + ".result", prefix + "_config.txt"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode != 0 and "INSECURE" in r.stdout and "refusing to run" in r.stdout
+    env.update(COGNN_B200_ALLOW_INSECURE_EMULATION="1", COGNN_B200_KEY="2d,0,0,0,0,0,0,0")  # the key the Engine wrapper defaults to
     cmd = [exe, "-t", str(T), "-g", str(T), "-i", "0", "-m", str(iters), "-p", "1", "-s", "gcn-optimize/x/2p", "-c", "0", "-r", "1",
            prefix + ".edge.preprocessed", prefix + ".vertex.preprocessed", prefix + ".part.preprocessed", prefix + ".result",
            prefix + "_config.txt"]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     out = r.stdout
-    assert out.count("::iteration took") == iters and "::preprocess took" in out and "Finish algo kernel" in out
+    assert out.count("::iteration took") == iters and "::preprocess took" in out and "Finish algo kernel" in out and "INSECURE" in out
     acc = [float(x) for x in re.findall(r"full set accuracy = ([0-9.]+)", out)]
     e = eng.Engine(T, g["cfg"])
     e.load(g["edges"], g["tid"], g["feats"], g["labels"])

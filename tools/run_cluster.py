@@ -46,6 +46,8 @@ def main():
                "-r", "1", prefix + ".edge.preprocessed", prefix + ".vertex.preprocessed", prefix + ".part.preprocessed",
                prefix + ".result", prefix + "_config.txt"]
         env = dict(os.environ)
+        env.setdefault("COGNN_B200_ALLOW_INSECURE_EMULATION", "1")  # a benchmark driver: dealer emulation acknowledged
+        env.setdefault("COGNN_B200_KEY", "2d,0,0,0,0,0,0,0")
         if args.loopback:
             env["COGNN_B200_PLANE"] = "loopback"
         else:
