@@ -26,7 +26,7 @@ struct cgb_ctx {
     // limb planes of the tensor-core matmul (grow-only, per context = per device and stream) and its per-device attribute flags
     void* tc_planes = nullptr;
     size_t tc_planes_bytes = 0;
-    bool tc_attr_set = false, tc_mc_attr_set = false;
+    bool tc_attr_set = false, tc_mc_attr_set = false, tc_p_attr_set = false;
     std::vector<void*> retired;  // outgrown buffers, freed with the context (captured graphs may still reference them)
     // double-buffered staging for the pipelined host entry point (cgb_host_gather_sum_async)
     struct HostPipe {

@@ -278,6 +278,174 @@ __global__ void __launch_bounds__(192, 1) matmul_tc_kernel(const __grid_constant
     }
 }
 
+// ---- persistent form (round 2) -------------------------------------------------------------------------------------------------
+// The kernel above runs one tile per CTA: TMEM allocation, barrier set-up and the fill of the operand ring are paid per tile, and
+// the tensor pipe idles while the epilogue drains the 512 accumulator columns (ncu round 1: 54 % tensor-pipe active at K = 512,
+// far less at K = 128).  Here one CTA per SM walks over tiles (consecutive tiles share the A row block, so its planes stay in L2):
+//   * the TMA producer runs AHEAD across tile boundaries -- while tile i is in its epilogue the ring already holds the first
+//     k-steps of tile i + 1;
+//   * the epilogue first pulls ALL accumulators into registers (64 u64 per thread, two tcgen05.ld per wait), releases TMEM
+//     (acc_empty) and only then adds Z / truncates / stores, so the MMAs of tile i + 1 overlap the output phase of tile i;
+//   * the output goes through a padded shared-memory staging chunk so that a warp stores 2 x 128 contiguous bytes per
+//     instruction instead of 32 scattered 16-byte pieces (and reads Z / C the same way).
+constexpr uint32_t TC_EPI_STRIDE = 17;                                  // u64 per staged row (16 + 1 pad: 2-way bank conflicts at most)
+constexpr uint32_t TC_EPI_BYTES = TC_BM * TC_EPI_STRIDE * 8;            // one 128 x 16 chunk
+constexpr uint32_t TC_P_SMEM_BYTES = TC_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + TC_EPI_BYTES + 1024;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+struct TcPArgs {
+    TcArgs t;
+    uint32_t n_mb, n_nb;
+};
+
+__global__ void __launch_bounds__(192, 1) matmul_tc_persistent_kernel(const __grid_constant__ TcPArgs pa) {
+    const TcArgs& a = pa.t;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], acc_full, acc_empty;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + TC_STAGES * A_STAGE_BYTES;
+    u64* sE = reinterpret_cast<u64*>(smem + TC_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+    const uint32_t n_tiles = pa.n_mb * pa.n_nb;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(&acc_full), 1);
+        mbar_init(smem_u32(&acc_empty), 4);  // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_smem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer: one running stage counter over all tiles of this CTA =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const uint32_t mb = tile / pa.n_nb, nb = tile - mb * pa.n_nb;
+                const uint8_t* gA = a.A + (size_t)mb * a.n_ksteps * A_STAGE_BYTES;
+                const uint8_t* gB = a.B + (size_t)nb * a.n_ksteps * B_STAGE_BYTES;
+                for (uint32_t ks = 0; ks < a.n_ksteps; ++ks, ++it) {
+                    const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+                    mbar_expect_tx(smem_u32(&full_bar[s]), A_STAGE_BYTES + B_STAGE_BYTES);
+                    bulk_g2s(smem_u32(sA + s * A_STAGE_BYTES), gA + (size_t)ks * A_STAGE_BYTES, A_STAGE_BYTES, smem_u32(&full_bar[s]));
+                    bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), gB + (size_t)ks * B_STAGE_BYTES, B_STAGE_BYTES, smem_u32(&full_bar[s]));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc0 = (2u << 4) | ((uint32_t)(TC_BM >> 4) << 24);
+            uint32_t it = 0, j = 0;
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+                mbar_wait(smem_u32(&acc_empty), (j & 1) ^ 1);  // the epilogue has read the previous tile out of TMEM
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (uint32_t ks = 0; ks < a.n_ksteps; ++ks, ++it) {
+                    const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                    mbar_wait(smem_u32(&full_bar[s]), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a0 = smem_u32(sA + s * A_STAGE_BYTES), b0 = smem_u32(sB + s * B_STAGE_BYTES);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint64_t da = smem_desc(a0 + i * A_PLANE_BYTES, TC_BM * 16, 128);
+#pragma unroll
+                        for (int j0 = 0; j0 + i < 8; j0 += 4) {
+                            const int planes = (8 - i - j0) < 4 ? (8 - i - j0) : 4;
+                            const uint32_t n = (uint32_t)planes * TC_BN;
+                            const uint64_t db = smem_desc(b0 + (uint32_t)j0 * TC_BN * 16, 8 * TC_BN * 16, 128);
+                            tc_mma_i8(tmem_base + (uint32_t)(i + j0) * TC_BN, da, db, idesc0 | ((n >> 3) << 17), (ks > 0 || i > 0) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(smem_u32(&empty_bar[s]));
+                }
+                tc_commit(smem_u32(&acc_full));
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5 =====
+        const uint32_t q = warp & 3;                  // TMEM lane quarter this warp may read
+        const uint32_t et = q * 32 + lane;            // 0..127: row of the tile this thread drains
+        const uint32_t lane_addr = tmem_base + ((q * 32) << 16);
+        uint32_t j = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+            const uint32_t mb = tile / pa.n_nb, nb = tile - mb * pa.n_nb;
+            mbar_wait(smem_u32(&acc_full), j & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            u64 acc[TC_BN];
+#pragma unroll
+            for (int c = 0; c < TC_BN; ++c) acc[c] = 0;
+#pragma unroll
+            for (int c = 0; c < TC_BN / 16; ++c) {
+#pragma unroll
+                for (int d = 0; d < 8; d += 2) {
+                    uint32_t r0[16], r1[16];
+                    const uint32_t t0 = lane_addr + (uint32_t)(d * TC_BN + c * 16), t1 = t0 + TC_BN;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]), "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]), "=r"(r0[8]),
+                          "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11]), "=r"(r0[12]), "=r"(r0[13]), "=r"(r0[14]), "=r"(r0[15])
+                        : "r"(t0));
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]),
+                          "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15])
+                        : "r"(t1));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        acc[c * 16 + k] += ((u64)r0[k] << (8 * d)) + ((u64)r1[k] << (8 * (d + 1)));
+                }
+            }
+            // TMEM is drained: hand it back before the output phase
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_empty));
+            // output phase, 16 columns at a time through the staging chunk
+#pragma unroll
+            for (int c = 0; c < TC_BN / 16; ++c) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) sE[et * TC_EPI_STRIDE + k] = acc[c * 16 + k];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t row = (et >> 4) + 8 * i, col = et & 15;
+                    const uint32_t gm = mb * TC_BM + row, gn = nb * TC_BN + c * 16 + col;
+                    if (gm < a.M && gn < a.N) {
+                        const size_t o = (size_t)gm * a.N + gn;
+                        u64 v = sE[row * TC_EPI_STRIDE + col];
+                        if (a.Z) v += a.Z[o];
+                        if (a.accumulate) v += a.C[o];
+                        a.C[o] = trunc_share(v, a.f, a.share);
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 // ---- pipe-ceiling probe ------------------------------------------------------------------------------------------------
 // The same 12 tcgen05.mma per k-step as matmul_tc_kernel (36 limb products, M = 128, N = 64..256, K = 32), issued back to back
 // on whatever the (zeroed) shared memory holds: no TMA, no epilogue.  One CTA per SM.  Its rate is the denominator of the
@@ -530,6 +698,24 @@ static int tc_chunk(cgb_ctx* ctx, const u64* const A[2], const u64* const B[2], 
         return CGB_OK;
     }
 #endif
+    static const bool one_tile_per_cta = getenv("CGB_MATMUL_TC_V1") != nullptr;  // round-1 kernel, kept for A/B
+    if (!one_tile_per_cta) {
+        if (!ctx->tc_p_attr_set) {
+            CGB_CHECK_CUDA(ctx, cudaFuncSetAttribute(matmul_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)TC_P_SMEM_BYTES));
+            ctx->tc_p_attr_set = true;
+        }
+        TcPArgs pa;
+        pa.t = a;
+        pa.n_mb = Mpad / TC_BM;
+        pa.n_nb = Npad / TC_BN;
+        const uint32_t n_tiles = pa.n_mb * pa.n_nb;
+        const unsigned ctas = (unsigned)std::min<uint32_t>(n_tiles, (uint32_t)ctx->num_sms);
+        matmul_tc_persistent_kernel<<<ctas, 192, TC_P_SMEM_BYTES, ctx->stream>>>(pa);
+        CGB_CHECK_LAUNCH(ctx, "matmul_tc_persistent_kernel");
+        ctx->last_kernel = "matmul_tc_persistent_kernel (tcgen05 kind::i8 limbs, TMEM diagonals, one CTA per SM) + limb_split_{rows,cols}_kernel";
+        return CGB_OK;
+    }
     matmul_tc_kernel<<<grid, 192, TC_SMEM_BYTES, ctx->stream>>>(a);
     CGB_CHECK_LAUNCH(ctx, "matmul_tc_kernel");
     ctx->last_kernel = "matmul_tc_kernel (tcgen05 kind::i8 limbs, TMEM diagonals) + limb_split_{rows,cols}_kernel";
