@@ -90,6 +90,11 @@ int cgb_ctx_destroy(cgb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->tc_planes) cudaFree(ctx->tc_planes);
+    if (ctx->tc_aux) {
+        cudaStreamSynchronize(ctx->tc_aux);
+        cudaStreamDestroy(ctx->tc_aux);
+        for (int i = 0; i < 9; ++i) cudaEventDestroy(ctx->tc_ev[i]);
+    }
     for (void* p : ctx->retired) cudaFree(p);
     if (ctx->pipe.ready) {
         cudaStreamSynchronize(ctx->pipe.h2d);

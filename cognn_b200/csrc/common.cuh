@@ -27,6 +27,8 @@ struct cgb_ctx {
     void* tc_planes = nullptr;
     size_t tc_planes_bytes = 0;
     bool tc_attr_set = false, tc_mc_attr_set = false, tc_p_attr_set = false;
+    cudaStream_t tc_aux = nullptr;  // limb split of the next row group runs here, beside the tensor kernel of the current one
+    cudaEvent_t tc_ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<void*> retired;  // outgrown buffers, freed with the context (captured graphs may still reference them)
     // double-buffered staging for the pipelined host entry point (cgb_host_gather_sum_async)
     struct HostPipe {

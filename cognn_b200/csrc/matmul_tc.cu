@@ -670,13 +670,79 @@ static int tc_chunk(cgb_ctx* ctx, const u64* const A[2], const u64* const B[2], 
     }
     uint8_t* dA = (uint8_t*)ctx->tc_planes;
     uint8_t* dB = dA + ((a_bytes + 255) & ~(size_t)255);
+    static const bool one_tile_per_cta = getenv("CGB_MATMUL_TC_V1") != nullptr;  // round-1 kernel, kept for A/B
+    // B planes first (small), on the main stream
     for (int p = 0; p < n_pairs; ++p) {
-        const uint64_t ta = (uint64_t)Mpad * ks_pair * 2, tb = (uint64_t)Npad * ks_pair * 2;
-        limb_split_rows_kernel<<<(unsigned)((ta + 255) / 256), 256, 0, ctx->stream>>>(A[p], dA, M, K, lda, Mpad, p * ks_pair, n_ksteps, ks_pair,
-                                                                                     transA);
-        CGB_CHECK_LAUNCH(ctx, "limb_split_rows_kernel");
+        const uint64_t tb = (uint64_t)Npad * ks_pair * 2;
         limb_split_cols_kernel<<<(unsigned)((tb + 255) / 256), 256, 0, ctx->stream>>>(B[p], dB, K, N, Npad, p * ks_pair, n_ksteps, ks_pair);
         CGB_CHECK_LAUNCH(ctx, "limb_split_cols_kernel");
+    }
+    // Row groups: the limb split of A is HBM work (8 bytes read + 8 written per element), the tensor kernel is tensor-pipe work
+    // that mostly re-reads planes out of L2; with the rows cut into groups, the split of group g + 1 runs on an auxiliary stream
+    // beside the tensor kernel of group g (it needs no shared memory and fits next to the one persistent CTA per SM), so only
+    // the first group's split is exposed.  Round 1 ran the whole split first: 1.75 of 10.3 ms at 2^20 x 512 x 512.
+    const uint32_t n_mb_all = Mpad / TC_BM;
+    uint32_t n_groups = 1;
+    if (!one_tile_per_cta && n_mb_all >= 8u * (uint32_t)ctx->num_sms) n_groups = std::min<uint32_t>(8, n_mb_all / (2u * (uint32_t)ctx->num_sms));
+    if (n_groups > 1 && !ctx->tc_aux) {
+        CGB_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->tc_aux, cudaStreamNonBlocking));
+        for (int i = 0; i < 9; ++i) CGB_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->tc_ev[i], cudaEventDisableTiming));
+    }
+    const uint32_t mb_per_group = (n_mb_all + n_groups - 1) / n_groups;
+    auto split_rows = [&](cudaStream_t st, uint32_t mb0, uint32_t mb1) -> int {
+        const uint32_t r0 = mb0 * TC_BM, rows = std::min(M, mb1 * TC_BM) - r0, rows_pad = (mb1 - mb0) * TC_BM;
+        for (int p = 0; p < n_pairs; ++p) {
+            const u64* src = transA ? A[p] + r0 : A[p] + (size_t)r0 * lda;
+            const uint64_t ta = (uint64_t)rows_pad * ks_pair * 2;
+            limb_split_rows_kernel<<<(unsigned)((ta + 255) / 256), 256, 0, st>>>(src, dA + (size_t)mb0 * n_ksteps * A_STAGE_BYTES, rows, K, lda,
+                                                                                rows_pad, p * ks_pair, n_ksteps, ks_pair, transA);
+            CGB_CHECK_LAUNCH(ctx, "limb_split_rows_kernel");
+        }
+        return CGB_OK;
+    };
+    if (n_groups > 1) {
+        if (!ctx->tc_p_attr_set) {
+            CGB_CHECK_CUDA(ctx, cudaFuncSetAttribute(matmul_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)TC_P_SMEM_BYTES));
+            ctx->tc_p_attr_set = true;
+        }
+        // fork: the auxiliary stream starts after everything queued so far (the planes buffer may still be read by an earlier launch)
+        CGB_CHECK_CUDA(ctx, cudaEventRecord(ctx->tc_ev[8], ctx->stream));
+        CGB_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->tc_aux, ctx->tc_ev[8], 0));
+        for (uint32_t g = 0; g < n_groups; ++g) {
+            const uint32_t mb0 = g * mb_per_group, mb1 = std::min(n_mb_all, mb0 + mb_per_group);
+            if (mb0 >= mb1) break;
+            int rc = split_rows(ctx->tc_aux, mb0, mb1);
+            if (rc) return rc;
+            CGB_CHECK_CUDA(ctx, cudaEventRecord(ctx->tc_ev[g], ctx->tc_aux));
+        }
+        for (uint32_t g = 0; g < n_groups; ++g) {
+            const uint32_t mb0 = g * mb_per_group, mb1 = std::min(n_mb_all, mb0 + mb_per_group);
+            if (mb0 >= mb1) break;
+            CGB_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->tc_ev[g], 0));  // join: group g's planes are written
+            const uint32_t r0 = mb0 * TC_BM;
+            TcPArgs pa;
+            pa.t.A = dA + (size_t)mb0 * n_ksteps * A_STAGE_BYTES;
+            pa.t.B = dB;
+            pa.t.Z = Z ? Z + (size_t)r0 * N : nullptr;
+            pa.t.C = C + (size_t)r0 * N;
+            pa.t.M = std::min(M, mb1 * TC_BM) - r0;
+            pa.t.N = N;
+            pa.t.n_ksteps = n_ksteps;
+            pa.t.f = f; pa.t.share = share; pa.t.accumulate = accumulate;
+            pa.n_mb = mb1 - mb0;
+            pa.n_nb = Npad / TC_BN;
+            const unsigned ctas = (unsigned)std::min<uint32_t>(pa.n_mb * pa.n_nb, (uint32_t)ctx->num_sms);
+            matmul_tc_persistent_kernel<<<ctas, 192, TC_P_SMEM_BYTES, ctx->stream>>>(pa);
+            CGB_CHECK_LAUNCH(ctx, "matmul_tc_persistent_kernel");
+        }
+        ctx->last_kernel = "matmul_tc_persistent_kernel (tcgen05 kind::i8 limbs, TMEM diagonals, one CTA per SM; row groups, limb split of "
+                           "the next group overlapped) + limb_split_{rows,cols}_kernel";
+        return CGB_OK;
+    }
+    {
+        int rc = split_rows(ctx->stream, 0, n_mb_all);
+        if (rc) return rc;
     }
     if (!ctx->tc_attr_set) {  // a per-device attribute: set once per context, not once per process
         CGB_CHECK_CUDA(ctx, cudaFuncSetAttribute(matmul_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
@@ -698,7 +764,6 @@ static int tc_chunk(cgb_ctx* ctx, const u64* const A[2], const u64* const B[2], 
         return CGB_OK;
     }
 #endif
-    static const bool one_tile_per_cta = getenv("CGB_MATMUL_TC_V1") != nullptr;  // round-1 kernel, kept for A/B
     if (!one_tile_per_cta) {
         if (!ctx->tc_p_attr_set) {
             CGB_CHECK_CUDA(ctx, cudaFuncSetAttribute(matmul_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
