@@ -677,13 +677,16 @@ static int tc_chunk(cgb_ctx* ctx, const u64* const A[2], const u64* const B[2], 
         limb_split_cols_kernel<<<(unsigned)((tb + 255) / 256), 256, 0, ctx->stream>>>(B[p], dB, K, N, Npad, p * ks_pair, n_ksteps, ks_pair);
         CGB_CHECK_LAUNCH(ctx, "limb_split_cols_kernel");
     }
-    // Row groups: the limb split of A is HBM work (8 bytes read + 8 written per element), the tensor kernel is tensor-pipe work
-    // that mostly re-reads planes out of L2; with the rows cut into groups, the split of group g + 1 runs on an auxiliary stream
-    // beside the tensor kernel of group g (it needs no shared memory and fits next to the one persistent CTA per SM), so only
-    // the first group's split is exposed.  Round 1 ran the whole split first: 1.75 of 10.3 ms at 2^20 x 512 x 512.
+    // Row groups (EXPERIMENT, off by default; CGB_MATMUL_TC_GROUPS=1): the limb split of A is HBM work, the tensor kernel is
+    // tensor-pipe work, so the split of group g + 1 could run on an auxiliary stream beside the tensor kernel of group g.
+    // Measured (profiles/r2k_matmul.json vs r2j_matmul.json): SLOWER -- 9.79 vs 8.28 ms at 2^20 x 512 x 512 -- the split's CTAs
+    // take issue slots and L2 bandwidth from the persistent tensor CTAs and every group adds a kernel tail.  The split therefore
+    // runs first, on the main stream (1.7 ms of the 8.3).
     const uint32_t n_mb_all = Mpad / TC_BM;
     uint32_t n_groups = 1;
-    if (!one_tile_per_cta && n_mb_all >= 8u * (uint32_t)ctx->num_sms) n_groups = std::min<uint32_t>(8, n_mb_all / (2u * (uint32_t)ctx->num_sms));
+    static const bool want_groups = getenv("CGB_MATMUL_TC_GROUPS") != nullptr;
+    if (want_groups && !one_tile_per_cta && n_mb_all >= 8u * (uint32_t)ctx->num_sms)
+        n_groups = std::min<uint32_t>(8, n_mb_all / (2u * (uint32_t)ctx->num_sms));
     if (n_groups > 1 && !ctx->tc_aux) {
         CGB_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->tc_aux, cudaStreamNonBlocking));
         for (int i = 0; i < 9; ++i) CGB_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->tc_ev[i], cudaEventDisableTiming));
