@@ -213,6 +213,10 @@ static uint64_t stream_id(uint64_t kind, uint64_t it, uint64_t owner, uint64_t s
 struct Side {
     int owner = 0, share = 0, peer = 0;
     uint32_t n = 0;
+    // a stream (context) of its own: between two exchanges the sides a process hosts are independent, so their kernels form
+    // parallel branches of the iteration's CUDA graph instead of one dependent chain (COGNN_B200_BRANCHES=0: one chain)
+    cgb_ctx* sctx = nullptr;
+    cudaEvent_t done = nullptr;
     DMat X, X_backup, W[2], h_t[2], z[2], g;
     // per-iteration temporaries
     DMat Xp, V, Y, m, tmp, tmp2;
@@ -241,7 +245,16 @@ struct PartyData {
 
 struct SSGcnEngine::Impl {
     Comm* comm;
-    cgb_ctx* ctx;
+    cgb_ctx* ctx;             // the context kernels are issued on RIGHT NOW: the main one, or a side's inside for_sides
+    cgb_ctx* main_ctx = nullptr;
+    bool branches = !(getenv("COGNN_B200_BRANCHES") && atoi(getenv("COGNN_B200_BRANCHES")) == 0);
+    cudaEvent_t fork_ev = nullptr;
+    std::vector<cgb_ctx*> side_ctxs;
+    uint64_t total_launches() const {
+        uint64_t n = cgb_ctx_launch_count(main_ctx);
+        for (cgb_ctx* c : side_ctxs) n += cgb_ctx_launch_count(c);
+        return n;
+    }
     GNNConfig cfg;
     int f;
     uint32_t key[8];
@@ -418,9 +431,36 @@ struct SSGcnEngine::Impl {
     // run `fn(side)` for every locally hosted side in the canonical order (owner 0 share 0, owner 0 share 1, ...)
     template <typename Fn>
     void for_sides(Fn&& fn) {
+        if (!branches || !fork_ev || ctx != main_ctx) {  // one chain (also: nested call, or before setup created the streams)
+            for (int o = 0; o < T; ++o)
+                for (int sh = 0; sh < 2; ++sh)
+                    if (Side* s = side(o, sh)) fn(*s);
+            return;
+        }
+        // fork: every side's stream continues after what the main stream has queued so far; join: the main stream (exchanges,
+        // weight averaging, the next fork) continues after every side.  Under stream capture this records parallel branches.
+        cudaStream_t ms = (cudaStream_t)cgb_ctx_stream(main_ctx);
+        if (cudaEventRecord(fork_ev, ms) != cudaSuccess) throw std::runtime_error("for_sides: cudaEventRecord failed");
         for (int o = 0; o < T; ++o)
             for (int sh = 0; sh < 2; ++sh)
-                if (Side* s = side(o, sh)) fn(*s);
+                if (Side* s = side(o, sh)) {
+                    if (!s->sctx) {  // no stream for this side (should not happen after setup): run it on the main one
+                        fn(*s);
+                        continue;
+                    }
+                    cudaStream_t st = (cudaStream_t)cgb_ctx_stream(s->sctx);
+                    if (cudaStreamWaitEvent(st, fork_ev, 0) != cudaSuccess) throw std::runtime_error("for_sides: fork failed");
+                    ctx = s->sctx;
+                    try {
+                        fn(*s);
+                    } catch (...) {
+                        ctx = main_ctx;
+                        throw;
+                    }
+                    ctx = main_ctx;
+                    if (cudaEventRecord(s->done, st) != cudaSuccess || cudaStreamWaitEvent(ms, s->done, 0) != cudaSuccess)
+                        throw std::runtime_error("for_sides: join failed");
+                }
     }
 
     // a full two-party row scaling of `x` (both sides), result in `out` chosen by the accessor
@@ -672,7 +712,7 @@ struct SSGcnEngine::Impl {
 SSGcnEngine::SSGcnEngine(Comm* comm, const GNNConfig& cfg, int f, const uint32_t key[8]) {
     impl_ = new Impl();
     impl_->comm = comm;
-    impl_->ctx = comm->ctx();
+    impl_->ctx = impl_->main_ctx = comm->ctx();
     impl_->cfg = cfg;
     impl_->f = f;
     memcpy(impl_->key, key, sizeof(impl_->key));
@@ -682,7 +722,7 @@ SSGcnEngine::SSGcnEngine(Comm* comm, const GNNConfig& cfg, int f, const uint32_t
     impl_->C = cfg.num_labels;
     if (cfg.num_layers != 2) throw std::runtime_error("SSGcnEngine: the reference operators hard-code 2 layers (gcn.h:898-927)");
     if (f <= 0 || f >= 31) throw std::runtime_error("SSGcnEngine: SCALER_BIT_LENGTH must be in (0, 31) (gcn.h:191)");
-    cgb_ctx* ctx = impl_->ctx;
+    cgb_ctx* ctx = impl_->main_ctx;
     void* p = nullptr;
     ck(ctx, cgb_malloc(ctx, 8, &p), "cgb_malloc");
     impl_->d_bias = (uint64_t*)p;
@@ -712,6 +752,18 @@ SSGcnEngine::~SSGcnEngine() {
         if (kv.second.csr) cgb_csr_destroy(impl_->ctx, kv.second.csr);
         if (kv.second.d_labels) cgb_free(impl_->ctx, kv.second.d_labels);
     }
+    // the sides' buffers were allocated through (and remember) their side contexts: release them first
+    for (cgb_ctx* c : impl_->side_ctxs) cgb_ctx_sync(c);
+    for (auto* m : {&impl_->own, &impl_->hlp})
+        for (auto& kv : *m)
+            if (kv.second.done) cudaEventDestroy(kv.second.done);
+    impl_->own.clear();
+    impl_->hlp.clear();
+    for (int l = 0; l < 2; ++l) {
+        impl_->wa_rx_own[l].clear(); impl_->wa_rx_hlp[l].clear(); impl_->wa_rxA0[l].clear(); impl_->wa_rxA1[l].clear();
+    }
+    for (cgb_ctx* c : impl_->side_ctxs) cgb_ctx_destroy(c);
+    if (impl_->fork_ev) cudaEventDestroy(impl_->fork_ev);
     delete impl_;
 }
 
@@ -763,7 +815,7 @@ static std::vector<double> init_weight(int d0, int d1) {
 
 void SSGcnEngine::setup() {
     Impl& im = *impl_;
-    cgb_ctx* ctx = im.ctx;
+    cgb_ctx*& ctx = im.ctx;  // follows the side contexts inside for_sides
     const int T = im.T;
     const uint32_t dims[3] = {im.F, im.H, im.C};
     std::vector<double> Wp[2] = {init_weight(im.F, im.H), init_weight(im.H, im.C)};
@@ -822,8 +874,19 @@ void SSGcnEngine::setup() {
         }
         im.comm->exchange();  // ssk.h:231-232
     }
+    if (im.branches && cgb_ctx_stream(im.main_ctx) != nullptr) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        im.for_sides([&](Side& s) {  // (still sequential here: fork_ev does not exist yet)
+            if (cgb_ctx_create(dev, &s.sctx) != CGB_OK) throw std::runtime_error("setup: side context creation failed");
+            ck(s.sctx, cgb_ctx_set_prg_stream_bias(s.sctx, im.d_bias), "cgb_ctx_set_prg_stream_bias");
+            if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) throw std::runtime_error("setup: event creation failed");
+            im.side_ctxs.push_back(s.sctx);
+        });
+        if (cudaEventCreateWithFlags(&im.fork_ev, cudaEventDisableTiming) != cudaSuccess) throw std::runtime_error("setup: event creation failed");
+    }
     im.for_sides([&](Side& s) { s.X_backup.copy_from(s.X); });  // ssk.h:226-227
-    ck(ctx, cgb_ctx_sync(ctx), "sync");
+    ck(im.main_ctx, cgb_ctx_sync(im.main_ctx), "sync");
 }
 
 static DMat* sel_V(Side& s, int) { return &s.V; }
@@ -834,7 +897,7 @@ static DMat* sel_Xz0(Side& s, int k) { return k == 0 ? &s.X : &s.z[0]; }
 // online phase of iteration `it` (everything after the dealer hand-out): only stream-ordered work, no allocation once the
 // buffers have their final sizes, no host synchronisation -- so it can be recorded into a CUDA graph
 static void online_iteration(SSGcnEngine::Impl& im, uint64_t it) {
-    cgb_ctx* ctx = im.ctx;
+    cgb_ctx*& ctx = im.ctx;  // follows the side contexts inside for_sides
     const uint32_t F = im.F, H = im.H, C = im.C;
     const int ph = (int)(it % 6);
     if (ph == 0) im.for_sides([&](Side& s) { s.X.copy_from(s.X_backup); });  // ssk.h:695, 938
@@ -981,7 +1044,7 @@ static void ckc(cudaError_t e, const char* what) {
 template <typename Body>
 static void run_phase(SSGcnEngine::Impl& im, cudaStream_t stream, bool use_graph, SSGcnEngine::Impl::IterGraph& ig, bool online,
                       Body&& body) {
-    cgb_ctx* ctx = im.ctx;
+    (void)im;
     if (!use_graph) {
         body();
         return;
@@ -1000,7 +1063,7 @@ static void run_phase(SSGcnEngine::Impl& im, cudaStream_t stream, bool use_graph
         });
         return;
     }
-    const uint64_t l0 = cgb_ctx_launch_count(ctx), w0 = im.comm->words_sent, r0 = im.comm->rounds;
+    const uint64_t l0 = im.total_launches(), w0 = im.comm->words_sent, r0 = im.comm->rounds;
     cudaGraph_t g = nullptr;
     ckc(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
     g_capturing = true;
@@ -1016,7 +1079,7 @@ static void run_phase(SSGcnEngine::Impl& im, cudaStream_t stream, bool use_graph
     ckc(cudaStreamEndCapture(stream, &g), "cudaStreamEndCapture");
     ckc(cudaGraphInstantiate(&ig.exec, g, 0), "cudaGraphInstantiate");
     cudaGraphDestroy(g);
-    ig.launches = cgb_ctx_launch_count(ctx) - l0;  // counted once while recording = the launch right below
+    ig.launches = im.total_launches() - l0;  // counted once while recording = the launch right below
     ig.words = im.comm->words_sent - w0;
     ig.rounds = im.comm->rounds - r0;
     ig.shapes.clear();
@@ -1027,7 +1090,7 @@ static void run_phase(SSGcnEngine::Impl& im, cudaStream_t stream, bool use_graph
 
 void SSGcnEngine::run(uint64_t n_iters) {
     Impl& im = *impl_;
-    cgb_ctx* ctx = im.ctx;
+    cgb_ctx* ctx = im.main_ctx;
     cudaStream_t stream = (cudaStream_t)cgb_ctx_stream(ctx);
     for (uint64_t step = 0; step < n_iters; ++step, ++iter_) {
         const uint64_t it = iter_;
@@ -1061,6 +1124,7 @@ void SSGcnEngine::run(uint64_t n_iters) {
 
 double SSGcnEngine::seconds_residual_host() const { return 0.0; }  // the stand-ins run on the device since round 1b
 uint64_t SSGcnEngine::replayed_launches() const { return impl_->replayed_launches; }
+uint64_t SSGcnEngine::eager_launches() const { return impl_->total_launches(); }
 uint64_t SSGcnEngine::graph_replays() const { return impl_->graph_replays; }
 
 std::vector<uint64_t> SSGcnEngine::download(int owner, int role, const std::string& name, uint32_t* rows, uint32_t* cols) {

@@ -101,6 +101,7 @@ public:
     double seconds_residual_host() const;   // 0: kept for the C ABI (the stand-ins moved to the device)
     // kernels that ran inside replayed CUDA graphs of the online phase (not seen by cgb_ctx_launch_count), and replays
     uint64_t replayed_launches() const;
+    uint64_t eager_launches() const;  // kernels launched outside graph replays, over the main and all side streams
     uint64_t graph_replays() const;
 
     struct Impl;
