@@ -464,7 +464,7 @@ def matmul_record(torch, ctx, dev, shapes=((128, 128), (256, 256), (512, 512), (
                          "frac_of_pipe": rate / imad_peak if impl == "imad" else rate * 36.0 / tensor_peak}
         ctx.set_matmul_impl("auto")
         ctx.matmul(A, B, out=C)
-        row["auto_picks"] = "tc" if "tc_kernel" in ctx.last_kernel else "imad"
+        row["auto_picks"] = "tc" if "matmul_tc" in ctx.last_kernel else "imad"
         rows.append(row)
         del A, B, C
     ctx.set_matmul_impl(None)
