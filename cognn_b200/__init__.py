@@ -292,6 +292,16 @@ class Context:
                                                      _ptr(out), M, K, N, share, f))
         return out
 
+    def beaver_matmul_finish_open(self, mine, peer, U, V, Z, share, f=SCALER_BITS):
+        """`mine` ([E_i | F_i] flat) is opened in place."""
+        M, K = U.shape
+        N = V.shape[1]
+        out = self.empty(M, N)
+        self.check(self.lib.cgb_beaver_matmul_finish_open(self.handle, _ptr(self._u64(mine)), _ptr(self._u64(peer)),
+                                                          _ptr(self._u64(U)), _ptr(self._u64(V)), _ptr(self._u64(Z)),
+                                                          _ptr(out), M, K, N, share, f))
+        return out
+
     # -- (3) elementwise ---------------------------------------------------------------------------------------
     def add(self, a, b, out=None):
         out = self.torch.empty_like(a) if out is None else out
@@ -334,6 +344,50 @@ class Context:
                                                      _ptr(self._u64(a)), _ptr(self._u64(b)), _ptr(self._u64(c)),
                                                      _ptr(out), rows, D, share, f))
         return out
+
+    def rowmul_beaver_finish_open(self, mine, peer, a, b, c, share, f=SCALER_BITS, out=None):
+        """`mine`, `peer`: the two halves of the opening, flat [rows * D | rows] words each."""
+        rows, D = a.shape
+        out = self.torch.empty_like(a) if out is None else out
+        self.check(self.lib.cgb_rowmul_beaver_finish_open(self.handle, _ptr(self._u64(mine)), _ptr(self._u64(peer)),
+                                                          _ptr(self._u64(a)), _ptr(self._u64(b)), _ptr(self._u64(c)),
+                                                          _ptr(out), rows, D, share, f))
+        return out
+
+    def sub_pair(self, a0, b0, a1, b1, out=None):
+        """out = [a0 - b0 | a1 - b1] flat; a1 None means 0 - b1."""
+        n0, n1 = a0.numel(), b1.numel()
+        out = self.empty(n0 + n1) if out is None else out
+        self.check(self.lib.cgb_sub_pair(self.handle, _ptr(self._u64(a0)), _ptr(self._u64(b0)), n0,
+                                         _ptr(self._u64(a1)) if a1 is not None else None, _ptr(self._u64(b1)), n1, _ptr(out)))
+        return out
+
+    def scale_apply_gradient(self, W, d, gs, lr, share, f=SCALER_BITS):
+        """In place: d <- trunc(d * gs), W <- W - trunc(d * lr)."""
+        m = 2**64 - 1
+        self.check(self.lib.cgb_scale_apply_gradient(self.handle, _ptr(self._u64(W)), _ptr(self._u64(d)), C.c_uint64(gs & m),
+                                                     C.c_uint64(lr & m), _ptr(d), _ptr(W), W.numel(), f, share))
+        return W
+
+    def avg_public(self, tensors, c, outs, share, f=SCALER_BITS):
+        ni, no = len(tensors), len(outs)
+        ip = (C.c_void_p * ni)(*[C.c_void_p(self._u64(t).data_ptr()) for t in tensors])
+        op = (C.c_void_p * no)(*[C.c_void_p(self._u64(t).data_ptr()) for t in outs])
+        self.check(self.lib.cgb_avg_public(self.handle, ip, ni, C.c_uint64(c & (2**64 - 1)), op, no, tensors[0].numel(), f, share))
+
+    def ideal_relu_reshare(self, key, stream, a0, a1, z0=None, z1=None, out=None):
+        out = self.torch.empty_like(a0) if out is None else out
+        self.check(self.lib.cgb_ideal_relu_reshare(self.handle, _lib.key_array(key), stream, _ptr(self._u64(a0)),
+                                                   _ptr(self._u64(a1)), _ptr(z0), _ptr(z1), _ptr(out), a0.numel()))
+        return out
+
+    def copy_segments(self, dsts, srcs):
+        """dsts[j][:] = srcs[j][:] for every j, one launch per 16 segments."""
+        n = len(dsts)
+        dp = (C.c_void_p * max(n, 1))(*[C.c_void_p(self._u64(t).data_ptr()) for t in dsts])
+        sp = (C.c_void_p * max(n, 1))(*[C.c_void_p(self._u64(t).data_ptr()) for t in srcs])
+        nw = (C.c_uint64 * max(n, 1))(*[t.numel() for t in srcs])
+        self.check(self.lib.cgb_copy_segments(self.handle, dp, sp, nw, n))
 
     def cond_add(self, v, u, cond, out=None):
         rows, D = v.shape
@@ -403,6 +457,16 @@ class Context:
         if out is None:
             out = self.empty(n_words)
         self.check(self.lib.cgb_prg_fill(self.handle, _lib.key_array(key), stream, word_offset, _ptr(out), n_words))
+        return out
+
+    def prg_sum(self, key, streams, tensors, n_words=None, out=None):
+        """out = sum(tensors) + sum_k PRG(key, streams[k]) (word offset 0)."""
+        n = n_words if n_words is not None else tensors[0].numel()
+        out = self.empty(n) if out is None else out
+        ns, ni = len(streams), len(tensors)
+        st = (C.c_uint64 * max(ns, 1))(*[int(x) & (2**64 - 1) for x in streams])
+        ptrs = (C.c_void_p * max(ni, 1))(*[C.c_void_p(self._u64(t).data_ptr()) for t in tensors])
+        self.check(self.lib.cgb_prg_sum(self.handle, _lib.key_array(key), st, ns, ptrs, ni, _ptr(out), n))
         return out
 
     def prg_mask_sub(self, key, stream, word_offset, x, out=None):

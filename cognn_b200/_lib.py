@@ -93,6 +93,17 @@ SIGNATURES = {
     "cgb_apply_gradient": (C.c_int, [ctx_p, u64p, u64p, C.c_uint64, u64p, C.c_uint64, C.c_int, C.c_int]),
     "cgb_rowmul_beaver_finish": (C.c_int, [ctx_p, u64p, u64p, u64p, u64p, u64p, u64p, C.c_uint64, C.c_uint32,
                                            C.c_int, C.c_int]),
+    "cgb_rowmul_beaver_finish_open": (C.c_int, [ctx_p, u64p, u64p, u64p, u64p, u64p, u64p, C.c_uint64, C.c_uint32,
+                                                C.c_int, C.c_int]),
+    "cgb_sub_pair": (C.c_int, [ctx_p, u64p, u64p, C.c_uint64, u64p, u64p, C.c_uint64, u64p]),
+    "cgb_beaver_matmul_finish_open": (C.c_int, [ctx_p, u64p, u64p, u64p, u64p, u64p, u64p, C.c_uint32, C.c_uint32,
+                                                C.c_uint32, C.c_int, C.c_int]),
+    "cgb_prg_sum": (C.c_int, [ctx_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p, C.c_uint32, u64p,
+                              C.c_uint64]),
+    "cgb_scale_apply_gradient": (C.c_int, [ctx_p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u64p, C.c_uint64, C.c_int, C.c_int]),
+    "cgb_avg_public": (C.c_int, [ctx_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_int]),
+    "cgb_ideal_relu_reshare": (C.c_int, [ctx_p, C.POINTER(C.c_uint32), C.c_uint64, u64p, u64p, u64p, u64p, u64p, C.c_uint64]),
+    "cgb_copy_segments": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32]),
     "cgb_cond_add": (C.c_int, [ctx_p, u64p, u64p, C.c_void_p, u64p, C.c_uint64, C.c_uint32]),
     "cgb_transpose": (C.c_int, [ctx_p, u64p, u64p, C.c_uint32, C.c_uint32]),
     "cgb_encode": (C.c_int, [ctx_p, C.c_void_p, u64p, C.c_uint64, C.c_int]),

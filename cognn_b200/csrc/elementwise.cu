@@ -83,6 +83,104 @@ __global__ void __launch_bounds__(EW_THREADS) rowmul_finish_kernel(const u64* e,
     }
 }
 
+// the same recombination reading the two halves of the opening straight from the wire buffers: e = mine + peer (rows x D,
+// then the `rows` scaler words), so the separate "open" pass over the message disappears
+__global__ void __launch_bounds__(EW_THREADS) rowmul_finish_open_kernel(const u64* __restrict__ mine, const u64* __restrict__ peer,
+                                                                       const u64* __restrict__ a, const u64* __restrict__ b,
+                                                                       const u64* __restrict__ c, u64* out, uint64_t rows,
+                                                                       uint32_t D, int share, int f) {
+    const uint64_t n = rows * D;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t r = i / D;
+        const u64 fr = __ldg(mine + n + r) + __ldg(peer + n + r), br = __ldg(b + r);
+        const u64 ei = mine[i] + peer[i];
+        u64 z = c[i] + ei * br + fr * a[i];
+        if (share == 0) z += ei * fr;
+        out[i] = trunc_share(z, f, share);
+    }
+}
+
+// two differences in one launch, written back to back: out[0, n0) = a0 - b0, out[n0, n0 + n1) = a1 - b1 (a1 == nullptr: -b1).
+// This is the message [X - U | W - V] of a Beaver product, or [x - a | s - b] of a row scaling.
+__global__ void __launch_bounds__(EW_THREADS) sub_pair_kernel(const u64* __restrict__ a0, const u64* __restrict__ b0, uint64_t n0,
+                                                             const u64* __restrict__ a1, const u64* __restrict__ b1, uint64_t n1,
+                                                             u64* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += stride) {
+        if (i < n0) out[i] = a0[i] - b0[i];
+        else {
+            const uint64_t k = i - n0;
+            out[i] = (a1 ? a1[k] : 0ull) - b1[k];
+        }
+    }
+}
+
+// opening of a Beaver product's message in place (mine += peer over nEF words) and, for share 0, VF = V + F in the same pass
+// (F = the last nF words of the opened message)
+__global__ void __launch_bounds__(EW_THREADS) mm_open_kernel(u64* mine, const u64* __restrict__ peer, uint64_t nEF, uint64_t nF,
+                                                            const u64* __restrict__ V, u64* __restrict__ VF) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t offF = nEF - nF;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nEF; i += stride) {
+        const u64 o = mine[i] + peer[i];
+        mine[i] = o;
+        if (VF && i >= offF) VF[i - offF] = o + V[i - offF];
+    }
+}
+
+// up to 16 independent device-to-device copies in one launch (blockIdx.y = segment): the loopback transport delivers all
+// messages of one communication round with it, where one copy node per message would serialise on the stream
+struct CopySegs {
+    const u64* src[16];
+    u64* dst[16];
+    uint64_t n[16];
+};
+__global__ void __launch_bounds__(EW_THREADS) copy_segments_kernel(const CopySegs a) {
+    const int sgm = blockIdx.y;
+    const u64* __restrict__ src = a.src[sgm];
+    u64* __restrict__ dst = a.dst[sgm];
+    const uint64_t n = a.n[sgm];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+        const uint64_t n2 = n >> 1;
+        for (uint64_t k = i; k < n2; k += stride)
+            reinterpret_cast<ulonglong2*>(dst)[k] = reinterpret_cast<const ulonglong2*>(src)[k];
+        if (i == 0 && (n & 1)) dst[n - 1] = src[n - 1];
+    } else {
+        for (uint64_t k = i; k < n; k += stride) dst[k] = src[k];
+    }
+}
+
+// weight-gradient step in one pass (gcn.h:673-678): d' = trunc(d * gs) (the 1/|train| scaling), W' = W - trunc(d' * lr)
+__global__ void __launch_bounds__(EW_THREADS) scale_apply_kernel(const u64* W, const u64* d, u64 gs, u64 lr, u64* d_out, u64* W_out,
+                                                                uint64_t n, int f, int share) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u64 ds = trunc_share(d[i] * gs, f, share);
+        if (d_out) d_out[i] = ds;
+        W_out[i] = W[i] - trunc_share(ds * lr, f, share);
+    }
+}
+
+// weight averaging (gcn.h:747-777): out_k = trunc( (sum of the replicas' shares) * c ), written to up to 4 places (the
+// average that is sent on, and the local / remote weight copies it replaces); outputs may alias inputs
+struct AvgArgs {
+    const u64* in[16];
+    u64* out[4];
+    int n_in, n_out;
+};
+__global__ void __launch_bounds__(EW_THREADS) avg_public_kernel(const AvgArgs a, u64 c, uint64_t n, int f, int share) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        u64 v = 0;
+        for (int j = 0; j < a.n_in; ++j) v += a.in[j][i];
+        v = trunc_share(v * c, f, share);
+        for (int k = 0; k < a.n_out; ++k) a.out[k][i] = v;
+    }
+}
+
 __global__ void __launch_bounds__(EW_THREADS) cond_add_kernel(const u64* v, const u64* u,
                                                              const uint8_t* cond, u64* out,
                                                              uint64_t rows, uint32_t D) {
@@ -307,6 +405,89 @@ int cgb_rowmul_beaver_finish(cgb_ctx* ctx, const uint64_t* d_e, const uint64_t* 
         (const u64*)d_e, (const u64*)d_fv, (const u64*)d_a, (const u64*)d_b, (const u64*)d_c, (u64*)d_out, rows, D,
         share, f);
     CGB_CHECK_LAUNCH(ctx, "rowmul_finish_kernel");
+    return CGB_OK;
+}
+int cgb_rowmul_beaver_finish_open(cgb_ctx* ctx, const uint64_t* d_mine, const uint64_t* d_peer, const uint64_t* d_a,
+                                  const uint64_t* d_b, const uint64_t* d_c, uint64_t* d_out, uint64_t rows, uint32_t D,
+                                  int share, int f) {
+    CGB_REQUIRE(ctx, (d_mine && d_peer && d_a && d_b && d_c && d_out) || rows == 0, "cgb_rowmul_beaver_finish_open: null argument");
+    CGB_REQUIRE(ctx, D > 0 && f < 64 && (share == 0 || share == 1), "cgb_rowmul_beaver_finish_open: bad D/f/share");
+    if (rows == 0) return CGB_OK;
+    rowmul_finish_open_kernel<<<ew_blocks(ctx, rows * D), EW_THREADS, 0, ctx->stream>>>(
+        (const u64*)d_mine, (const u64*)d_peer, (const u64*)d_a, (const u64*)d_b, (const u64*)d_c, (u64*)d_out, rows, D, share, f);
+    CGB_CHECK_LAUNCH(ctx, "rowmul_finish_open_kernel");
+    return CGB_OK;
+}
+int cgb_sub_pair(cgb_ctx* ctx, const uint64_t* d_a0, const uint64_t* d_b0, uint64_t n0, const uint64_t* d_a1,
+                 const uint64_t* d_b1, uint64_t n1, uint64_t* d_out) {
+    CGB_REQUIRE(ctx, ((d_a0 && d_b0) || n0 == 0) && (d_b1 || n1 == 0) && (d_out || n0 + n1 == 0), "cgb_sub_pair: null argument");
+    if (n0 + n1 == 0) return CGB_OK;
+    sub_pair_kernel<<<ew_blocks(ctx, n0 + n1), EW_THREADS, 0, ctx->stream>>>((const u64*)d_a0, (const u64*)d_b0, n0,
+                                                                           (const u64*)d_a1, (const u64*)d_b1, n1, (u64*)d_out);
+    CGB_CHECK_LAUNCH(ctx, "sub_pair_kernel");
+    return CGB_OK;
+}
+// internal (matmul.cu): open [E | F] in place and form V + F for share 0 in one launch
+int cgb_mm_open_launch(cgb_ctx* ctx, uint64_t* d_mine, const uint64_t* d_peer, uint64_t nEF, uint64_t nF, const uint64_t* d_V,
+                       uint64_t* d_VF) {
+    if (nEF == 0) return CGB_OK;
+    mm_open_kernel<<<ew_blocks(ctx, nEF), EW_THREADS, 0, ctx->stream>>>((u64*)d_mine, (const u64*)d_peer, nEF, nF, (const u64*)d_V,
+                                                                     (u64*)d_VF);
+    CGB_CHECK_LAUNCH(ctx, "mm_open_kernel");
+    return CGB_OK;
+}
+int cgb_copy_segments(cgb_ctx* ctx, uint64_t* const* d_dst, const uint64_t* const* d_src, const uint64_t* n_words, uint32_t n_seg) {
+    CGB_REQUIRE(ctx, n_seg == 0 || (d_dst && d_src && n_words), "cgb_copy_segments: null argument");
+    for (uint32_t base = 0; base < n_seg; base += 16) {
+        CopySegs a;
+        uint32_t cnt = 0;
+        uint64_t longest = 0;
+        for (uint32_t j = base; j < n_seg && cnt < 16; ++j) {
+            if (n_words[j] == 0) continue;
+            CGB_REQUIRE(ctx, d_dst[j] && d_src[j], "cgb_copy_segments: null segment");
+            a.src[cnt] = (const u64*)d_src[j];
+            a.dst[cnt] = (u64*)d_dst[j];
+            a.n[cnt] = n_words[j];
+            if (n_words[j] > longest) longest = n_words[j];
+            ++cnt;
+        }
+        if (cnt == 0) continue;
+        unsigned bx = ew_blocks(ctx, (longest + 1) / 2);
+        const unsigned cap = (unsigned)((ctx->num_sms * 16 + cnt - 1) / cnt);
+        if (bx > cap) bx = cap;
+        copy_segments_kernel<<<dim3(bx, cnt), EW_THREADS, 0, ctx->stream>>>(a);
+        CGB_CHECK_LAUNCH(ctx, "copy_segments_kernel");
+    }
+    return CGB_OK;
+}
+int cgb_scale_apply_gradient(cgb_ctx* ctx, const uint64_t* d_W, const uint64_t* d_d, uint64_t gs, uint64_t lr, uint64_t* d_d_out,
+                             uint64_t* d_W_out, uint64_t n, int f, int share) {
+    CGB_REQUIRE(ctx, (d_W && d_d && d_W_out) || n == 0, "cgb_scale_apply_gradient: null argument");
+    CGB_REQUIRE(ctx, f < 64 && (share == 0 || share == 1), "cgb_scale_apply_gradient: bad f/share");
+    if (n == 0) return CGB_OK;
+    scale_apply_kernel<<<ew_blocks(ctx, n), EW_THREADS, 0, ctx->stream>>>((const u64*)d_W, (const u64*)d_d, (u64)gs, (u64)lr,
+                                                                        (u64*)d_d_out, (u64*)d_W_out, n, f, share);
+    CGB_CHECK_LAUNCH(ctx, "scale_apply_kernel");
+    return CGB_OK;
+}
+int cgb_avg_public(cgb_ctx* ctx, const uint64_t* const* d_in, uint32_t n_in, uint64_t c, uint64_t* const* d_out, uint32_t n_out,
+                   uint64_t n, int f, int share) {
+    CGB_REQUIRE(ctx, d_in && d_out && n_in >= 1 && n_in <= 16 && n_out >= 1 && n_out <= 4, "cgb_avg_public: 1..16 inputs, 1..4 outputs");
+    CGB_REQUIRE(ctx, f < 64 && (share == 0 || share == 1), "cgb_avg_public: bad f/share");
+    if (n == 0) return CGB_OK;
+    AvgArgs a;
+    a.n_in = (int)n_in;
+    a.n_out = (int)n_out;
+    for (uint32_t j = 0; j < n_in; ++j) {
+        CGB_REQUIRE(ctx, d_in[j], "cgb_avg_public: null input");
+        a.in[j] = (const u64*)d_in[j];
+    }
+    for (uint32_t k = 0; k < n_out; ++k) {
+        CGB_REQUIRE(ctx, d_out[k], "cgb_avg_public: null output");
+        a.out[k] = (u64*)d_out[k];
+    }
+    avg_public_kernel<<<ew_blocks(ctx, n), EW_THREADS, 0, ctx->stream>>>(a, (u64)c, n, f, share);
+    CGB_CHECK_LAUNCH(ctx, "avg_public_kernel");
     return CGB_OK;
 }
 int cgb_cond_add(cgb_ctx* ctx, const uint64_t* d_v, const uint64_t* d_u, const uint8_t* d_cond, uint64_t* d_out,

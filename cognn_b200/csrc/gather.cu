@@ -814,7 +814,9 @@ int build_chunks(cgb_ctx* ctx, cgb_csr* c, const uint32_t* h_rowptr) {
     c->n_empty = (uint32_t)empty.size();
     static const int forced_shift = getenv("CGB_CHUNK_SHIFT") ? atoi(getenv("CGB_CHUNK_SHIFT")) : 0;
     c->chunk_shift = forced_shift >= 4 && forced_shift <= 12 ? (uint32_t)forced_shift
-                     : (c->n_edges >= CGB_BIG_GRAPH_EDGES ? CGB_CHUNK_SHIFT_BIG : CGB_CHUNK_SHIFT_SMALL);
+                     : (c->n_edges >= CGB_BIG_GRAPH_EDGES ? CGB_CHUNK_SHIFT_BIG
+                        : c->n_edges >= (1ull << 21) ? CGB_CHUNK_SHIFT_SMALL
+                        : c->n_edges >= (1ull << 18) ? 5u : 4u);  // small graphs are latency bound: shorter serial chains
     const uint64_t chunk_edges = 1ull << c->chunk_shift;
     c->n_chunks = (uint32_t)((c->n_edges + chunk_edges - 1) / chunk_edges);
     std::vector<uint32_t> chunk_nz(c->n_chunks);

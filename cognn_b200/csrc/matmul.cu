@@ -35,6 +35,7 @@ struct MatmulArgs {
     int f, share;    // fused truncation (f <= 0: none), only with k_splits == 1
     uint32_t k_chunk;  // K range per split (multiple of BK)
     uint32_t k_splits;
+    size_t scratch_off;  // host side: bytes at the start of ctx->scratch the caller keeps for itself (V + F of the Beaver finish)
 };
 
 template <int BM, int BN, int BK, int TM, int TN>
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), (TM * TN >= 32) ? 1 : 2
             if (gn >= a.N) continue;
             const size_t o = (size_t)gm * a.N + gn;
             if (a.k_splits > 1) {
-                atomicAdd(a.C + o, acc[i][j]);
+                a.C[(size_t)blockIdx.z * a.M * a.N + o] = acc[i][j];  // this split's plane; add_trunc_kernel sums the planes
             } else {
                 u64 v = acc[i][j];
                 if (a.Z) v += a.Z[o];
@@ -145,16 +146,70 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), (TM * TN >= 32) ? 1 : 2
     }
 }
 
-__global__ void __launch_bounds__(256) add_trunc_kernel(const u64* t, const u64* z, u64* out, uint64_t n, int f, int share) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = trunc_share(t[i] + (z ? z[i] : 0ull), f, share);
+// out = trunc( sum of the `splits` partial planes of t + z + (acc ? out : 0) ).  A CTA is 32 outputs x 8 plane lanes: with a
+// few hundred planes over a few hundred outputs (weight gradients) the planes are what has to be spread over threads.
+__global__ void __launch_bounds__(256) add_trunc_kernel(const u64* __restrict__ t, uint32_t splits, const u64* __restrict__ z,
+                                                        u64* out, uint64_t n, int accumulate, int f, int share) {
+    __shared__ u64 part[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * 32; i0 < n; i0 += (uint64_t)gridDim.x * 32) {
+        const uint64_t i = i0 + tx;
+        u64 v = 0;
+        if (i < n)
+            for (uint32_t sp = ty; sp < splits; sp += 8) v += t[(size_t)sp * n + i];
+        part[ty][tx] = v;
+        __syncthreads();
+        if (ty == 0 && i < n) {
+#pragma unroll
+            for (int k = 1; k < 8; ++k) v += part[k][tx];
+            if (z) v += z[i];
+            if (accumulate) v += out[i];
+            out[i] = trunc_share(v, f, share);
+        }
+        __syncthreads();
+    }
 }
 
 template <int BM, int BN, int BK, int TM, int TN>
 void launch_cfg(cgb_ctx* ctx, MatmulArgs& a) {
     dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.k_splits);
     matmul_kernel<BM, BN, BK, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, ctx->stream>>>(a);
+}
+
+// Tile shape and split-K plan of the integer-pipe kernel for one problem size.  K is split when the output tiles alone cannot
+// fill the machine (weight gradients h^T v: a handful of tiles, K = vertices of the party); every split then owns a plane of
+// partial sums, so the scratch need grows with the split count and is capped.
+struct SplitPlan {
+    uint32_t BM, BN, splits, k_chunk;
+    size_t plane_bytes;  // splits * M * N * 8 when splits > 1, else 0
+};
+SplitPlan plan_splits(const cgb_ctx* ctx, uint32_t M, uint32_t K, uint32_t N) {
+    constexpr uint32_t BK = 16;
+    SplitPlan p{};
+    if (N > 32) { p.BM = 128; p.BN = 64; }
+    else if (N > 8) { p.BM = 128; p.BN = 16; }
+    else { p.BM = 256; p.BN = 8; }
+    if (M <= 32) p.BM = 32;  // weight gradients h^T v (M = hidden width or classes): a 128-row tile would be 3/4 padding
+    const uint64_t tiles = (uint64_t)((M + p.BM - 1) / p.BM) * ((N + p.BN - 1) / p.BN);
+    static const int want_env = getenv("CGB_MATMUL_SPLIT_WANT") ? atoi(getenv("CGB_MATMUL_SPLIT_WANT")) : 0;
+    static const int depth_env = getenv("CGB_MATMUL_SPLIT_DEPTH") ? atoi(getenv("CGB_MATMUL_SPLIT_DEPTH")) : 0;
+    const uint64_t want = (want_env > 0 ? (uint64_t)want_env : 2ull) * ctx->num_sms;
+    const uint64_t depth = depth_env >= 1 && depth_env <= 64 ? (uint64_t)depth_env : 2;  // at least this many K steps per split
+    uint32_t splits = 1;
+    if (tiles < want && K >= 2 * depth * BK) {
+        uint64_t s = (want + tiles - 1) / tiles;
+        const uint64_t max_s = K / (depth * BK);
+        const uint64_t plane = (uint64_t)M * N * sizeof(u64);
+        const uint64_t max_mem = std::max<uint64_t>(1, (64ull << 20) / std::max<uint64_t>(plane, 1));  // <= 64 MB of partial planes
+        splits = (uint32_t)std::max<uint64_t>(1, std::min(std::min(s, max_s), max_mem));
+    }
+    uint32_t k_chunk = (K + splits - 1) / splits;
+    k_chunk = (k_chunk + BK - 1) / BK * BK;
+    if (k_chunk == 0) k_chunk = BK;
+    p.splits = K == 0 ? 1 : (K + k_chunk - 1) / k_chunk;
+    p.k_chunk = k_chunk;
+    p.plane_bytes = p.splits > 1 ? (size_t)p.splits * M * N * sizeof(u64) : 0;
+    return p;
 }
 
 // Runs the (up to two pair) product with optional Z / truncation epilogue.
@@ -178,56 +233,36 @@ int run_matmul(cgb_ctx* ctx, MatmulArgs a) {
         }
         if (tc) return cgb_matmul_tc_run(ctx, a.A, a.B, a.n_pairs, a.Z, a.C, a.M, a.K, a.N, a.transA, a.accumulate, a.f, a.share);
     }
-    constexpr uint32_t BK = 16;
-    uint32_t BM, BN;
-    if (a.N > 32) { BM = 128; BN = 64; }
-    else if (a.N > 8) { BM = 128; BN = 16; }
-    else { BM = 256; BN = 8; }
-    const uint64_t tiles = (uint64_t)((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
-    // split K when the output alone cannot fill the machine
-    uint32_t splits = 1;
-    const uint64_t want = 2ull * ctx->num_sms;
-    if (tiles < want && a.K >= 8 * BK) {
-        uint64_t s = (want + tiles - 1) / tiles;
-        uint64_t max_s = a.K / (4 * BK);
-        splits = (uint32_t)std::max<uint64_t>(1, std::min(s, max_s));
-    }
-    uint32_t k_chunk = (a.K + splits - 1) / splits;
-    k_chunk = (k_chunk + BK - 1) / BK * BK;
-    if (k_chunk == 0) k_chunk = BK;
-    splits = a.K == 0 ? 1 : (a.K + k_chunk - 1) / k_chunk;
-    a.k_chunk = k_chunk;
-    a.k_splits = splits;
+    SplitPlan pl = plan_splits(ctx, a.M, a.K, a.N);
+    a.k_chunk = pl.k_chunk;
+    a.k_splits = pl.splits;
 
     const u64* Z = a.Z;
     u64* C = a.C;
     const int f = a.f, share = a.share, accumulate = a.accumulate;
-    const bool needs_finish = splits > 1 && (Z != nullptr || f > 0);
-    if (splits > 1) {
-        // atomics accumulate onto a zeroed buffer (or onto C itself when accumulating without epilogue)
-        if (needs_finish || !accumulate) {
-            u64* T = C;
-            if (needs_finish) {
-                int rc = cgb_scratch_reserve(ctx, (size_t)a.M * a.N * sizeof(u64));
-                if (rc) return rc;
-                T = (u64*)ctx->scratch;
-            }
-            CGB_CHECK_CUDA(ctx, cudaMemsetAsync(T, 0, (size_t)a.M * a.N * sizeof(u64), ctx->stream));
-            a.C = T;
-        }
+    if (pl.splits > 1) {
+        // every split stores its own M x N plane (plain stores: no zeroing pass, no atomics on shared addresses); the
+        // finishing launch sums the planes, adds Z / the old C and truncates
+        int rc = cgb_scratch_reserve(ctx, a.scratch_off + pl.plane_bytes);
+        if (rc) return rc;
+        a.C = (u64*)((char*)ctx->scratch + a.scratch_off);
         a.Z = nullptr; a.f = 0; a.accumulate = 0;
     }
-    if (BN == 64) launch_cfg<128, 64, 16, 8, 4>(ctx, a);
-    else if (BN == 16) launch_cfg<128, 16, 16, 4, 2>(ctx, a);
+    if (pl.BM == 32) {
+        if (pl.BN == 64) launch_cfg<32, 64, 16, 2, 4>(ctx, a);
+        else if (pl.BN == 16) launch_cfg<32, 16, 16, 2, 1>(ctx, a);
+        else launch_cfg<32, 8, 16, 1, 1>(ctx, a);
+    } else if (pl.BN == 64) launch_cfg<128, 64, 16, 8, 4>(ctx, a);
+    else if (pl.BN == 16) launch_cfg<128, 16, 16, 4, 2>(ctx, a);
     else launch_cfg<256, 8, 16, 8, 1>(ctx, a);
     CGB_CHECK_LAUNCH(ctx, "matmul_kernel");
-    ctx->last_kernel = BN == 64 ? "matmul_kernel<128,64,16,8,4> (IMAD.WIDE u64 tiles)"
-                                : (BN == 16 ? "matmul_kernel<128,16,16,4,2> (IMAD.WIDE u64 tiles)" : "matmul_kernel<256,8,16,8,1> (IMAD.WIDE u64 tiles)");
-    if (needs_finish) {
+    ctx->last_kernel = pl.BM == 32 ? "matmul_kernel<32,*,16,*,*> (IMAD.WIDE u64 tiles, short M)" : pl.BN == 64 ? "matmul_kernel<128,64,16,8,4> (IMAD.WIDE u64 tiles)"
+                                   : (pl.BN == 16 ? "matmul_kernel<128,16,16,4,2> (IMAD.WIDE u64 tiles)"
+                                                  : "matmul_kernel<256,8,16,8,1> (IMAD.WIDE u64 tiles)");
+    if (pl.splits > 1) {
         const uint64_t n = (uint64_t)a.M * a.N;
-        // accumulate + finish: C = trunc(T + Z + (accumulate ? C : 0)) is only needed without accumulate here
-        unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->num_sms * 16);
-        add_trunc_kernel<<<blocks, 256, 0, ctx->stream>>>((const u64*)ctx->scratch, Z, C, n, f, share);
+        unsigned blocks = (unsigned)std::min<uint64_t>((n + 31) / 32, (uint64_t)ctx->num_sms * 16);
+        add_trunc_kernel<<<blocks, 256, 0, ctx->stream>>>((const u64*)a.C, pl.splits, Z, C, n, accumulate, f, share);
         CGB_CHECK_LAUNCH(ctx, "add_trunc_kernel");
     }
     return CGB_OK;
@@ -264,19 +299,55 @@ int cgb_beaver_matmul_finish(cgb_ctx* ctx, const uint64_t* d_E, const uint64_t* 
     if (M == 0 || N == 0) return CGB_OK;
     // share 0 folds the E*F term into the first product: E*(V+F) + U*F
     const u64* Bfirst = (const u64*)d_V;
+    size_t vf_bytes = 0;
     if (share == 0) {
-        // keep V+F in the tail of the scratch buffer, after the split-K accumulator
-        const size_t acc_bytes = ((size_t)M * N * sizeof(u64) + 255) & ~(size_t)255;
-        int rc = cgb_scratch_reserve(ctx, acc_bytes + (size_t)K * N * sizeof(u64));
+        // keep V+F at the head of the scratch buffer, before the split-K planes (reserved together: growing the buffer later
+        // would move it)
+        vf_bytes = ((size_t)K * N * sizeof(u64) + 255) & ~(size_t)255;
+        int rc = cgb_scratch_reserve(ctx, vf_bytes + plan_splits(ctx, M, K, N).plane_bytes);
         if (rc) return rc;
-        u64* VF = (u64*)((char*)ctx->scratch + acc_bytes);
+        u64* VF = (u64*)ctx->scratch;
         rc = cgb_add(ctx, d_V, d_F, (uint64_t*)VF, (uint64_t)K * N);
         if (rc) return rc;
         Bfirst = VF;
     }
     MatmulArgs a{};
+    a.scratch_off = vf_bytes;
     a.A[0] = (const u64*)d_E; a.B[0] = Bfirst;
     a.A[1] = (const u64*)d_U; a.B[1] = (const u64*)d_F;
+    a.n_pairs = 2;
+    a.Z = (const u64*)d_Z; a.C = (u64*)d_C; a.M = M; a.K = K; a.N = N;
+    a.transA = 0; a.accumulate = 0; a.f = f; a.share = share;
+    return run_matmul(ctx, a);
+}
+
+int cgb_mm_open_launch(cgb_ctx* ctx, uint64_t* d_mine, const uint64_t* d_peer, uint64_t nEF, uint64_t nF, const uint64_t* d_V,
+                       uint64_t* d_VF);  // elementwise.cu
+
+int cgb_beaver_matmul_finish_open(cgb_ctx* ctx, uint64_t* d_mine, const uint64_t* d_peer, const uint64_t* d_U,
+                                  const uint64_t* d_V, const uint64_t* d_Z, uint64_t* d_C, uint32_t M, uint32_t K,
+                                  uint32_t N, int share, int f) {
+    CGB_REQUIRE(ctx, d_mine && d_peer && d_U && d_V && d_Z && d_C, "cgb_beaver_matmul_finish_open: null argument");
+    CGB_REQUIRE(ctx, share == 0 || share == 1, "cgb_beaver_matmul_finish_open: bad share");
+    CGB_REQUIRE(ctx, f < 64, "cgb_beaver_matmul_finish_open: bad f");
+    CGB_REQUIRE(ctx, d_C != d_mine && d_C != d_peer && d_C != d_U && d_C != d_V && d_C != d_Z,
+                "cgb_beaver_matmul_finish_open: C must not alias the inputs");
+    if (M == 0 || N == 0) return CGB_OK;
+    const uint64_t nE = (uint64_t)M * K, nF = (uint64_t)K * N;
+    u64* VF = nullptr;
+    size_t vf_bytes = 0;
+    if (share == 0) {  // V + F at the head of the scratch buffer, the split-K planes behind it (reserved together)
+        vf_bytes = ((size_t)nF * sizeof(u64) + 255) & ~(size_t)255;
+        int rc = cgb_scratch_reserve(ctx, vf_bytes + plan_splits(ctx, M, K, N).plane_bytes);
+        if (rc) return rc;
+        VF = (u64*)ctx->scratch;
+    }
+    int rc = cgb_mm_open_launch(ctx, d_mine, d_peer, nE + nF, nF, d_V, (uint64_t*)VF);
+    if (rc) return rc;
+    MatmulArgs a{};
+    a.scratch_off = vf_bytes;
+    a.A[0] = (const u64*)d_mine; a.B[0] = share == 0 ? VF : (const u64*)d_V;
+    a.A[1] = (const u64*)d_U; a.B[1] = (const u64*)d_mine + nE;
     a.n_pairs = 2;
     a.Z = (const u64*)d_Z; a.C = (u64*)d_C; a.M = M; a.K = K; a.N = N;
     a.transA = 0; a.accumulate = 0; a.f = f; a.share = share;

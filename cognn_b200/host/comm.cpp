@@ -38,6 +38,9 @@ public:
     }
     void exchange() override {
         ++rounds;
+        std::vector<uint64_t*> dst;
+        std::vector<const uint64_t*> src;
+        std::vector<uint64_t> len;
         for (auto& pr : order_) {
             auto& sq = sends_[pr];
             auto& rq = recvs_[pr];
@@ -47,7 +50,9 @@ public:
             sq.pop_front();
             rq.pop_front();
             if (s.n != r.n) throw std::runtime_error("LoopbackComm: size mismatch on " + s.tag);
-            if (s.n && cgb_d2d(ctx_, r.p, s.p, s.n * sizeof(uint64_t)) != CGB_OK) throw std::runtime_error("LoopbackComm: copy failed");
+            dst.push_back(r.p);
+            src.push_back(s.p);
+            len.push_back(s.n);
             words_sent += s.n;
             if (record) {
                 Message m{cur_iter, s.src, s.dst, s.tag, std::vector<uint64_t>(s.n)};
@@ -56,6 +61,9 @@ public:
                 transcript.push_back(std::move(m));
             }
         }
+        // every message of the round in one launch (one copy node per message would serialise on the stream)
+        if (!dst.empty() && cgb_copy_segments(ctx_, dst.data(), src.data(), len.data(), (uint32_t)dst.size()) != CGB_OK)
+            throw std::runtime_error(std::string("LoopbackComm: copy failed: ") + cgb_last_error(ctx_));
         order_.clear();
         for (auto& kv : recvs_)
             if (!kv.second.empty()) throw std::runtime_error("LoopbackComm: recv without matching send");

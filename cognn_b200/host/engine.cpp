@@ -193,8 +193,9 @@ struct DMat {
         rows = r;
         cols = cl;
     }
-    void copy_from(const DMat& o) {
-        resize(o.ctx, o.rows, o.cols);
+    // on the stream of `c` -- the context the CALLER is issuing on (a side's inside for_sides), not the one `o` was last resized by
+    void copy_from(cgb_ctx* c, const DMat& o) {
+        resize(c, o.rows, o.cols);
         if (n()) ck(ctx, cgb_d2d(ctx, p, o.p, n() * sizeof(uint64_t)), "cgb_d2d");
     }
 };
@@ -228,7 +229,7 @@ struct Side {
     double* h_prob = nullptr;     // pinned host copy, read after the iteration's synchronise
     size_t h_prob_cap = 0;
     std::vector<DMat> upd_recv;  // helper side: masked sums received from the other owners
-    DMat delta, S;
+    DMat delta, S, Smask;  // Smask: sum of the OM mask shares this side holds for its own block (dealt offline)
     // dealer emulation temporaries (offline phase): grow-only members, so that phase neither allocates nor synchronises
     // after the first epoch and can be replayed as a CUDA graph like the online phase
     DMat dl_U0, dl_V0, dl_Z0, dl_a0, dl_b0, dl_c0, dl_zero_mat, dl_zero_vec, dl_negc, dl_r;
@@ -286,7 +287,7 @@ struct SSGcnEngine::Impl {
             DMat* mats[] = {&s.X, &s.X_backup, &s.W[0], &s.W[1], &s.h_t[0], &s.h_t[1], &s.z[0], &s.z[1], &s.g, &s.Xp, &s.V,
                             &s.Y, &s.m, &s.tmp, &s.tmp2, &s.P, &s.Ppeer, &s.grad, &s.prob, &s.res_in, &s.res_plain, &s.res_plain2,
                             &s.mmU[0], &s.mmU[1], &s.mmV[0], &s.mmV[1], &s.mmZ[0], &s.mmZ[1], &s.rmA[0], &s.rmA[1], &s.rmB[0],
-                            &s.rmB[1], &s.rmC[0], &s.rmC[1], &s.delta, &s.S, &s.mm_mine, &s.mm_peer, &s.rm_mine, &s.rm_peer};
+                            &s.rmB[1], &s.rmC[0], &s.rmC[1], &s.delta, &s.S, &s.Smask, &s.mm_mine, &s.mm_peer, &s.rm_mine, &s.rm_peer};
             for (DMat* m : mats) fn(*m);
         });
     }
@@ -358,8 +359,7 @@ struct SSGcnEngine::Impl {
             throw std::runtime_error("mm_prepare: triple was dealt for another shape");
         s.mm_mine.resize(ctx, 1, M * K + K * N);
         s.mm_peer.resize(ctx, 1, M * K + K * N);
-        vsub(A.p, s.mmU[sub].p, s.mm_mine.p, (size_t)M * K);
-        vsub(B.p, s.mmV[sub].p, s.mm_mine.p + (size_t)M * K, (size_t)K * N);
+        ck(ctx, cgb_sub_pair(ctx, A.p, s.mmU[sub].p, (size_t)M * K, B.p, s.mmV[sub].p, (size_t)K * N, s.mm_mine.p), "cgb_sub_pair");
     }
     void mm_post(Side& s, int sub) {
         const int holder = s.share == 0 ? s.owner : q(s.owner);
@@ -368,10 +368,9 @@ struct SSGcnEngine::Impl {
         recv(holder, other, s.mm_peer);
     }
     void mm_finish(Side& s, int sub, uint32_t M, uint32_t K, uint32_t N, DMat& C_out) {
-        vadd(s.mm_mine.p, s.mm_peer.p, s.mm_mine.p, s.mm_mine.n());  // E | F opened
-        C_out.resize(ctx, M, N);
-        ck(ctx, cgb_beaver_matmul_finish(ctx, s.mm_mine.p, s.mm_mine.p + (size_t)M * K, s.mmU[sub].p, s.mmV[sub].p, s.mmZ[sub].p,
-                                         C_out.p, M, K, N, s.share, f), "cgb_beaver_matmul_finish");
+        C_out.resize(ctx, M, N);  // E | F are opened (mine += peer) by the launch that also forms V + F for share 0
+        ck(ctx, cgb_beaver_matmul_finish_open(ctx, s.mm_mine.p, s.mm_peer.p, s.mmU[sub].p, s.mmV[sub].p, s.mmZ[sub].p, C_out.p, M, K,
+                                              N, s.share, f), "cgb_beaver_matmul_finish_open");
     }
 
     // ---- Beaver row scaling (sci::twoPartyGCNVectorScale, gcn.h:247,476): scaler private to the owner -------------
@@ -407,13 +406,9 @@ struct SSGcnEngine::Impl {
         if (s.rmA[sub].rows != rows || s.rmA[sub].cols != D) throw std::runtime_error("rm_prepare: triple was dealt for another shape");
         s.rm_mine.resize(ctx, 1, rows * D + rows);
         s.rm_peer.resize(ctx, 1, rows * D + rows);
-        vsub(x.p, s.rmA[sub].p, s.rm_mine.p, (size_t)rows * D);
-        if (s.share == 0) {
-            vsub(scaler->p, s.rmB[sub].p, s.rm_mine.p + (size_t)rows * D, rows);
-        } else {
-            ck(ctx, cgb_memset(ctx, s.rm_mine.p + (size_t)rows * D, 0, (size_t)rows * 8), "memset");
-            vsub(s.rm_mine.p + (size_t)rows * D, s.rmB[sub].p, s.rm_mine.p + (size_t)rows * D, rows);
-        }
+        // [x - a | scaler - b]; the helper's share of the owner-private scaler is zero
+        ck(ctx, cgb_sub_pair(ctx, x.p, s.rmA[sub].p, (size_t)rows * D, s.share == 0 ? scaler->p : nullptr, s.rmB[sub].p, rows,
+                             s.rm_mine.p), "cgb_sub_pair");
     }
     void rm_post(Side& s, int sub) {
         const int holder = s.share == 0 ? s.owner : q(s.owner);
@@ -422,10 +417,9 @@ struct SSGcnEngine::Impl {
         recv(holder, other, s.rm_peer);
     }
     void rm_finish(Side& s, int sub, uint32_t rows, uint32_t D, DMat& out) {
-        vadd(s.rm_mine.p, s.rm_peer.p, s.rm_mine.p, s.rm_mine.n());
         out.resize(ctx, rows, D);
-        ck(ctx, cgb_rowmul_beaver_finish(ctx, s.rm_mine.p, s.rm_mine.p + (size_t)rows * D, s.rmA[sub].p, s.rmB[sub].p, s.rmC[sub].p,
-                                         out.p, rows, D, s.share, f), "cgb_rowmul_beaver_finish");
+        ck(ctx, cgb_rowmul_beaver_finish_open(ctx, s.rm_mine.p, s.rm_peer.p, s.rmA[sub].p, s.rmB[sub].p, s.rmC[sub].p, out.p, rows,
+                                              D, s.share, f), "cgb_rowmul_beaver_finish_open");
     }
 
     // run `fn(side)` for every locally hosted side in the canonical order (owner 0 share 0, owner 0 share 1, ...)
@@ -482,6 +476,21 @@ struct SSGcnEngine::Impl {
 
     // offline: the owner's OM correlation delta = A r - S (S = the mask shares s_{p->t} of all destination blocks)
     void om_deal(Side& s, uint64_t it, uint32_t D) {
+        {   // the mask shares this side holds for its destination block, summed: dealer material, so the online GatherComp
+            // additions are one plain sum (share 0 holds s_{p->t} of every other source party, share 1 holds s_{t->t})
+            const int t = s.owner;
+            uint64_t streams[16];
+            uint32_t n_st = 0;
+            if (T > 16) throw std::runtime_error("om_deal: more than 16 parties");
+            if (s.share == 0) {
+                for (int p = 0; p < T; ++p)
+                    if (p != t) streams[n_st++] = stream_id(K_OM_S, it, p, t);
+            } else {
+                streams[n_st++] = stream_id(K_OM_S, it, t, t);
+            }
+            s.Smask.resize(ctx, s.n, D);
+            ck(ctx, cgb_prg_sum(ctx, key, streams, n_st, nullptr, 0, s.Smask.p, s.Smask.n()), "cgb_prg_sum(mask shares)");
+        }
         if (s.share != 0) return;
         PartyData& pd = party[s.owner];
         const uint32_t n_rows = pd.g.offsets[T];
@@ -563,25 +572,23 @@ struct SSGcnEngine::Impl {
             const uint32_t D = s.Xp.cols;
             const int t = s.owner;
             s.V.resize(ctx, s.n, D);
+            // one launch: V = Xp + (the blocks this side holds) + (the sum of the mask shares it holds, dealt offline)
+            const uint64_t* in[16];
+            uint32_t n_in = 0;
+            if (T > 14) throw std::runtime_error("gas: more than 14 parties");
+            if (s.Smask.rows != s.n || s.Smask.cols != D) throw std::runtime_error("gas: OM mask shares were dealt for another shape");
+            in[n_in++] = s.Xp.p;
+            in[n_in++] = s.Smask.p;
             if (s.share == 0) {
-                PartyData& pd = party[t];
-                vadd(s.Xp.p, s.Y.p + (size_t)pd.g.offsets[t] * D, s.V.p, s.V.n());
-                for (int p = 0; p < T; ++p) {
-                    if (p == t) continue;
-                    prg(K_OM_S, it, p, t, s.tmp, s.n, D);  // the owner holds the mask share s_{p->t}
-                    vadd(s.V.p, s.tmp.p, s.V.p, s.V.n());
-                }
+                in[n_in++] = s.Y.p + (size_t)party[t].g.offsets[t] * D;
             } else {
-                prg(K_OM_S, it, t, t, s.tmp, s.n, D);
-                vadd(s.Xp.p, s.tmp.p, s.V.p, s.V.n());
                 for (int p = 0; p < T; ++p) {
                     if (p == t) continue;
-                    const uint64_t* blk;
-                    if (q(t) == p) blk = own.at(p).Y.p + (size_t)party[p].g.offsets[t] * D;  // computed on this very party
-                    else blk = s.upd_recv[p].p;
-                    vadd(s.V.p, blk, s.V.p, s.V.n());
+                    if (q(t) == p) in[n_in++] = own.at(p).Y.p + (size_t)party[p].g.offsets[t] * D;  // computed on this very party
+                    else in[n_in++] = s.upd_recv[p].p;
                 }
             }
+            ck(ctx, cgb_sum_n(ctx, in, n_in, s.V.p, s.V.n()), "cgb_sum_n");
         });
     }
 
@@ -594,7 +601,9 @@ struct SSGcnEngine::Impl {
             size_t total = 0;
             for (int i = 0; i < n_in; ++i) total += in_sel(s, i)->n();
             s.res_in.resize(ctx, 1, (uint32_t)total);
-            if (s.share == 1) {
+            if (s.share == 1 && n_in == 1) {  // a single operand goes out from where it lives
+                send(q(s.owner), s.owner, *in_sel(s, 0), tagf("res", 0, s.owner));
+            } else if (s.share == 1) {
                 size_t off = 0;
                 for (int i = 0; i < n_in; ++i) {
                     DMat* m = in_sel(s, i);
@@ -612,11 +621,14 @@ struct SSGcnEngine::Impl {
                 DMat* a = in_sel(s, 0);
                 DMat* plain[2] = {&s.res_plain, &s.res_plain2};
                 for (int k = 0; k < n_out; ++k) plain[k]->resize(ctx, a->rows, a->cols);
-                if (kind == 1) {
-                    ck(ctx, cgb_ideal_relu(ctx, a->p, s.res_in.p, s.res_plain.p, a->n()), "cgb_ideal_relu");
-                } else if (kind == 2) {
-                    ck(ctx, cgb_ideal_relu_grad(ctx, a->p, s.res_in.p, in_sel(s, 1)->p, s.res_in.p + a->n(), s.res_plain.p, a->n()),
-                       "cgb_ideal_relu_grad");
+                if (kind == 1 || kind == 2) {  // the stand-in and the re-sharing of its single result in one launch
+                    DMat* o = out_sel(s, 0);
+                    o->resize(ctx, a->rows, a->cols);
+                    const uint64_t* z0 = kind == 2 ? in_sel(s, 1)->p : nullptr;
+                    const uint64_t* z1 = kind == 2 ? s.res_in.p + a->n() : nullptr;
+                    ck(ctx, cgb_ideal_relu_reshare(ctx, key, stream_id(K_RESHARE, it, s.owner, 0), a->p, s.res_in.p, z0, z1, o->p,
+                                                   a->n()), "cgb_ideal_relu_reshare");
+                    return;
                 } else {
                     const uint64_t train = (uint64_t)(s.n * cfg.train_ratio);  // gcn.h:560
                     ck(ctx, cgb_ideal_softmax(ctx, a->p, s.res_in.p, party.at(s.owner).d_labels, a->rows, a->cols, train, f,
@@ -638,7 +650,7 @@ struct SSGcnEngine::Impl {
 
     // ---- weight averaging (gcn.h:747-802): reduce to parties 0 and 1, public scale 1/T, redistribute ---------------
     // receive buffers and the averages live in the sides (grow-only), so the online phase never allocates
-    std::map<int, DMat> wa_rx_own[2], wa_rx_hlp[2], wa_rxA0[2], wa_rxA1[2];
+    std::map<int, DMat> wa_rx_own[2], wa_rx_hlp[2];
     DMat wa_A0[2], wa_A1[2];
     void weight_average(uint64_t, int layer) {
         if (T == 1) return;
@@ -667,22 +679,29 @@ struct SSGcnEngine::Impl {
         const uint64_t c = (uint64_t)(int64_t)((1.0 / T) * (double)(1ull << f));  // gcn.h:763-764
         DMat& A0 = wa_A0[layer];
         DMat& A1 = wa_A1[layer];
-        if (comm->is_local(0)) {
-            DMat& w = own.at(0).W[layer];
-            A0.copy_from(w);
-            for (int i = 2; i < T; ++i) vadd(A0.p, rx_hlp[i].p, A0.p, A0.n());
-            vadd(A0.p, hlp.at(T - 1).W[layer].p, A0.p, A0.n());  // party 0's remoteWeight: share 1 of party T-1's replica
-            ck(ctx, cgb_scale_public(ctx, A0.p, c, A0.p, A0.n(), f, 0), "scale");
-        }
-        if (comm->is_local(1)) {
-            DMat& w = own.at(1).W[layer];
-            A1.copy_from(w);
-            for (int i = 2; i < T; ++i) vadd(A1.p, rx_own[i].p, A1.p, A1.n());
-            vadd(A1.p, hlp.at(0).W[layer].p, A1.p, A1.n());
-            ck(ctx, cgb_scale_public(ctx, A1.p, c, A1.p, A1.n(), f, 1), "scale");
-        }
-        auto& rxA1 = wa_rxA1[layer];
-        auto& rxA0 = wa_rxA0[layer];
+        // parties 0 and 1: sum of the replicas' shares, public scale, and the result written straight over the local and the
+        // remote weight copy it replaces (gcn.h:765-777) -- one launch each; the separate buffer only when it is sent on
+        auto average = [&](int p, DMat& A, std::map<int, DMat>& rx, int share) {
+            DMat& w = own.at(p).W[layer];
+            DMat& rw = hlp.at((p - 1 + T) % T).W[layer];  // this party's remoteWeight: share 1 of party p-1's replica
+            const uint64_t* in[16];
+            uint64_t* out[4];
+            uint32_t n_in = 0, n_out = 0;
+            if (T > 16) throw std::runtime_error("weight_average: more than 16 parties");
+            in[n_in++] = w.p;
+            for (int i = 2; i < T; ++i) in[n_in++] = rx[i].p;
+            in[n_in++] = rw.p;
+            if (T > 2) {
+                A.resize(ctx, w.rows, w.cols);
+                out[n_out++] = A.p;
+            }
+            out[n_out++] = w.p;
+            out[n_out++] = rw.p;
+            ck(ctx, cgb_avg_public(ctx, in, n_in, c, out, n_out, w.n(), f, share), "cgb_avg_public");
+        };
+        if (comm->is_local(0)) average(0, A0, rx_hlp, 0);
+        if (comm->is_local(1)) average(1, A1, rx_own, 1);
+        // parties i >= 2 receive both averages where they are used: local weight <- A1, remote weight <- A0
         for (int i = 2; i < T; ++i) {
             snprintf(tg, sizeof tg, "wavg%d.A1", layer);
             if (comm->is_local(1)) comm->post_send(1, i, A1.p, A1.n(), tg);
@@ -690,21 +709,12 @@ struct SSGcnEngine::Impl {
             if (comm->is_local(0)) comm->post_send(0, i, A0.p, A0.n(), tg);
             if (comm->is_local(i)) {
                 DMat& w = own.at(i).W[layer];
-                rxA1[i].resize(ctx, w.rows, w.cols);
-                rxA0[i].resize(ctx, w.rows, w.cols);
-                comm->post_recv(i, 1, rxA1[i].p, rxA1[i].n());
-                comm->post_recv(i, 0, rxA0[i].p, rxA0[i].n());
+                DMat& rw = hlp.at(i - 1).W[layer];
+                comm->post_recv(i, 1, w.p, w.n());
+                comm->post_recv(i, 0, rw.p, rw.n());
             }
         }
         comm->exchange();
-        // afterwards: party 0 holds (A0, A0), party 1 (A1, A1), party i >= 2 (local A1, remote A0)  (gcn.h:765-777)
-        for (int p = 0; p < T; ++p) {
-            if (!comm->is_local(p)) continue;
-            const DMat& local_w = p == 0 ? A0 : (p == 1 ? A1 : rxA1[p]);
-            const DMat& remote_w = p == 0 ? A0 : (p == 1 ? A1 : rxA0[p]);
-            own.at(p).W[layer].copy_from(local_w);
-            hlp.at((p - 1 + T) % T).W[layer].copy_from(remote_w);  // this party's remoteWeight
-        }
     }
 };
 
@@ -760,7 +770,7 @@ SSGcnEngine::~SSGcnEngine() {
     impl_->own.clear();
     impl_->hlp.clear();
     for (int l = 0; l < 2; ++l) {
-        impl_->wa_rx_own[l].clear(); impl_->wa_rx_hlp[l].clear(); impl_->wa_rxA0[l].clear(); impl_->wa_rxA1[l].clear();
+        impl_->wa_rx_own[l].clear(); impl_->wa_rx_hlp[l].clear();
     }
     for (cgb_ctx* c : impl_->side_ctxs) cgb_ctx_destroy(c);
     if (impl_->fork_ev) cudaEventDestroy(impl_->fork_ev);
@@ -885,11 +895,16 @@ void SSGcnEngine::setup() {
         });
         if (cudaEventCreateWithFlags(&im.fork_ev, cudaEventDisableTiming) != cudaSuccess) throw std::runtime_error("setup: event creation failed");
     }
-    im.for_sides([&](Side& s) { s.X_backup.copy_from(s.X); });  // ssk.h:226-227
+    im.for_sides([&](Side& s) {
+        s.X_backup.copy_from(ctx, s.X);  // ssk.h:226-227
+        s.h_t[0].resize(ctx, im.F, s.n);  // gcn.h:230-231 for layer 0: the transpose of a constant
+        ck(ctx, cgb_transpose(ctx, s.X_backup.p, s.h_t[0].p, s.n, im.F), "transpose");
+    });
     ck(im.main_ctx, cgb_ctx_sync(im.main_ctx), "sync");
 }
 
-static DMat* sel_V(Side& s, int) { return &s.V; }
+static DMat* sel_z0(Side& s, int) { return &s.z[0]; }
+static DMat* sel_z1(Side& s, int) { return &s.z[1]; }
 static DMat* sel_X(Side& s, int) { return &s.X; }
 static DMat* sel_XP(Side& s, int k) { return k == 0 ? &s.P : &s.X; }
 static DMat* sel_Xz0(Side& s, int k) { return k == 0 ? &s.X : &s.z[0]; }
@@ -900,7 +915,8 @@ static void online_iteration(SSGcnEngine::Impl& im, uint64_t it) {
     cgb_ctx*& ctx = im.ctx;  // follows the side contexts inside for_sides
     const uint32_t F = im.F, H = im.H, C = im.C;
     const int ph = (int)(it % 6);
-    if (ph == 0) im.for_sides([&](Side& s) { s.X.copy_from(s.X_backup); });  // ssk.h:695, 938
+    // ssk.h:695, 938: every epoch restarts from the input features.  They never change, so layer 0 reads X_backup (and its
+    // transpose, made once in setup) instead of copying it into X first.
     im.tick(nullptr);
 
     if (ph == 0 || ph == 1) {
@@ -908,9 +924,11 @@ static void online_iteration(SSGcnEngine::Impl& im, uint64_t it) {
         const int layer = ph;
         const uint32_t Din = layer == 0 ? F : H, Dout = layer == 0 ? H : C;
         im.for_sides([&](Side& s) {  // PreScatterComp (gcn.h:198-255)
-            s.h_t[layer].resize(ctx, Din, s.n);
-            ck(ctx, cgb_transpose(ctx, s.X.p, s.h_t[layer].p, s.n, Din), "transpose");  // gcn.h:230-231
-            im.mm_prepare(s, it, 0, s.X, s.W[layer]);
+            if (layer != 0) {
+                s.h_t[layer].resize(ctx, Din, s.n);
+                ck(ctx, cgb_transpose(ctx, s.X.p, s.h_t[layer].p, s.n, Din), "transpose");  // gcn.h:230-231
+            }
+            im.mm_prepare(s, it, 0, layer == 0 ? s.X_backup : s.X, s.W[layer]);
             im.mm_post(s, 0);
         });
         im.comm->exchange();
@@ -921,18 +939,18 @@ static void online_iteration(SSGcnEngine::Impl& im, uint64_t it) {
         im.gas(it);
         im.tick("Scatter+Gather (OM message, fused gather-sum, update exchange, adds)");
         // gcn.h:470-484: in-degree scaling ((it + 1) % 6 != 0 for the forward layers)
-        im.rowscale_all(it, 1, [](Side& s) -> DMat& { return s.V; }, [](Side& s) -> DMat& { return s.V; });
+        // the scaled aggregate is the layer's pre-activation z (gcn.h:546,559): written where the backward pass reads it
+        im.rowscale_all(it, 1, [](Side& s) -> DMat& { return s.V; }, [layer](Side& s) -> DMat& { return s.z[layer]; });
         im.tick("Gather_computation (in-degree scale)");
-        im.for_sides([&](Side& s) { s.z[layer].copy_from(s.V); });
         if (layer == 0) {  // gcn.h:546-558: ReLU -- 2PC-RESIDUAL
             im.for_sides([&](Side& s) { s.X.resize(ctx, s.n, Dout); });
-            im.residual(it, 1, 1, 1, sel_V, sel_X);
+            im.residual(it, 1, 1, 1, sel_z0, sel_X);
         } else {  // gcn.h:559-642: softmax, p - y -- 2PC-RESIDUAL; then p is opened to the owner (gcn.h:604)
             im.for_sides([&](Side& s) {
                 s.X.resize(ctx, s.n, Dout);
                 s.P.resize(ctx, s.n, Dout);
             });
-            im.residual(it, 3, 1, 2, sel_V, sel_XP);
+            im.residual(it, 3, 1, 2, sel_z1, sel_XP);
             im.for_sides([&](Side& s) {
                 if (s.share == 1) im.send(im.q(s.owner), s.owner, s.P, SSGcnEngine::Impl::tagf("open_p", -1, s.owner));
                 else {
@@ -988,10 +1006,10 @@ static void online_iteration(SSGcnEngine::Impl& im, uint64_t it) {
             im.mm_finish(s, 1, Din, s.n, Dout, d);
             const uint64_t train = (uint64_t)(s.n * im.cfg.train_ratio);
             const uint64_t gs = train ? (uint64_t)(int64_t)((1.0 / (double)train) * (double)(1ull << im.f)) : 0;  // gcn.h:673-676
-            ck(ctx, cgb_scale_public(ctx, d.p, gs, d.p, d.n(), im.f, s.share), "scale");
-            ck(ctx, cgb_apply_gradient(ctx, s.W[layer].p, d.p, im.lr_fixed, s.W[layer].p, d.n(), im.f, s.share), "apply_gradient");
-            if (layer == 1) s.X.copy_from(s.g);  // dstVec.swap(g) (gcn.h:684)
-            else s.X.copy_from(s.V);             // first layer: g is empty in the reference; never used again
+            ck(ctx, cgb_scale_apply_gradient(ctx, s.W[layer].p, d.p, gs, im.lr_fixed, d.p, s.W[layer].p, d.n(), im.f, s.share),
+               "cgb_scale_apply_gradient");
+            if (layer == 1) s.X.copy_from(ctx, s.g);  // dstVec.swap(g) (gcn.h:684)
+            else s.X.copy_from(ctx, s.V);             // first layer: g is empty in the reference; never used again
         });
         im.tick("Apply_computation");
         im.weight_average(it, layer);

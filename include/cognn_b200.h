@@ -211,6 +211,11 @@ int cgb_matmul(cgb_ctx* ctx, const uint64_t* d_A, const uint64_t* d_B, uint64_t*
 int cgb_beaver_matmul_finish(cgb_ctx* ctx, const uint64_t* d_E, const uint64_t* d_F, const uint64_t* d_U,
                              const uint64_t* d_V, const uint64_t* d_Z, uint64_t* d_C, uint32_t M, uint32_t K,
                              uint32_t N, int share, int f);
+/* the same starting from the two halves of the opening: d_mine = this side's [E_i | F_i] (M*K + K*N words), d_peer the
+ * peer's; d_mine is OPENED IN PLACE (mine += peer) by the launch that also forms V + F for share 0. */
+int cgb_beaver_matmul_finish_open(cgb_ctx* ctx, uint64_t* d_mine, const uint64_t* d_peer, const uint64_t* d_U,
+                                  const uint64_t* d_V, const uint64_t* d_Z, uint64_t* d_C, uint32_t M, uint32_t K,
+                                  uint32_t N, int share, int f);
 
 /* Pipe selection of cgb_matmul / cgb_beaver_matmul_finish for this context: -1 = CGB_MATMUL_IMPL from the environment or auto
  * (default), 0 = auto by shape, 1 = integer pipe (IMAD tiles), 2 = tensor pipe (tcgen05 int8 limbs).  Same bits either way. */
@@ -235,8 +240,30 @@ int cgb_apply_gradient(cgb_ctx* ctx, const uint64_t* d_W, const uint64_t* d_d, u
 int cgb_rowmul_beaver_finish(cgb_ctx* ctx, const uint64_t* d_e, const uint64_t* d_fv, const uint64_t* d_a,
                              const uint64_t* d_b, const uint64_t* d_c, uint64_t* d_out, uint64_t rows, uint32_t D,
                              int share, int f);
+/* weight-gradient step in one pass (gcn.h:673-678): d' = trunc_i(d * gs), W' = W - trunc_i(d' * lr); d_d_out may be NULL
+ * or alias d_d, d_W_out may alias d_W. */
+int cgb_scale_apply_gradient(cgb_ctx* ctx, const uint64_t* d_W, const uint64_t* d_d, uint64_t gs, uint64_t lr,
+                             uint64_t* d_d_out, uint64_t* d_W_out, uint64_t n, int f, int share);
+/* weight averaging (gcn.h:747-777): every d_out[k] = trunc_i( (sum_j d_in[j]) * c ); HOST arrays of device pointers
+ * (<= 16 inputs, <= 4 outputs); outputs may alias inputs. */
+int cgb_avg_public(cgb_ctx* ctx, const uint64_t* const* d_in, uint32_t n_in, uint64_t c, uint64_t* const* d_out,
+                   uint32_t n_out, uint64_t n, int f, int share);
+/* the same with the opening folded in: e = mine + peer over the message layout [ rows x D words | rows scaler words ] that
+ * sci::twoPartyGCNVectorScale's parties exchange (gcn.h:247,476); saves the separate pass that opens the message. */
+int cgb_rowmul_beaver_finish_open(cgb_ctx* ctx, const uint64_t* d_mine, const uint64_t* d_peer, const uint64_t* d_a,
+                                  const uint64_t* d_b, const uint64_t* d_c, uint64_t* d_out, uint64_t rows, uint32_t D,
+                                  int share, int f);
+/* one launch for the two halves of a Beaver message: out[0,n0) = a0 - b0, out[n0,n0+n1) = a1 - b1 (a1 == NULL: 0 - b1),
+ * i.e. [X - U | W - V] of twoPartyGCNMatMul (gcn.h:233) or [x - a | s - b] of twoPartyGCNVectorScale (gcn.h:247). */
+int cgb_sub_pair(cgb_ctx* ctx, const uint64_t* d_a0, const uint64_t* d_b0, uint64_t n0, const uint64_t* d_a1,
+                 const uint64_t* d_b1, uint64_t n1, uint64_t* d_out);
 int cgb_cond_add(cgb_ctx* ctx, const uint64_t* d_v, const uint64_t* d_u, const uint8_t* d_cond, uint64_t* d_out,
                  uint64_t rows, uint32_t D);
+/* n_seg independent device-to-device copies of n_words[j] words in one launch per 16 segments (HOST arrays of device
+ * pointers; segments must not overlap): all messages of one communication round between parties hosted on one GPU
+ * (the single-process form of CommSync::sendShareVecVec / recvShareVecVec, include/comm_sync.h:245-277). */
+int cgb_copy_segments(cgb_ctx* ctx, uint64_t* const* d_dst, const uint64_t* const* d_src, const uint64_t* n_words,
+                      uint32_t n_seg);
 int cgb_transpose(cgb_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint32_t rows, uint32_t cols);
 int cgb_encode(cgb_ctx* ctx, const double* d_x, uint64_t* d_out, uint64_t n, int f);
 int cgb_decode(cgb_ctx* ctx, const uint64_t* d_v, double* d_out, uint64_t n, int f);
@@ -251,6 +278,11 @@ int cgb_prg_fill(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, uint64_t 
 /* out = in - PRG(...): the server side of the OM online message (x1 - r) without materialising r */
 int cgb_prg_mask_sub(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, uint64_t word_offset,
                      const uint64_t* d_in, uint64_t* d_out, uint64_t n_words);
+/* out = sum_j d_in[j] + sum_k PRG(key, streams[k], 0 ...): the GatherComp additions of one destination party
+ * (gcn.h:456-463) with the OM mask shares regenerated in registers.  `streams` and `d_in` are HOST arrays (<= 16 each);
+ * out may alias an input. */
+int cgb_prg_sum(cgb_ctx* ctx, const uint32_t key[8], const uint64_t* streams, uint32_t n_streams,
+                const uint64_t* const* d_in, uint32_t n_in, uint64_t* d_out, uint64_t n_words);
 
 /* ---- 2PC-RESIDUAL stand-ins (IDEAL FUNCTIONALITY, NOT SECURE) ------------------------------------------------- */
 /* sci::twoPartyGCNRelu (gcn.h:549) and the ReLU' mask of sci::twoPartyGCNBackwardNNWithoutAH (gcn.h:705) stay on the
@@ -258,6 +290,11 @@ int cgb_prg_mask_sub(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, uint6
  * after the helper has sent its share to the owner -- a stand-in for the 2PC, exact integer arithmetic:
  *   relu:      out = (int64)(a0+a1) > 0 ? a0+a1 : 0
  *   relu_grad: out = (int64)(z0+z1) > 0 ? g0+g1 : 0                                                              */
+/* the stand-in and the re-sharing of its result in one pass: out = relu-or-gate(...) - PRG(key, stream, 0 ...), i.e. the
+ * owner's new share when the helper's is the PRG stream; d_z0 == d_z1 == NULL: ReLU of a, else ReLU'(z) applied to a. */
+int cgb_ideal_relu_reshare(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, const uint64_t* d_a0,
+                           const uint64_t* d_a1, const uint64_t* d_z0, const uint64_t* d_z1, uint64_t* d_out,
+                           uint64_t n_words);
 int cgb_ideal_relu(cgb_ctx* ctx, const uint64_t* d_a0, const uint64_t* d_a1, uint64_t* d_out, uint64_t n);
 int cgb_ideal_relu_grad(cgb_ctx* ctx, const uint64_t* d_g0, const uint64_t* d_g1, const uint64_t* d_z0,
                         const uint64_t* d_z1, uint64_t* d_out, uint64_t n);

@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.mark.parametrize("M,K,N", [(1, 1, 1), (5, 3, 2), (130, 17, 7), (257, 1433, 16), (300, 64, 40), (129, 500, 3),
-                                    (64, 128, 256), (1000, 33, 65)])
+                                    (64, 128, 256), (1000, 33, 65), (16, 21168, 40), (7, 1354, 16), (16, 1354, 7),
+                                    (32, 5000, 64), (3, 700, 2)])
 def test_matmul_matches_oracle(cgb, oracle, M, K, N):
     rng = np.random.default_rng(M * 7 + K * 3 + N)
     A, B = rand_u64(rng, M, K), rand_u64(rng, K, N)
@@ -270,3 +271,109 @@ def test_tensor_core_matmul_matches_oracle(cgb, oracle, M, K, N, monkeypatch):
                 want = oracle.beaver_matmul_finish(E, F, U, V, Z, share, f)
                 got = cgb.beaver_matmul_finish(to_dev(E), to_dev(F), to_dev(U), to_dev(V), to_dev(Z), share, f)
                 assert np.array_equal(to_np(got), want), (share, f)
+
+
+# ---- fused forms the engine issues (one launch where the plain forms take two or three) ------------------------------------
+@pytest.mark.parametrize("M,K,N", [(9, 6, 4), (700, 500, 16), (1433, 1354, 16), (300, 128, 256), (16, 9000, 40), (16, 1354, 7)])
+@pytest.mark.parametrize("f", [-1, 16])
+def test_beaver_matmul_finish_open_matches_oracle(cgb, oracle, M, K, N, f):
+    rng = np.random.default_rng(M + K + N + 1)
+    U, V, Z = rand_u64(rng, M, K), rand_u64(rng, K, N), rand_u64(rng, M, N)
+    mine, peer = rand_u64(rng, M * K + K * N), rand_u64(rng, M * K + K * N)
+    opened = mine + peer
+    E, F = opened[:M * K].reshape(M, K), opened[M * K:].reshape(K, N)
+    for share in (0, 1):
+        want = oracle.beaver_matmul_finish(E, F, U, V, Z, share, f)
+        m = to_dev(mine)
+        got = cgb.beaver_matmul_finish_open(m, to_dev(peer), to_dev(U), to_dev(V), to_dev(Z), share, f)
+        assert np.array_equal(to_np(got), want)
+        assert np.array_equal(to_np(m), opened)  # the message is opened in place
+
+
+@pytest.mark.parametrize("rows,D", [(1, 1), (11, 6), (1354, 16), (500, 7), (0, 4)])
+def test_rowmul_finish_open_and_sub_pair_match_oracle(cgb, oracle, rows, D):
+    rng = np.random.default_rng(rows * 31 + D)
+    a, c, x = rand_u64(rng, rows, D), rand_u64(rng, rows, D), rand_u64(rng, rows, D)
+    b, sc = rand_u64(rng, rows), rand_u64(rng, rows)
+    mine, peer = rand_u64(rng, rows * D + rows), rand_u64(rng, rows * D + rows)
+    opened = mine + peer
+    e, fv = opened[:rows * D].reshape(rows, D), opened[rows * D:]
+    if rows:
+        for share in (0, 1):
+            for f in (-1, 16):
+                want = oracle.rowmul_beaver_finish(e, fv, a, b, c, share, f)
+                got = cgb.rowmul_beaver_finish_open(to_dev(mine), to_dev(peer), to_dev(a), to_dev(b), to_dev(c), share, f)
+                assert np.array_equal(to_np(got), want)
+    # the message builder: [x - a | scaler - b], and the helper's form with a zero scaler share
+    got = to_np(cgb.sub_pair(to_dev(x), to_dev(a), to_dev(sc), to_dev(b)))
+    assert np.array_equal(got, np.concatenate([(x - a).ravel(), sc - b]))
+    got = to_np(cgb.sub_pair(to_dev(x), to_dev(a), None, to_dev(b)))
+    assert np.array_equal(got, np.concatenate([(x - a).ravel(), (0 - b.astype(np.uint64)).astype(np.uint64)]))
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 300, 100_003])
+@pytest.mark.parametrize("n_streams,n_in", [(1, 2), (3, 2), (1, 4), (0, 3), (2, 0), (7, 8)])
+def test_prg_sum_matches_oracle(cgb, oracle, n, n_streams, n_in):
+    key = [45, 0, 1, 2, 3, 4, 5, 6]
+    rng = np.random.default_rng(n + 17 * n_streams + n_in)
+    streams = [int(s) for s in rng.integers(1, 2**62, size=n_streams)]
+    ins = [rand_u64(rng, n) for _ in range(n_in)]
+    want = np.zeros(n, dtype=np.uint64)
+    for s in streams:
+        want = want + oracle.prg_fill(key, s, 0, n)
+    for x in ins:
+        want = want + x
+    got = cgb.prg_sum(key, streams, [to_dev(x) for x in ins], n_words=n)
+    assert np.array_equal(to_np(got), want)
+    if n_in:  # out may alias an input
+        d = [to_dev(x) for x in ins]
+        cgb.prg_sum(key, streams, d, n_words=n, out=d[0])
+        assert np.array_equal(to_np(d[0]), want)
+
+
+def test_copy_segments(cgb):
+    rng = np.random.default_rng(5)
+    sizes = [1, 0, 7, 4096, 100_003] + [33] * 20  # > 16 segments: two launches; a zero-length one in the middle
+    srcs = [to_dev(rand_u64(rng, n)) for n in sizes]
+    dsts = [cgb.empty(n) for n in sizes]
+    before = cgb.launches
+    cgb.copy_segments(dsts, srcs)
+    assert cgb.launches - before == 2
+    for d, s in zip(dsts, srcs):
+        assert np.array_equal(to_np(d), to_np(s))
+    # unaligned views take the word-wise path
+    a, b = to_dev(rand_u64(rng, 101)), cgb.empty(101)
+    cgb.copy_segments([b[1:]], [a[1:]])
+    assert np.array_equal(to_np(b[1:]), to_np(a[1:]))
+
+
+def test_scale_apply_avg_and_relu_reshare_match_oracle(cgb, oracle):
+    rng = np.random.default_rng(77)
+    n = 1433 * 16 + 3
+    W, d = rand_u64(rng, n), rand_u64(rng, n)
+    gs, lr = 0x1F3, 0x28F
+    for share in (0, 1):
+        ds = oracle.scale_public(d, gs, 16, share)
+        want_W = oracle.apply_gradient(W, ds, lr, 16, share)
+        dW, dd = to_dev(W), to_dev(d)
+        cgb.scale_apply_gradient(dW, dd, gs, lr, share)
+        assert np.array_equal(to_np(dd), ds) and np.array_equal(to_np(dW), want_W)
+        # average of 3 replicas' shares into 3 places, one of them an input
+        ins = [rand_u64(rng, n) for _ in range(3)]
+        want = oracle.scale_public(ins[0] + ins[1] + ins[2], 0x5555, 16, share)
+        dins = [to_dev(x) for x in ins]
+        outs = [cgb.empty(n), dins[0], dins[2]]
+        cgb.avg_public(dins, 0x5555, outs, share)
+        for o in outs:
+            assert np.array_equal(to_np(o), want)
+    # stand-in + re-share: relu(a0 + a1) - PRG, and the gated form
+    key = [3, 1, 4, 1, 5, 9, 2, 6]
+    a0, a1, z0, z1 = (rand_u64(rng, n) for _ in range(4))
+    a0[:4], a1[:4] = np.array([5, 2**63, 0, 7], dtype=np.uint64), np.array([0, 0, 0, 2**64 - 7], dtype=np.uint64)
+    ks = oracle.prg_fill(key, 99, 0, n)
+    v = a0 + a1
+    want = np.where(v.astype(np.int64) > 0, v, 0).astype(np.uint64) - ks
+    assert np.array_equal(to_np(cgb.ideal_relu_reshare(key, 99, to_dev(a0), to_dev(a1))), want)
+    gate = (z0 + z1).astype(np.int64) > 0
+    want = np.where(gate, v, 0).astype(np.uint64) - ks
+    assert np.array_equal(to_np(cgb.ideal_relu_reshare(key, 99, to_dev(a0), to_dev(a1), to_dev(z0), to_dev(z1))), want)
