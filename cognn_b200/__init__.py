@@ -156,6 +156,14 @@ class Context:
         self.check(self.lib.cgb_flag_wait(self.handle, C.c_void_p(int(flag_ptr)), int(value) & 0xFFFFFFFF, int(mode),
                                           C.c_void_p(int(err_ptr)) if err_ptr else None))
 
+    def peer_round(self, segs, links, slot_words, ctas_per_seg=0, err_ptr=None):
+        """segs: [(src_ptr, dst_ptr, n_words, link)] (push segments first), links: [(seq, done, wait_flag, signal_flag, recv)]
+        (raw device addresses)."""
+        sa = (_lib.XSeg * max(len(segs), 1))(*[_lib.XSeg(int(a), int(b), int(n), int(l)) for a, b, n, l in segs])
+        la = (_lib.XLink * max(len(links), 1))(*[_lib.XLink(int(a), int(b), int(c), int(d), int(r)) for a, b, c, d, r in links])
+        self.check(self.lib.cgb_peer_round(self.handle, sa, len(segs), la, len(links), int(slot_words), int(ctas_per_seg),
+                                           C.c_void_p(int(err_ptr)) if err_ptr else None))
+
     def set_matmul_impl(self, impl):
         """'auto' | 'imad' | 'tc' | None (environment)."""
         self.check(self.lib.cgb_ctx_set_matmul_impl(self.handle, {None: -1, "auto": 0, "imad": 1, "tc": 2}[impl]))

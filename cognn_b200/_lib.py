@@ -62,6 +62,8 @@ SIGNATURES = {
     "cgb_probe_imad_peak": (C.c_int, [ctx_p, C.POINTER(C.c_double)]),
     "cgb_probe_tensor_i8_peak": (C.c_int, [ctx_p, C.POINTER(C.c_double)]),
     "cgb_ipc_export": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p]),
+    "cgb_peer_round": (C.c_int, [ctx_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32,
+                                 C.c_void_p]),
     "cgb_ipc_open": (C.c_int, [ctx_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "cgb_ipc_close": (C.c_int, [ctx_p, C.c_void_p]),
     "cgb_peer_copy": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]),
@@ -140,6 +142,17 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+class XSeg(C.Structure):
+    """cgb_xseg (include/cognn_b200.h)"""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("n_words", C.c_uint64), ("link", C.c_uint32)]
+
+
+class XLink(C.Structure):
+    """cgb_xlink (include/cognn_b200.h)"""
+    _fields_ = [("seq", C.c_void_p), ("done", C.c_void_p), ("wait_flag", C.c_void_p), ("signal_flag", C.c_void_p),
+                ("recv", C.c_uint32)]
 
 
 def key_array(key):

@@ -17,6 +17,8 @@
 // so a late waiter never misses a signal.
 #include <cuda.h>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace {
@@ -118,6 +120,99 @@ __global__ void __launch_bounds__(SA_THREADS) scatter_add_rows_v1_kernel(const u
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ---- one protocol round between parties on different GPUs: push into the peer's arena, flag, consume, acknowledge -----------
+// Every ordered pair of parties (a "link") owns a double-buffered slot pair in the RECEIVER's arena, a data flag in the
+// receiver's memory and an acknowledge flag in the sender's.  The s-th round that carries data over a link uses slot s & 1.
+//   push (MODE 0): wait until the peer has consumed round s - 2 (ack >= s - 2), copy the segments of this link into the peer's
+//                  slot over NVLink, and the CTA that finishes last raises the peer's data flag to s;
+//   recv (MODE 1): wait for the data flag >= s, copy the segments out of the local slot to where the protocol wants them, and
+//                  the CTA that finishes last raises the peer's acknowledge flag to s.
+// The round number s lives in DEVICE memory (link.seq, advanced by the finishing CTA), never in a kernel argument, so a CUDA
+// graph that recorded these launches replays correctly.  All waits are bounded and report through *err.
+struct XSeg {
+    const u64* src;
+    u64* dst;
+    uint64_t n_words;
+    uint32_t link;
+};
+struct XLink {
+    uint32_t* seq;               // rounds completed on this link in this direction (local)
+    uint32_t* done;              // CTA completion counter (local, self-resetting)
+    const uint32_t* wait_flag;   // local flag the PEER writes
+    uint32_t* signal_flag;       // flag in the peer's memory
+    uint32_t n_ctas;             // CTAs of this launch that work on this link
+    uint32_t recv;               // 0: push link, 1: recv link
+};
+struct XArgs {
+    XSeg seg[16];
+    XLink link[16];
+    uint64_t slot_words;
+    uint32_t* err;
+    uint32_t max_polls;
+};
+
+// One launch carries both directions: the push segments come first in blockIdx.y, so their CTAs are dispatched before any
+// CTA that waits for a peer's data -- a rank never blocks its own outgoing messages behind its incoming ones.
+__global__ void __launch_bounds__(256) peer_round_kernel(const __grid_constant__ XArgs a) {
+    const XSeg& sg = a.seg[blockIdx.y];
+    const XLink& lk = a.link[sg.link];
+    const uint32_t MODE = lk.recv;
+    __shared__ uint32_t s_round;
+    if (threadIdx.x == 0) {
+        uint32_t seq;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seq) : "l"(lk.seq) : "memory");
+        const uint32_t s = seq + 1;
+        const uint32_t need = MODE == 0 ? s - 2 : s;  // push: the slot's previous round was consumed; recv: this round has arrived
+        if (MODE == 1 || s > 2) {
+            uint32_t v = 0, polls = 0;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(lk.wait_flag) : "memory");
+                if ((int32_t)(v - need) >= 0) break;
+                if (++polls > a.max_polls) {
+                    if (a.err) atomicExch(a.err, MODE == 0 ? 2u : 3u);
+                    break;
+                }
+                __nanosleep(40);
+            }
+        }
+        s_round = s;
+    }
+    __syncthreads();
+    const uint32_t s = s_round;
+    const u64* src = sg.src + (MODE == 1 ? (size_t)(s & 1u) * a.slot_words : 0);
+    u64* dst = sg.dst + (MODE == 0 ? (size_t)(s & 1u) * a.slot_words : 0);
+    const uint64_t n = sg.n_words;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+        const uint64_t n2 = n >> 1;
+        const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(src);
+        ulonglong2* d2 = reinterpret_cast<ulonglong2*>(dst);
+        uint64_t k = i;
+        for (; k + 3 * stride < n2; k += 4 * stride) {  // four 16-byte loads in flight per thread (NVLink round trip)
+            // L2-only loads: in recv mode the slot was written by the peer GPU, and L1 knows nothing about remote writes
+            const ulonglong2 v0 = __ldcg(s2 + k), v1 = __ldcg(s2 + k + stride), v2 = __ldcg(s2 + k + 2 * stride),
+                             v3 = __ldcg(s2 + k + 3 * stride);
+            d2[k] = v0; d2[k + stride] = v1; d2[k + 2 * stride] = v2; d2[k + 3 * stride] = v3;
+        }
+        for (; k < n2; k += stride) d2[k] = __ldcg(s2 + k);
+        if (i == 0 && (n & 1)) dst[n - 1] = __ldcg(src + n - 1);
+    } else {
+        for (uint64_t k = i; k < n; k += stride) dst[k] = __ldcg(src + k);
+    }
+    __threadfence_system();  // this thread's stores (peer memory in push mode) are visible system-wide before the CTA reports
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(lk.done, 1u);
+        if (prev + 1 == lk.n_ctas) {  // every CTA of this link has finished (and has read seq)
+            atomicExch(lk.done, 0u);
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(lk.seq), "r"(s) : "memory");
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(lk.signal_flag), "r"(s) : "memory");
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -140,6 +235,45 @@ int cgb_flag_wait(cgb_ctx* ctx, const uint32_t* d_flag, uint32_t value, int mode
     }
     flag_wait_kernel<<<1, 1, 0, ctx->stream>>>(d_flag, value, d_err, 2000000u);
     CGB_CHECK_LAUNCH(ctx, "flag_wait_kernel");
+    return CGB_OK;
+}
+
+int cgb_peer_round(cgb_ctx* ctx, const cgb_xseg* segs, uint32_t n_seg, const cgb_xlink* links, uint32_t n_links,
+                   uint64_t slot_words, uint32_t ctas_per_seg, uint32_t* d_err) {
+    CGB_REQUIRE(ctx, n_seg <= 16 && n_links <= 16 && (n_seg == 0 || (segs && links)), "cgb_peer_round: at most 16 segments / links");
+    if (n_seg == 0) return CGB_OK;
+    if (ctas_per_seg == 0) ctas_per_seg = 8;
+    XArgs a;
+    memset(&a, 0, sizeof(a));
+    uint32_t per_link[16] = {0};
+    bool seen_recv = false;
+    for (uint32_t i = 0; i < n_seg; ++i) {
+        CGB_REQUIRE(ctx, segs[i].link < n_links && segs[i].src && segs[i].dst, "cgb_peer_round: bad segment");
+        const bool r = links[segs[i].link].recv != 0;
+        CGB_REQUIRE(ctx, r || !seen_recv, "cgb_peer_round: push segments must precede recv segments");
+        seen_recv = seen_recv || r;
+        a.seg[i].src = (const u64*)segs[i].src;
+        a.seg[i].dst = (u64*)segs[i].dst;
+        a.seg[i].n_words = segs[i].n_words;
+        a.seg[i].link = segs[i].link;
+        per_link[segs[i].link] += ctas_per_seg;
+    }
+    for (uint32_t l = 0; l < n_links; ++l) {
+        CGB_REQUIRE(ctx, per_link[l] > 0, "cgb_peer_round: a link without segments");
+        CGB_REQUIRE(ctx, links[l].seq && links[l].done && links[l].wait_flag && links[l].signal_flag, "cgb_peer_round: null link field");
+        a.link[l].seq = links[l].seq;
+        a.link[l].done = links[l].done;
+        a.link[l].wait_flag = links[l].wait_flag;
+        a.link[l].signal_flag = links[l].signal_flag;
+        a.link[l].n_ctas = per_link[l];
+        a.link[l].recv = links[l].recv ? 1u : 0u;
+    }
+    a.slot_words = slot_words;
+    a.err = d_err;
+    a.max_polls = 10000000u;  // ~2-10 s
+    const dim3 grid(ctas_per_seg, n_seg);
+    peer_round_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+    CGB_CHECK_LAUNCH(ctx, "peer_round_kernel");
     return CGB_OK;
 }
 

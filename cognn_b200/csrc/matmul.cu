@@ -253,7 +253,7 @@ int run_matmul(cgb_ctx* ctx, MatmulArgs a) {
         else if (pl.BN == 16) launch_cfg<32, 16, 16, 2, 1>(ctx, a);
         else launch_cfg<32, 8, 16, 1, 1>(ctx, a);
     } else if (pl.BN == 64) launch_cfg<128, 64, 16, 8, 4>(ctx, a);
-    else if (pl.BN == 16) launch_cfg<128, 16, 16, 4, 2>(ctx, a);
+    else if (pl.BN == 16) launch_cfg<128, 16, 16, 4, 2>(ctx, a);  // (128x16 tm8 and 256x16 tm8 tiles measured slower: r2v probe)
     else launch_cfg<256, 8, 16, 8, 1>(ctx, a);
     CGB_CHECK_LAUNCH(ctx, "matmul_kernel");
     ctx->last_kernel = pl.BM == 32 ? "matmul_kernel<32,*,16,*,*> (IMAD.WIDE u64 tiles, short M)" : pl.BN == 64 ? "matmul_kernel<128,64,16,8,4> (IMAD.WIDE u64 tiles)"

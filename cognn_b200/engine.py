@@ -22,7 +22,7 @@ class CgeConfig(C.Structure):
 ENGINE_SYMBOLS = ["cge_last_error", "cge_nccl_unique_id", "cge_create_loopback", "cge_create_nccl", "cge_destroy",
                   "cge_add_party", "cge_setup", "cge_run", "cge_download", "cge_message_count", "cge_message_info",
                   "cge_message_data", "cge_words_sent", "cge_rounds", "cge_launch_count", "cge_seconds_online", "cge_seconds_offline", "cge_seconds_residual_host",
-                  "cge_metrics_count", "cge_metrics_get", "cge_build_party_graph", "cge_graph_replays"]
+                  "cge_metrics_count", "cge_metrics_get", "cge_build_party_graph", "cge_graph_replays", "cge_plane"]
 
 
 def load_host():
@@ -57,6 +57,8 @@ def load_host():
     h.cge_build_party_graph.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_int] + [C.c_void_p] * 6 + \
         [C.POINTER(C.c_uint64)] * 3
     h.cge_nccl_unique_id.argtypes = [C.c_void_p]
+    h.cge_plane.restype = C.c_char_p
+    h.cge_plane.argtypes = [C.c_void_p]
     _host = h
     return h
 
@@ -167,6 +169,11 @@ class Engine:
     @property
     def words_sent(self):
         return int(self.h.cge_words_sent(self.e))
+
+    @property
+    def plane(self):
+        """The message plane the rounds run on (decided in setup: peer memory when every rank could map its peers)."""
+        return self.h.cge_plane(self.e).decode()
 
     @property
     def rounds(self):

@@ -151,6 +151,7 @@ int cge_message_data(cge_engine* h, uint64_t i, uint64_t* out, uint64_t capacity
 }
 uint64_t cge_words_sent(cge_engine* h) { return h->comm->words_sent; }
 uint64_t cge_rounds(cge_engine* h) { return h->comm->rounds; }
+const char* cge_plane(cge_engine* h) { return h->comm->plane(); }
 uint64_t cge_launch_count(cge_engine* h) { return h->eng->eager_launches() + h->eng->replayed_launches(); }
 uint64_t cge_graph_replays(cge_engine* h) { return h->eng->graph_replays(); }
 double cge_seconds_online(cge_engine* h) { return h->eng->seconds_online; }

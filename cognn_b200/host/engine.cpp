@@ -901,6 +901,15 @@ void SSGcnEngine::setup() {
         ck(ctx, cgb_transpose(ctx, s.X_backup.p, s.h_t[0].p, s.n, im.F), "transpose");
     });
     ck(im.main_ctx, cgb_ctx_sync(im.main_ctx), "sync");
+    {   // the most words one party sends another in one online round (two sides may share a pair: x 2), for the plane's arenas
+        size_t nmax = 0;
+        for (uint32_t v : im.n_of) nmax = std::max<size_t>(nmax, v);
+        const size_t F = im.F, H = im.H, C = im.C, D = std::max(H, C);
+        size_t m = nmax * F + std::max(F * H, nmax * H);            // Beaver product messages [E | F]
+        m = std::max(m, nmax * D + std::max(D * D, nmax * D));
+        m = std::max(m, 2 * nmax * D + nmax);                        // row scaling, residual operands, update blocks
+        im.comm->reserve(2 * m + 64);
+    }
 }
 
 static DMat* sel_z0(Side& s, int) { return &s.z[0]; }

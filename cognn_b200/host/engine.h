@@ -44,6 +44,11 @@ public:
     // all parties have reached this point and their streams are idle (no data message; used between the offline and the
     // online phase so that one party's dealer time is not counted as another party's online waiting time)
     virtual void barrier() {}
+    // the engine announces, once its shapes are known, the most words one party sends another in one round; a plane may use it
+    // to set up fixed receive arenas (NcclComm: peer-memory rounds instead of ncclSend / ncclRecv).  No data moves here.
+    virtual void reserve(size_t /*max_words_per_pair_round*/) {}
+    // name of the plane the rounds actually run on ("loopback", "nccl", "peer-memory (nccl bootstrap)")
+    virtual const char* plane() const { return "loopback"; }
     bool record = false;        // keep a copy of every message sent by a local party (tests)
     uint64_t cur_iter = 0;
     std::vector<Message> transcript;

@@ -153,6 +153,34 @@ int cgb_flag_wait(cgb_ctx* ctx, const uint32_t* d_flag, uint32_t value, int mode
 /* name of the kernel the last cgb_gather_sum* / cgb_matmul dispatch of this context chose (static string) */
 const char* cgb_ctx_last_kernel(cgb_ctx* ctx);
 /* CUDA IPC plumbing for the peer buffers (one process per GPU): d_ptr must come from cgb_malloc; handle is 64 bytes */
+/* One protocol round between parties on different GPUs of a box without a library collective: the replacement of
+ * CommSync::sendShareVecVec / recvShareVecVec (include/comm_sync.h:245-277) used by the engine's message plane.
+ * A "link" is an ordered pair of parties; its receiver owns a double-buffered slot pair (2 * slot_words words, mapped by the
+ * sender with cgb_ipc_open), a data flag (receiver's memory) and an acknowledge flag (sender's memory).
+ * Both directions of a round go into ONE launch (a link says which it is); push segments must come first in `segs`, so a
+ * rank's outgoing data is never queued behind CTAs that wait for incoming data.
+ *   push link:     for every segment, wait until the peer acknowledged round s - 2 of the link, copy src -> dst + (s & 1) *
+ *                  slot_words (dst = slot 0 address inside the PEER's arena); the last CTA of a link raises signal_flag to s.
+ *   recv link:     wait for wait_flag >= s, copy src + (s & 1) * slot_words -> dst (src = slot 0 address inside the local
+ *                  arena); the last CTA of a link raises signal_flag (the peer's acknowledge flag) to s.
+ * s = *seq + 1 is read and advanced ON THE DEVICE, so the launches can be recorded into a CUDA graph.  seq, done and the
+ * flags start at zero.  At most 16 segments and 16 links per call; waits are bounded (*d_err = 2 / 3 on a push / recv
+ * timeout). */
+typedef struct {
+    const uint64_t* src;
+    uint64_t* dst;
+    uint64_t n_words;
+    uint32_t link; /* index into the links array */
+} cgb_xseg;
+typedef struct {
+    uint32_t* seq;             /* local: rounds completed on this link in this direction */
+    uint32_t* done;            /* local: CTA completion counter, self-resetting */
+    const uint32_t* wait_flag; /* local flag the peer writes (push: its acknowledgements, recv: its data flag) */
+    uint32_t* signal_flag;     /* flag in the peer's memory (push: its data flag, recv: its acknowledge flag) */
+    uint32_t recv;             /* 0: push link, 1: recv link */
+} cgb_xlink;
+int cgb_peer_round(cgb_ctx* ctx, const cgb_xseg* segs, uint32_t n_seg, const cgb_xlink* links, uint32_t n_links,
+                   uint64_t slot_words, uint32_t ctas_per_seg, uint32_t* d_err);
 int cgb_ipc_export(cgb_ctx* ctx, void* d_ptr, void* out_handle64);
 int cgb_ipc_open(cgb_ctx* ctx, const void* handle64, void** d_peer_out);
 int cgb_ipc_close(cgb_ctx* ctx, void* d_peer);

@@ -46,6 +46,8 @@ int cge_message_info(cge_engine* h, uint64_t i, uint64_t* iter, int* src, int* d
 int cge_message_data(cge_engine* h, uint64_t i, uint64_t* out, uint64_t capacity);
 uint64_t cge_words_sent(cge_engine* h);
 uint64_t cge_rounds(cge_engine* h);
+/* the message plane the protocol rounds run on: "loopback", "nccl", or "peer-memory rounds over NVLink (...)" */
+const char* cge_plane(cge_engine* h);
 uint64_t cge_launch_count(cge_engine* h);   /* kernels launched, including those inside replayed CUDA graphs */
 /* From the second epoch on, the online phase of each GAS iteration is one CUDA graph (captured at its first later
  * occurrence, replayed afterwards; COGNN_B200_GRAPHS=0 or record_messages keep the eager path).  Number of replays: */

@@ -87,7 +87,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         online = float(t.item())
     rec = {"bench": "secure_gcn_" + ("epoch" if args.mode == "train" else "inference"), "shape": args.shape, "parties": T,
-           "plane": "nccl" if world > 1 else "loopback(1 GPU)", "N": g["N"], "E": g["E"],
+           "plane": e.plane if world > 1 else "loopback(1 GPU)", "N": g["N"], "E": g["E"],
            "inter_party_edges": g["inter_party_edges"], "cfg": {k: g["cfg"][k] for k in ("input_dim", "hidden_dim", "num_labels")},
            "iterations": iters, "online_s": online,
            "online_mode": "CUDA-graph replay of each iteration's online phase" if graphs else "eager launches",
