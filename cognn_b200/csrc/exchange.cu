@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(256) peer_round_kernel(const __grid_constant__
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seq) : "l"(lk.seq) : "memory");
         const uint32_t s = seq + 1;
         const uint32_t need = MODE == 0 ? s - 2 : s;  // push: the slot's previous round was consumed; recv: this round has arrived
-        if (MODE == 1 || s > 2) {
+        uint32_t failed = 0;  // a run that already timed out once does not wait again: it ends quickly and reports
+        if (a.err) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(failed) : "l"(a.err) : "memory");
+        if (!failed && (MODE == 1 || s > 2)) {
             uint32_t v = 0, polls = 0;
             for (;;) {
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(lk.wait_flag) : "memory");
@@ -270,7 +272,7 @@ int cgb_peer_round(cgb_ctx* ctx, const cgb_xseg* segs, uint32_t n_seg, const cgb
     }
     a.slot_words = slot_words;
     a.err = d_err;
-    a.max_polls = 10000000u;  // ~2-10 s
+    a.max_polls = 8000000u;  // several seconds: far beyond any skew between ranks inside an iteration (cold first epoch included)
     const dim3 grid(ctas_per_seg, n_seg);
     peer_round_kernel<<<grid, 256, 0, ctx->stream>>>(a);
     CGB_CHECK_LAUNCH(ctx, "peer_round_kernel");

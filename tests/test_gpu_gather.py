@@ -405,3 +405,29 @@ def test_gather_sum_signal_blocks_and_flags(cgb, oracle, D):
     torch.cuda.synchronize()
     assert np.array_equal(to_np(bufs[0])[:700], dense[:700]) and flags.tolist() == [7] * nb
     csr.destroy()
+
+
+@pytest.mark.parametrize("n_edges,D", [(300_000, 16), (600_000, 7), (1_500_000, 40), (2_500_000, 16)])
+def test_gather_sum_every_chunk_size_class(cgb, oracle, n_edges, D):
+    """The chunk size follows the edge count (16 / 32 / 64 / 128 edges below 2^18 / 2^21 / 2^24 / above): the small tests above
+    run 16-edge chunks, the 2^24- and 10^8-edge tests 128; these sizes run the 32- and 64-edge classes, with hub rows that span
+    hundreds of chunks, empty rows, and delta, against the oracle on every row."""
+    rng = np.random.default_rng(n_edges % 1000 + D)
+    n_dst, n_src = n_edges // 12, n_edges // 10
+    rowptr, col = power_law_csr(rng, n_dst, n_src, n_edges)
+    deg = np.diff(rowptr.astype(np.int64))
+    assert deg.max() > 4000 and (deg == 0).any()
+    x, delta = rand_u64(rng, n_src, D), rand_u64(rng, n_dst, D)
+    csr = cgb.csr_create(to_dev(rowptr, "cpu"), to_dev(col, "cpu"), n_src)
+    dx, dd = to_dev(x), to_dev(delta)
+    for use_delta in (False, True):
+        want = oracle.gather_sum_csr(rowptr, col, x, delta if use_delta else None)
+        for _ in range(2):  # the second launch reuses the self-resetting arrival counters
+            got = cgb.gather_sum(csr, dx, dd if use_delta else None)
+            assert np.array_equal(to_np(got), want)
+    # the compact form on the same CSR
+    nz = to_np(csr.nonempty_rows()).astype(np.int64)
+    want = oracle.gather_sum_csr(rowptr, col, x, None)
+    got = cgb.gather_sum_compact(csr, dx)
+    assert np.array_equal(to_np(got), want[nz])
+    csr.destroy()
