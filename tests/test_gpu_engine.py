@@ -159,3 +159,20 @@ def test_engine_matches_committed_golden_digests():
                     assert got == gold[name][f"W{l}.{rname}{p}"], (name, p, role, l)
         assert len([m for m in e.messages() if not m[3].startswith("setup")]) == gold[name]["n_messages"]
         e.close()
+
+
+def test_engine_launch_budget_per_epoch():
+    """The fused launches of round 2 stay fused: one message builder per Beaver product / row scaling, openings inside the
+    finishes, one launch per loopback round, one for scale + apply, one per weight average.  A 2-party
+    epoch (4 hosted sides) was 634 launches + 27 x up to 4 copies before; the budget leaves room above today's 545 (dealer launches included)."""
+    from cognn_b200 import engine as eng
+
+    g = small_graph(n=70, n_edges=260, F=10, C=4, T=2, seed=42)
+    cfg = dict(input_dim=10, hidden_dim=8, num_labels=4, learning_rate=0.5, train_ratio=0.4, val_ratio=0.2)
+    e = eng.Engine(2, cfg)
+    e.load(g["edges"], g["tid"], g["feats"], g["labels"])
+    l0, r0 = e.launches, e.rounds
+    e.run(6)
+    assert e.rounds - r0 == 27
+    assert e.launches - l0 <= 600, e.launches - l0
+    e.close()
