@@ -202,9 +202,9 @@ __global__ void __launch_bounds__(256) peer_round_kernel(const __grid_constant__
     } else {
         for (uint64_t k = i; k < n; k += stride) dst[k] = __ldcg(src + k);
     }
-    __threadfence_system();  // this thread's stores (peer memory in push mode) are visible system-wide before the CTA reports
-    __syncthreads();
+    __syncthreads();  // every thread's stores happen-before thread 0's fence below (cumulative): one system fence per CTA
     if (threadIdx.x == 0) {
+        __threadfence_system();  // the CTA's stores (peer memory in push mode) are visible system-wide before it reports
         const uint32_t prev = atomicAdd(lk.done, 1u);
         if (prev + 1 == lk.n_ctas) {  // every CTA of this link has finished (and has read seq)
             atomicExch(lk.done, 0u);

@@ -107,11 +107,14 @@ public:
     // (cgb_peer_round push, then recv) instead of one NCCL group: no proxy thread, no channel set-up, a few microseconds of
     // latency, and the round counters live on the device so the launches replay from a CUDA graph.  Handles travel once, over
     // NCCL.  Pairs whose messages do not fit the slot (or more than 16 messages) keep using ncclSend / ncclRecv, and so does
-    // everything when any rank could not map its peers (different nodes, IPC disabled) or COGNN_B200_PEER_EXCHANGE=0.
+    // everything when any rank could not map its peers (different nodes, IPC disabled) or when the plane is off (see below).
     void reserve(size_t max_words) override {
         if (world_ < 2 || peer_ok_ || max_words == 0) return;
+        // Default: on for more than 4 parties.  Measured: 8 parties 4.5 ms against 6.0 ms per arxiv-shaped
+        // epoch over ncclSend / ncclRecv (rounds with six peers), a tie at 2, and 8 % behind NCCL at 4 parties on the
+        // CiteSeer shape, whose 25 MB product messages pay for the copy out of the slot.  =1 / =0 force it on / off.
         const char* env = getenv("COGNN_B200_PEER_EXCHANGE");
-        int ok = !(env && env[0] == '0') && world_ <= 16;
+        int ok = (env ? env[0] != '0' : world_ > 4) && world_ <= 16;
         cudaStream_t st = (cudaStream_t)cgb_ctx_stream(ctx_);
         const size_t slot = (max_words + 1) & ~(size_t)1;
         size_t free_b = 0, total_b = 0;

@@ -1,4 +1,5 @@
-"""Tests that need two GPUs on the box (skipped otherwise): the engine's epoch with one party per GPU, protocol rounds over the
+"""(COGNN_B200_PEER_EXCHANGE=1 forces the peer plane, which is on by default only above 4 parties.)
+Tests that need two GPUs on the box (skipped otherwise): the engine's epoch with one party per GPU, protocol rounds over the
 peer-memory plane (cgb_peer_round through CUDA-IPC mappings) and over ncclSend / ncclRecv, both bit exact against the epoch
 oracle.  One process per GPU under torchrun, rendezvous on 127.0.0.1."""
 import json
