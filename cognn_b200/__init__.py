@@ -467,6 +467,25 @@ class Context:
         self.check(self.lib.cgb_prg_fill(self.handle, _lib.key_array(key), stream, word_offset, _ptr(out), n_words))
         return out
 
+    def prg_fill_multi(self, key, segs):
+        """segs: [(out, stream_a)] or [(out, stream_a, stream_b, out_b or None)]: out = PRG(a) [+ PRG(b)], out_b = PRG(b)."""
+        m = 2**64 - 1
+        arr = (_lib.PrgSeg * max(len(segs), 1))()
+        for i, sg in enumerate(segs):
+            out, a = sg[0], sg[1]
+            arr[i].out, arr[i].n_words, arr[i].stream_a = self._u64(out).data_ptr(), out.numel(), int(a) & m
+            if len(sg) > 2:
+                arr[i].stream_b, arr[i].has_b = int(sg[2]) & m, 1
+                arr[i].out_b = self._u64(sg[3]).data_ptr() if sg[3] is not None else None
+        self.check(self.lib.cgb_prg_fill_multi(self.handle, _lib.key_array(key), arr, len(segs)))
+
+    def rowmul_sub(self, a, b, c, out=None):
+        rows, D = a.shape
+        out = self.torch.empty_like(a) if out is None else out
+        self.check(self.lib.cgb_rowmul_sub(self.handle, _ptr(self._u64(a)), _ptr(self._u64(b)), _ptr(self._u64(c)), _ptr(out),
+                                           rows, D))
+        return out
+
     def prg_sum(self, key, streams, tensors, n_words=None, out=None):
         """out = sum(tensors) + sum_k PRG(key, streams[k]) (word offset 0)."""
         n = n_words if n_words is not None else tensors[0].numel()

@@ -105,6 +105,8 @@ SIGNATURES = {
     "cgb_scale_apply_gradient": (C.c_int, [ctx_p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u64p, C.c_uint64, C.c_int, C.c_int]),
     "cgb_avg_public": (C.c_int, [ctx_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_int]),
     "cgb_ideal_relu_reshare": (C.c_int, [ctx_p, C.POINTER(C.c_uint32), C.c_uint64, u64p, u64p, u64p, u64p, u64p, C.c_uint64]),
+    "cgb_prg_fill_multi": (C.c_int, [ctx_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32]),
+    "cgb_rowmul_sub": (C.c_int, [ctx_p, u64p, u64p, u64p, u64p, C.c_uint64, C.c_uint32]),
     "cgb_copy_segments": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32]),
     "cgb_cond_add": (C.c_int, [ctx_p, u64p, u64p, C.c_void_p, u64p, C.c_uint64, C.c_uint32]),
     "cgb_transpose": (C.c_int, [ctx_p, u64p, u64p, C.c_uint32, C.c_uint32]),
@@ -142,6 +144,12 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+class PrgSeg(C.Structure):
+    """cgb_prg_seg (include/cognn_b200.h)"""
+    _fields_ = [("out", C.c_void_p), ("out_b", C.c_void_p), ("n_words", C.c_uint64), ("stream_a", C.c_uint64),
+                ("stream_b", C.c_uint64), ("has_b", C.c_uint32)]
 
 
 class XSeg(C.Structure):

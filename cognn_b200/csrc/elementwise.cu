@@ -101,6 +101,13 @@ __global__ void __launch_bounds__(EW_THREADS) rowmul_finish_open_kernel(const u6
     }
 }
 
+__global__ void __launch_bounds__(EW_THREADS) rowmul_sub_kernel(const u64* __restrict__ a, const u64* __restrict__ b,
+                                                               const u64* __restrict__ c, u64* out, uint64_t rows, uint32_t D) {
+    const uint64_t n = rows * D;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = a[i] * __ldg(b + i / D) - c[i];
+}
+
 // two differences in one launch, written back to back: out[0, n0) = a0 - b0, out[n0, n0 + n1) = a1 - b1 (a1 == nullptr: -b1).
 // This is the message [X - U | W - V] of a Beaver product, or [x - a | s - b] of a row scaling.
 __global__ void __launch_bounds__(EW_THREADS) sub_pair_kernel(const u64* __restrict__ a0, const u64* __restrict__ b0, uint64_t n0,
@@ -416,6 +423,16 @@ int cgb_rowmul_beaver_finish_open(cgb_ctx* ctx, const uint64_t* d_mine, const ui
     rowmul_finish_open_kernel<<<ew_blocks(ctx, rows * D), EW_THREADS, 0, ctx->stream>>>(
         (const u64*)d_mine, (const u64*)d_peer, (const u64*)d_a, (const u64*)d_b, (const u64*)d_c, (u64*)d_out, rows, D, share, f);
     CGB_CHECK_LAUNCH(ctx, "rowmul_finish_open_kernel");
+    return CGB_OK;
+}
+int cgb_rowmul_sub(cgb_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_c, uint64_t* d_out, uint64_t rows,
+                   uint32_t D) {
+    CGB_REQUIRE(ctx, (d_a && d_b && d_c && d_out) || rows == 0, "cgb_rowmul_sub: null argument");
+    CGB_REQUIRE(ctx, D > 0, "cgb_rowmul_sub: D must be positive");
+    if (rows == 0) return CGB_OK;
+    rowmul_sub_kernel<<<ew_blocks(ctx, rows * D), EW_THREADS, 0, ctx->stream>>>((const u64*)d_a, (const u64*)d_b, (const u64*)d_c,
+                                                                             (u64*)d_out, rows, D);
+    CGB_CHECK_LAUNCH(ctx, "rowmul_sub_kernel");
     return CGB_OK;
 }
 int cgb_sub_pair(cgb_ctx* ctx, const uint64_t* d_a0, const uint64_t* d_b0, uint64_t n0, const uint64_t* d_a1,

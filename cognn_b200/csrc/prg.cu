@@ -7,6 +7,9 @@
 //   block b: key = key, counter = (u32) b, nonce = { (u32) S, (u32)(S>>32), (u32)(b>>32) }.
 // One thread computes one 64-byte block in registers (ALU-bound, ~1000 integer ops per block); a warp stages its
 // 32 blocks through shared memory so global stores (and the loads of the fused mask-subtract) are coalesced.
+#include <algorithm>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace {
@@ -159,6 +162,58 @@ __global__ void __launch_bounds__(PRG_THREADS) prg_sum_kernel(const Key key, con
     }
 }
 
+// Several keystream fills in ONE launch (blockIdx.y = segment): everything the dealer emulation hands a side for one Beaver
+// triple or one OM correlation.  Per segment: out = PRG(a) [+ PRG(b)], and optionally out_b = PRG(b) alone -- the helper's own
+// share of a triple operand next to the opened sum the dealer needs for Z1 = (U0 + U1)(V0 + V1) - Z0.
+struct PrgSeg {
+    u64* out;
+    u64* out_b;
+    uint64_t n_words;
+    uint64_t stream_a, stream_b;
+    uint32_t has_b;
+};
+struct PrgMultiArgs {
+    PrgSeg seg[16];
+};
+__global__ void __launch_bounds__(PRG_THREADS) prg_multi_kernel(const Key key, const __grid_constant__ PrgMultiArgs a,
+                                                               const u64* __restrict__ stream_bias) {
+    const PrgSeg& sg = a.seg[blockIdx.y];
+    const uint64_t bias = stream_bias ? __ldg(stream_bias) : 0ull;
+    const uint64_t n_blks = (sg.n_words + 7) / 8;
+    __shared__ u64 stage[2][PRG_THREADS / 32][32][9];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t warps_total = (uint64_t)gridDim.x * (PRG_THREADS / 32);
+    for (uint64_t wb = (uint64_t)blockIdx.x * (PRG_THREADS / 32) + warp; wb * 32 < n_blks; wb += warps_total) {
+        const uint64_t blk = wb * 32 + lane;
+        uint32_t w[16];
+        chacha_block(key, sg.stream_a + bias, blk, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) stage[0][warp][lane][i] = (u64)w[2 * i] | ((u64)w[2 * i + 1] << 32);
+        if (sg.has_b) {
+            chacha_block(key, sg.stream_b + bias, blk, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) stage[1][warp][lane][i] = (u64)w[2 * i] | ((u64)w[2 * i + 1] << 32);
+        }
+        __syncwarp();
+        const uint64_t w0 = wb * 32 * 8;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int j = it * 32 + lane;
+            const uint64_t wi = w0 + j;
+            if (wi < sg.n_words) {
+                u64 v = stage[0][warp][j >> 3][j & 7];
+                if (sg.has_b) {
+                    const u64 vb = stage[1][warp][j >> 3][j & 7];
+                    if (sg.out_b) sg.out_b[wi] = vb;
+                    v += vb;
+                }
+                sg.out[wi] = v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 int launch_prg(cgb_ctx* ctx, int mode, const uint32_t key[8], uint64_t stream, uint64_t word_offset, const u64* in,
                u64* out, uint64_t n_words, PrgExtra ex = PrgExtra{}) {
     if (n_words == 0) return CGB_OK;
@@ -198,6 +253,38 @@ int cgb_prg_mask_sub(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, uint6
     return launch_prg(ctx, 1, key, stream, word_offset, (const u64*)d_in, (u64*)d_out, n_words);
 }
 
+int cgb_prg_fill_multi(cgb_ctx* ctx, const uint32_t key[8], const cgb_prg_seg* segs, uint32_t n_seg) {
+    CGB_REQUIRE(ctx, key && (segs || n_seg == 0), "cgb_prg_fill_multi: null argument");
+    for (uint32_t base = 0; base < n_seg; base += 16) {
+        PrgMultiArgs a;
+        memset(&a, 0, sizeof(a));
+        uint32_t cnt = 0;
+        uint64_t longest = 0;
+        for (uint32_t j = base; j < n_seg && cnt < 16; ++j) {
+            if (segs[j].n_words == 0) continue;
+            CGB_REQUIRE(ctx, segs[j].out, "cgb_prg_fill_multi: null output");
+            CGB_REQUIRE(ctx, segs[j].has_b || !segs[j].out_b, "cgb_prg_fill_multi: out_b without a second stream");
+            a.seg[cnt].out = (u64*)segs[j].out;
+            a.seg[cnt].out_b = (u64*)segs[j].out_b;
+            a.seg[cnt].n_words = segs[j].n_words;
+            a.seg[cnt].stream_a = segs[j].stream_a;
+            a.seg[cnt].stream_b = segs[j].stream_b;
+            a.seg[cnt].has_b = segs[j].has_b ? 1u : 0u;
+            longest = std::max<uint64_t>(longest, segs[j].n_words);
+            ++cnt;
+        }
+        if (cnt == 0) continue;
+        Key k;
+        for (int i = 0; i < 8; ++i) k.k[i] = key[i];
+        const uint64_t warps = ((longest + 7) / 8 + 31) / 32;
+        uint64_t bx = (warps + (PRG_THREADS / 32) - 1) / (PRG_THREADS / 32);
+        const uint64_t cap = std::max<uint64_t>(1, (uint64_t)ctx->num_sms * 16 / cnt);
+        if (bx > cap) bx = cap;
+        prg_multi_kernel<<<dim3((unsigned)bx, cnt), PRG_THREADS, 0, ctx->stream>>>(k, a, (const u64*)ctx->prg_bias);
+        CGB_CHECK_LAUNCH(ctx, "prg_multi_kernel");
+    }
+    return CGB_OK;
+}
 int cgb_ideal_relu_reshare(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, const uint64_t* d_a0, const uint64_t* d_a1,
                            const uint64_t* d_z0, const uint64_t* d_z1, uint64_t* d_out, uint64_t n_words) {
     CGB_REQUIRE(ctx, key && ((d_a0 && d_a1 && d_out) || n_words == 0), "cgb_ideal_relu_reshare: null argument");

@@ -232,7 +232,7 @@ struct Side {
     DMat delta, S, Smask;  // Smask: sum of the OM mask shares this side holds for its own block (dealt offline)
     // dealer emulation temporaries (offline phase): grow-only members, so that phase neither allocates nor synchronises
     // after the first epoch and can be replayed as a CUDA graph like the online phase
-    DMat dl_U0, dl_V0, dl_Z0, dl_a0, dl_b0, dl_c0, dl_zero_mat, dl_zero_vec, dl_negc, dl_r;
+    DMat dl_U0, dl_V0, dl_a0, dl_b0, dl_c0, dl_r;
 };
 
 struct PartyData {
@@ -333,23 +333,26 @@ struct SSGcnEngine::Impl {
     // ---- Beaver matmul (sci::twoPartyGCNMatMul, gcn.h:233,665,671,710): prepare -> exchange -> finish --------------
     // offline (dealer emulation): this side's share of the triple (U, V, Z = U V)
     void mm_deal(Side& s, uint64_t it, int sub, uint32_t M, uint32_t K, uint32_t N) {
-        if (s.share == 0) {
-            prg(K_MM_U0, it, s.owner, sub, s.mmU[sub], M, K);
-            prg(K_MM_V0, it, s.owner, sub, s.mmV[sub], K, N);
-            prg(K_MM_Z0, it, s.owner, sub, s.mmZ[sub], M, N);
+        auto sid = [&](uint64_t kind) { return stream_id(kind, it, s.owner, sub); };
+        s.mmU[sub].resize(ctx, M, K);
+        s.mmV[sub].resize(ctx, K, N);
+        s.mmZ[sub].resize(ctx, M, N);
+        if (s.share == 0) {  // one launch: the three keystreams of this side's triple share
+            cgb_prg_seg sg[3] = {{s.mmU[sub].p, nullptr, s.mmU[sub].n(), sid(K_MM_U0), 0, 0},
+                                 {s.mmV[sub].p, nullptr, s.mmV[sub].n(), sid(K_MM_V0), 0, 0},
+                                 {s.mmZ[sub].p, nullptr, s.mmZ[sub].n(), sid(K_MM_Z0), 0, 0}};
+            ck(ctx, cgb_prg_fill_multi(ctx, key, sg, 3), "cgb_prg_fill_multi");
         } else {
-            // Z1 = (U0+U1)(V0+V1) - Z0
-            DMat &U0 = s.dl_U0, &V0 = s.dl_V0, &Z0 = s.dl_Z0;
-            prg(K_MM_U0, it, s.owner, sub, U0, M, K);
-            prg(K_MM_V0, it, s.owner, sub, V0, K, N);
-            prg(K_MM_Z0, it, s.owner, sub, Z0, M, N);
-            prg(K_MM_U1, it, s.owner, sub, s.mmU[sub], M, K);
-            prg(K_MM_V1, it, s.owner, sub, s.mmV[sub], K, N);
-            vadd(U0.p, s.mmU[sub].p, U0.p, U0.n());
-            vadd(V0.p, s.mmV[sub].p, V0.p, V0.n());
-            s.mmZ[sub].resize(ctx, M, N);
-            ck(ctx, cgb_matmul(ctx, U0.p, V0.p, s.mmZ[sub].p, M, K, N, 0, 0), "cgb_matmul(dealer)");
-            vsub(s.mmZ[sub].p, Z0.p, s.mmZ[sub].p, s.mmZ[sub].n());
+            // Z1 = (U0+U1)(V0+V1) - Z0: one launch makes U1, V1 and the opened sums U0+U1, V0+V1; the product; Z0 comes off
+            // as a keystream subtraction in place
+            DMat &U = s.dl_U0, &V = s.dl_V0;
+            U.resize(ctx, M, K);
+            V.resize(ctx, K, N);
+            cgb_prg_seg sg[2] = {{U.p, s.mmU[sub].p, U.n(), sid(K_MM_U0), sid(K_MM_U1), 1},
+                                 {V.p, s.mmV[sub].p, V.n(), sid(K_MM_V0), sid(K_MM_V1), 1}};
+            ck(ctx, cgb_prg_fill_multi(ctx, key, sg, 2), "cgb_prg_fill_multi");
+            ck(ctx, cgb_matmul(ctx, U.p, V.p, s.mmZ[sub].p, M, K, N, 0, 0), "cgb_matmul(dealer)");
+            ck(ctx, cgb_prg_mask_sub(ctx, key, sid(K_MM_Z0), 0, s.mmZ[sub].p, s.mmZ[sub].p, s.mmZ[sub].n()), "cgb_prg_mask_sub");
         }
     }
     // online: [E_i | F_i] = [A - U | B - V] in one message
@@ -375,30 +378,26 @@ struct SSGcnEngine::Impl {
 
     // ---- Beaver row scaling (sci::twoPartyGCNVectorScale, gcn.h:247,476): scaler private to the owner -------------
     void rm_deal(Side& s, uint64_t it, int sub, uint32_t rows, uint32_t D) {
+        auto sid = [&](uint64_t kind) { return stream_id(kind, it, s.owner, sub); };
+        s.rmA[sub].resize(ctx, rows, D);
+        s.rmB[sub].resize(ctx, 1, rows);
+        s.rmC[sub].resize(ctx, rows, D);
         if (s.share == 0) {
-            prg(K_RM_A0, it, s.owner, sub, s.rmA[sub], rows, D);
-            prg(K_RM_B0, it, s.owner, sub, s.rmB[sub], 1, rows);
-            prg(K_RM_C0, it, s.owner, sub, s.rmC[sub], rows, D);
+            cgb_prg_seg sg[3] = {{s.rmA[sub].p, nullptr, s.rmA[sub].n(), sid(K_RM_A0), 0, 0},
+                                 {s.rmB[sub].p, nullptr, s.rmB[sub].n(), sid(K_RM_B0), 0, 0},
+                                 {s.rmC[sub].p, nullptr, s.rmC[sub].n(), sid(K_RM_C0), 0, 0}};
+            ck(ctx, cgb_prg_fill_multi(ctx, key, sg, 3), "cgb_prg_fill_multi");
         } else {
-            DMat &a0 = s.dl_a0, &b0 = s.dl_b0, &c0 = s.dl_c0;
-            prg(K_RM_A0, it, s.owner, sub, a0, rows, D);
-            prg(K_RM_B0, it, s.owner, sub, b0, 1, rows);
-            prg(K_RM_C0, it, s.owner, sub, c0, rows, D);
-            prg(K_RM_A1, it, s.owner, sub, s.rmA[sub], rows, D);
-            prg(K_RM_B1, it, s.owner, sub, s.rmB[sub], 1, rows);
-            vadd(a0.p, s.rmA[sub].p, a0.p, a0.n());
-            vadd(b0.p, s.rmB[sub].p, b0.p, b0.n());
-            // c1 = (a0+a1) * (b0+b1)[row] - c0, with the generic kernel: out = c + e*b' + fv*a' + e*fv, a' = b' = 0, c = -c0
-            DMat &zero_mat = s.dl_zero_mat, &zero_vec = s.dl_zero_vec, &negc = s.dl_negc;
-            zero_mat.resize(ctx, rows, D);
-            zero_vec.resize(ctx, 1, rows);
-            ck(ctx, cgb_memset(ctx, zero_mat.p, 0, zero_mat.n() * 8), "memset");
-            ck(ctx, cgb_memset(ctx, zero_vec.p, 0, zero_vec.n() * 8), "memset");
-            negc.resize(ctx, rows, D);
-            vsub(zero_mat.p, c0.p, negc.p, negc.n());
-            s.rmC[sub].resize(ctx, rows, D);
-            ck(ctx, cgb_rowmul_beaver_finish(ctx, a0.p, b0.p, zero_mat.p, zero_vec.p, negc.p, s.rmC[sub].p, rows, D, 0, -1),
-               "rowmul(dealer)");
+            // c1 = (a0+a1) * (b0+b1)[row] - c0: one launch for a1, b1, the opened sums and c0, one for the product
+            DMat &a = s.dl_a0, &b = s.dl_b0, &c0 = s.dl_c0;
+            a.resize(ctx, rows, D);
+            b.resize(ctx, 1, rows);
+            c0.resize(ctx, rows, D);
+            cgb_prg_seg sg[3] = {{a.p, s.rmA[sub].p, a.n(), sid(K_RM_A0), sid(K_RM_A1), 1},
+                                 {b.p, s.rmB[sub].p, b.n(), sid(K_RM_B0), sid(K_RM_B1), 1},
+                                 {c0.p, nullptr, c0.n(), sid(K_RM_C0), 0, 0}};
+            ck(ctx, cgb_prg_fill_multi(ctx, key, sg, 3), "cgb_prg_fill_multi");
+            ck(ctx, cgb_rowmul_sub(ctx, a.p, b.p, c0.p, s.rmC[sub].p, rows, D), "cgb_rowmul_sub");
         }
     }
     void rm_prepare(Side& s, uint64_t, int sub, const DMat& x, const DMat* scaler) {
@@ -495,11 +494,14 @@ struct SSGcnEngine::Impl {
         PartyData& pd = party[s.owner];
         const uint32_t n_rows = pd.g.offsets[T];
         DMat& r = s.dl_r;
-        prg(K_OM_R, it, s.owner, 0, r, s.n, D);
+        r.resize(ctx, s.n, D);
         s.S.resize(ctx, n_rows, D);
-        for (int t = 0; t < T; ++t) {
-            const size_t off = (size_t)pd.g.offsets[t] * D, cnt = (size_t)n_of[t] * D;
-            ck(ctx, cgb_prg_fill(ctx, key, stream_id(K_OM_S, it, s.owner, t), 0, s.S.p + off, cnt), "prg S");
+        {   // one launch: the input mask r and the T output-mask blocks s_{p->t}
+            std::vector<cgb_prg_seg> sg;
+            sg.push_back({r.p, nullptr, r.n(), stream_id(K_OM_R, it, s.owner, 0), 0, 0});
+            for (int t = 0; t < T; ++t)
+                sg.push_back({s.S.p + (size_t)pd.g.offsets[t] * D, nullptr, (size_t)n_of[t] * D, stream_id(K_OM_S, it, s.owner, t), 0, 0});
+            ck(ctx, cgb_prg_fill_multi(ctx, key, sg.data(), (uint32_t)sg.size()), "cgb_prg_fill_multi");
         }
         s.delta.resize(ctx, n_rows, D);
         ck(ctx, cgb_gather_sum(ctx, pd.csr, r.p, nullptr, s.delta.p, D), "gather(dealer)");

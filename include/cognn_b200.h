@@ -281,6 +281,9 @@ int cgb_avg_public(cgb_ctx* ctx, const uint64_t* const* d_in, uint32_t n_in, uin
 int cgb_rowmul_beaver_finish_open(cgb_ctx* ctx, const uint64_t* d_mine, const uint64_t* d_peer, const uint64_t* d_a,
                                   const uint64_t* d_b, const uint64_t* d_c, uint64_t* d_out, uint64_t rows, uint32_t D,
                                   int share, int f);
+/* out = a * b[row] - c (rows x D; b has one word per row): the dealer's third row-scaling share c1 = (a0+a1)(b0+b1)[row] - c0. */
+int cgb_rowmul_sub(cgb_ctx* ctx, const uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_c, uint64_t* d_out,
+                   uint64_t rows, uint32_t D);
 /* one launch for the two halves of a Beaver message: out[0,n0) = a0 - b0, out[n0,n0+n1) = a1 - b1 (a1 == NULL: 0 - b1),
  * i.e. [X - U | W - V] of twoPartyGCNMatMul (gcn.h:233) or [x - a | s - b] of twoPartyGCNVectorScale (gcn.h:247). */
 int cgb_sub_pair(cgb_ctx* ctx, const uint64_t* d_a0, const uint64_t* d_b0, uint64_t n0, const uint64_t* d_a1,
@@ -306,6 +309,16 @@ int cgb_prg_fill(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, uint64_t 
 /* out = in - PRG(...): the server side of the OM online message (x1 - r) without materialising r */
 int cgb_prg_mask_sub(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, uint64_t word_offset,
                      const uint64_t* d_in, uint64_t* d_out, uint64_t n_words);
+/* Several fills in one launch: out = PRG(stream_a) [+ PRG(stream_b) if has_b], and out_b (optional) = PRG(stream_b) alone --
+ * what the dealer emulation hands one side for one Beaver triple or OM correlation (word offset 0). */
+typedef struct {
+    uint64_t* out;
+    uint64_t* out_b;
+    uint64_t n_words;
+    uint64_t stream_a, stream_b;
+    uint32_t has_b;
+} cgb_prg_seg;
+int cgb_prg_fill_multi(cgb_ctx* ctx, const uint32_t key[8], const cgb_prg_seg* segs, uint32_t n_seg);
 /* out = sum_j d_in[j] + sum_k PRG(key, streams[k], 0 ...): the GatherComp additions of one destination party
  * (gcn.h:456-463) with the OM mask shares regenerated in registers.  `streams` and `d_in` are HOST arrays (<= 16 each);
  * out may alias an input. */

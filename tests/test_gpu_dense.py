@@ -377,3 +377,37 @@ def test_scale_apply_avg_and_relu_reshare_match_oracle(cgb, oracle):
     gate = (z0 + z1).astype(np.int64) > 0
     want = np.where(gate, v, 0).astype(np.uint64) - ks
     assert np.array_equal(to_np(cgb.ideal_relu_reshare(key, 99, to_dev(a0), to_dev(a1), to_dev(z0), to_dev(z1))), want)
+
+
+def test_prg_fill_multi_and_rowmul_sub_match_oracle(cgb, oracle):
+    key = [7, 7, 7, 1, 2, 3, 4, 5]
+    rng = np.random.default_rng(21)
+    sizes = [1, 8, 9, 1433 * 16, 100_003, 7, 64, 5000, 12, 300, 4096, 33, 2, 77777, 640, 19, 250]  # 17 segments: two launches
+    outs = [cgb.empty(n) for n in sizes]
+    outs_b = [cgb.empty(n) if i % 3 == 0 else None for i, n in enumerate(sizes)]
+    segs = []
+    for i, n in enumerate(sizes):
+        if i % 2 == 0:
+            segs.append((outs[i], 1000 + i, 2000 + i, outs_b[i]))
+        else:
+            segs.append((outs[i], 1000 + i))
+    before = cgb.launches
+    cgb.prg_fill_multi(key, segs)
+    assert cgb.launches - before == 2
+    for i, n in enumerate(sizes):
+        a = oracle.prg_fill(key, 1000 + i, 0, n)
+        if i % 2 == 0:
+            b = oracle.prg_fill(key, 2000 + i, 0, n)
+            assert np.array_equal(to_np(outs[i]), a + b), i
+            if outs_b[i] is not None:
+                assert np.array_equal(to_np(outs_b[i]), b), i
+        else:
+            assert np.array_equal(to_np(outs[i]), a), i
+    # an unaligned destination (a block inside a larger matrix starting at an odd word)
+    big = cgb.empty(1001)
+    cgb.prg_fill_multi(key, [(big[1:], 55)])
+    assert np.array_equal(to_np(big[1:]), oracle.prg_fill(key, 55, 0, 1000))
+    rows, D = 1354, 7
+    a, c = rand_u64(rng, rows, D), rand_u64(rng, rows, D)
+    b = rand_u64(rng, rows)
+    assert np.array_equal(to_np(cgb.rowmul_sub(to_dev(a), to_dev(b), to_dev(c))), a * b[:, None] - c)
