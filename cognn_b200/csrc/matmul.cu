@@ -189,6 +189,10 @@ SplitPlan plan_splits(const cgb_ctx* ctx, uint32_t M, uint32_t K, uint32_t N) {
     if (N > 32) { p.BM = 128; p.BN = 64; }
     else if (N > 8) { p.BM = 128; p.BN = 16; }
     else { p.BM = 256; p.BN = 8; }
+    // narrow outputs over few rows (a party of a small graph: 1354 x 1433 x 16): 64-row tiles give twice the CTAs and shorter
+    // chains -- 41.7 -> 38.1 us for the Cora-shaped X W0, 8.4 -> 5.7 us for g W1^T (profiles/r3e_matmul_small_tiles.jsonl)
+    static const int small_env = getenv("CGB_MATMUL_SMALL_TILES") ? atoi(getenv("CGB_MATMUL_SMALL_TILES")) : 1;
+    if (small_env && N <= 32 && (M + 127) / 128 < (uint32_t)ctx->num_sms) p.BM = 64;
     if (M <= 32) p.BM = 32;  // weight gradients h^T v (M = hidden width or classes): a 128-row tile would be 3/4 padding
     const uint64_t tiles = (uint64_t)((M + p.BM - 1) / p.BM) * ((N + p.BN - 1) / p.BN);
     static const int want_env = getenv("CGB_MATMUL_SPLIT_WANT") ? atoi(getenv("CGB_MATMUL_SPLIT_WANT")) : 0;
@@ -253,10 +257,14 @@ int run_matmul(cgb_ctx* ctx, MatmulArgs a) {
         else if (pl.BN == 16) launch_cfg<32, 16, 16, 2, 1>(ctx, a);
         else launch_cfg<32, 8, 16, 1, 1>(ctx, a);
     } else if (pl.BN == 64) launch_cfg<128, 64, 16, 8, 4>(ctx, a);
-    else if (pl.BN == 16) launch_cfg<128, 16, 16, 4, 2>(ctx, a);  // (128x16 tm8 and 256x16 tm8 tiles measured slower: r2v probe)
+    else if (pl.BM == 64) {
+        if (pl.BN == 16) launch_cfg<64, 16, 16, 2, 2>(ctx, a);
+        else launch_cfg<64, 8, 16, 2, 1>(ctx, a);
+    } else if (pl.BN == 16) launch_cfg<128, 16, 16, 4, 2>(ctx, a);  // (128x16 tm8 / tn4 and 256x16 tiles measured slower: r2v, r3e probes)
     else launch_cfg<256, 8, 16, 8, 1>(ctx, a);
     CGB_CHECK_LAUNCH(ctx, "matmul_kernel");
-    ctx->last_kernel = pl.BM == 32 ? "matmul_kernel<32,*,16,*,*> (IMAD.WIDE u64 tiles, short M)" : pl.BN == 64 ? "matmul_kernel<128,64,16,8,4> (IMAD.WIDE u64 tiles)"
+    ctx->last_kernel = pl.BM == 32 ? "matmul_kernel<32,*,16,*,*> (IMAD.WIDE u64 tiles, short M)"
+                     : pl.BM == 64 ? "matmul_kernel<64,*,16,2,*> (IMAD.WIDE u64 tiles, few rows)" : pl.BN == 64 ? "matmul_kernel<128,64,16,8,4> (IMAD.WIDE u64 tiles)"
                                    : (pl.BN == 16 ? "matmul_kernel<128,16,16,4,2> (IMAD.WIDE u64 tiles)"
                                                   : "matmul_kernel<256,8,16,8,1> (IMAD.WIDE u64 tiles)");
     if (pl.splits > 1) {
