@@ -185,26 +185,38 @@ struct SplitPlan {
 };
 SplitPlan plan_splits(const cgb_ctx* ctx, uint32_t M, uint32_t K, uint32_t N) {
     constexpr uint32_t BK = 16;
+    static const int depth_env = getenv("CGB_MATMUL_SPLIT_DEPTH") ? atoi(getenv("CGB_MATMUL_SPLIT_DEPTH")) : 0;
+    static const int want_env = getenv("CGB_MATMUL_SPLIT_WANT") ? atoi(getenv("CGB_MATMUL_SPLIT_WANT")) : 0;
+    static const int small_env = getenv("CGB_MATMUL_SMALL_TILES") ? atoi(getenv("CGB_MATMUL_SMALL_TILES")) : 1;
+    const uint64_t depth = depth_env >= 1 && depth_env <= 64 ? (uint64_t)depth_env : 2;  // at least this many K steps per split
+    const uint64_t want = (want_env > 0 ? (uint64_t)want_env : 2ull) * ctx->num_sms;
+    const uint32_t sms = (uint32_t)ctx->num_sms;
     SplitPlan p{};
+    // Tile shape.  Every rule below is a measurement (tools/small_kernel_probe.py, profiles/r3*_probe*.jsonl):
     if (N > 32) { p.BM = 128; p.BN = 64; }
     else if (N > 8) { p.BM = 128; p.BN = 16; }
     else { p.BM = 256; p.BN = 8; }
-    // narrow outputs over few rows (a party of a small graph: 1354 x 1433 x 16): 64-row tiles give twice the CTAs and shorter
-    // chains -- 41.7 -> 38.1 us for the Cora-shaped X W0, 8.4 -> 5.7 us for g W1^T (profiles/r3e_matmul_small_tiles.jsonl)
-    static const int small_env = getenv("CGB_MATMUL_SMALL_TILES") ? atoi(getenv("CGB_MATMUL_SMALL_TILES")) : 1;
-    if (small_env && N <= 32 && (M + 127) / 128 < (uint32_t)ctx->num_sms) p.BM = 64;
-    if (M <= 32) p.BM = 32;  // weight gradients h^T v (M = hidden width or classes): a 128-row tile would be 3/4 padding
+    if (small_env) {
+        const uint32_t row_tiles = (M + 127) / 128;
+        // a 64-wide tile over a few hundred row tiles pads N and quantises into waves: 21168 x 16 x 40 is 166 CTAs of 128 x 64
+        // on 148 SMs (40 us); as 498 CTAs of 128 x 16 it takes 22 us.  Only when 16-wide tiles pad N clearly less.
+        if (N > 32 && (uint64_t)row_tiles * ((N + 63) / 64) < 2ull * sms && ((N + 15) / 16) * 16 * 5 <= ((N + 63) / 64) * 64 * 4) p.BN = 16;
+        // narrow outputs over few rows (a party of a small graph): 64-row tiles give twice the CTAs and shorter chains --
+        // Cora-shaped X W0 41.7 -> 38.1 us, H W1 9.6 -> 4.5 us, g W1^T 8.4 -> 5.7 us
+        if (N <= 32 && row_tiles < sms) p.BM = 64;
+    }
+    if (M <= 32) {  // weight gradients h^T v (M = hidden width or classes): a 128-row tile would be 3/4 padding
+        p.BM = 32;
+        p.BN = N > 32 ? 64 : (N > 8 ? 16 : 8);
+    }
+    // K is split when the output tiles alone cannot fill the machine; every split owns a plane of partial sums (<= 64 MB)
     const uint64_t tiles = (uint64_t)((M + p.BM - 1) / p.BM) * ((N + p.BN - 1) / p.BN);
-    static const int want_env = getenv("CGB_MATMUL_SPLIT_WANT") ? atoi(getenv("CGB_MATMUL_SPLIT_WANT")) : 0;
-    static const int depth_env = getenv("CGB_MATMUL_SPLIT_DEPTH") ? atoi(getenv("CGB_MATMUL_SPLIT_DEPTH")) : 0;
-    const uint64_t want = (want_env > 0 ? (uint64_t)want_env : 2ull) * ctx->num_sms;
-    const uint64_t depth = depth_env >= 1 && depth_env <= 64 ? (uint64_t)depth_env : 2;  // at least this many K steps per split
     uint32_t splits = 1;
     if (tiles < want && K >= 2 * depth * BK) {
-        uint64_t s = (want + tiles - 1) / tiles;
+        const uint64_t s = (want + tiles - 1) / tiles;
         const uint64_t max_s = K / (depth * BK);
         const uint64_t plane = (uint64_t)M * N * sizeof(u64);
-        const uint64_t max_mem = std::max<uint64_t>(1, (64ull << 20) / std::max<uint64_t>(plane, 1));  // <= 64 MB of partial planes
+        const uint64_t max_mem = std::max<uint64_t>(1, (64ull << 20) / std::max<uint64_t>(plane, 1));
         splits = (uint32_t)std::max<uint64_t>(1, std::min(std::min(s, max_s), max_mem));
     }
     uint32_t k_chunk = (K + splits - 1) / splits;
@@ -256,11 +268,11 @@ int run_matmul(cgb_ctx* ctx, MatmulArgs a) {
         if (pl.BN == 64) launch_cfg<32, 64, 16, 2, 4>(ctx, a);
         else if (pl.BN == 16) launch_cfg<32, 16, 16, 2, 1>(ctx, a);
         else launch_cfg<32, 8, 16, 1, 1>(ctx, a);
-    } else if (pl.BN == 64) launch_cfg<128, 64, 16, 8, 4>(ctx, a);
-    else if (pl.BM == 64) {
+    } else if (pl.BM == 64) {
         if (pl.BN == 16) launch_cfg<64, 16, 16, 2, 2>(ctx, a);
         else launch_cfg<64, 8, 16, 2, 1>(ctx, a);
-    } else if (pl.BN == 16) launch_cfg<128, 16, 16, 4, 2>(ctx, a);  // (128x16 tm8 / tn4 and 256x16 tiles measured slower: r2v, r3e probes)
+    } else if (pl.BN == 64) launch_cfg<128, 64, 16, 8, 4>(ctx, a);
+    else if (pl.BN == 16) launch_cfg<128, 16, 16, 4, 2>(ctx, a);  // (128x16 tm8 / tn4 and 256x16 tiles measured slower: r2v, r3e probes)
     else launch_cfg<256, 8, 16, 8, 1>(ctx, a);
     CGB_CHECK_LAUNCH(ctx, "matmul_kernel");
     ctx->last_kernel = pl.BM == 32 ? "matmul_kernel<32,*,16,*,*> (IMAD.WIDE u64 tiles, short M)"
