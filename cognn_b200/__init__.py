@@ -467,6 +467,21 @@ class Context:
         self.check(self.lib.cgb_prg_fill(self.handle, _lib.key_array(key), stream, word_offset, _ptr(out), n_words))
         return out
 
+    def prediction_metrics(self, s0, s1, labels, train_rows, val_rows, f=SCALER_BITS):
+        """(loss sum, hits full, hits train, hits test) from the two shares of the n x C probabilities and int32 labels."""
+        n, Cc = s0.shape
+        nb = C.c_uint32()
+        self.check(self.lib.cgb_prediction_metrics(self.handle, None, None, None, n, Cc, train_rows, val_rows, f, None, C.byref(nb)))
+        out = self.torch.zeros(max(nb.value, 1) * 4, dtype=self.torch.float64, device=self._dev())
+        self.check(self.lib.cgb_prediction_metrics(self.handle, _ptr(self._u64(s0)), _ptr(self._u64(s1)), _ptr(labels), n, Cc,
+                                                   train_rows, val_rows, f, _ptr(out), C.byref(nb)))
+        rec = out.cpu().numpy().reshape(-1, 4)
+        tot = [0.0, 0.0, 0.0, 0.0]
+        for r in rec:  # in block order, like the engine's host side
+            for k in range(4):
+                tot[k] += float(r[k])
+        return tuple(tot)
+
     def prg_fill_multi(self, key, segs):
         """segs: [(out, stream_a)] or [(out, stream_a, stream_b, out_b or None)]: out = PRG(a) [+ PRG(b)], out_b = PRG(b)."""
         m = 2**64 - 1

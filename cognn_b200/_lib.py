@@ -105,6 +105,8 @@ SIGNATURES = {
     "cgb_scale_apply_gradient": (C.c_int, [ctx_p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u64p, C.c_uint64, C.c_int, C.c_int]),
     "cgb_avg_public": (C.c_int, [ctx_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_int]),
     "cgb_ideal_relu_reshare": (C.c_int, [ctx_p, C.POINTER(C.c_uint32), C.c_uint64, u64p, u64p, u64p, u64p, u64p, C.c_uint64]),
+    "cgb_prediction_metrics": (C.c_int, [ctx_p, u64p, u64p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                                         C.c_void_p, C.POINTER(C.c_uint32)]),
     "cgb_prg_fill_multi": (C.c_int, [ctx_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32]),
     "cgb_rowmul_sub": (C.c_int, [ctx_p, u64p, u64p, u64p, u64p, C.c_uint64, C.c_uint32]),
     "cgb_copy_segments": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32]),

@@ -235,6 +235,48 @@ __global__ void __launch_bounds__(EW_THREADS) decode_kernel(const u64* __restric
         out[i] = decode_fixed(s0[i] + (s1 ? s1[i] : 0ull), f);
 }
 
+// Loss / accuracy of the opened prediction layer (optimize-gcn/gcn.h:603-632) on the device: one thread per vertex opens its row
+// p = decode(s0 + s1), replaces exact zeros by 0.001 (gcn.h:615), takes the first maximal class and -log p[label]; a fixed-order
+// tree in shared memory reduces the block, and every block writes {loss, hits full / train / test} -- the host adds the few
+// hundred block records in order, so the result does not depend on scheduling.  Replaces a D2H of all n x C probabilities and a
+// host loop over them that sat in the timed online phase (arxiv-shaped party: ~1 ms per epoch).
+constexpr int PM_THREADS = 256;
+__global__ void __launch_bounds__(PM_THREADS) prediction_metrics_kernel(const u64* __restrict__ s0, const u64* __restrict__ s1,
+                                                                       const int32_t* __restrict__ labels, uint32_t n, uint32_t C,
+                                                                       uint32_t train, uint32_t val, int f, double* __restrict__ out) {
+    __shared__ double sh[4][PM_THREADS];
+    const uint32_t i = blockIdx.x * PM_THREADS + threadIdx.x;
+    double loss = 0, full = 0, tr = 0, te = 0;
+    if (i < n) {
+        const u64* a = s0 + (size_t)i * C;
+        const u64* b = s1 + (size_t)i * C;
+        const uint32_t lab = (uint32_t)labels[i];
+        double best = 0, plab = 0;
+        uint32_t arg = 0;
+        for (uint32_t j = 0; j < C; ++j) {
+            double pj = decode_fixed(a[j] + b[j], f);
+            if (pj == 0) pj = 0.001;
+            if (j == 0 || pj > best) { best = pj; arg = j; }
+            if (j == lab) plab = pj;
+        }
+        loss = -log(fmax(plab, 1e-30));
+        const double ok = arg == lab ? 1.0 : 0.0;
+        full = ok;
+        if (i < train) tr = ok;
+        if (i >= train + val) te = ok;
+    }
+    sh[0][threadIdx.x] = loss; sh[1][threadIdx.x] = full; sh[2][threadIdx.x] = tr; sh[3][threadIdx.x] = te;
+    __syncthreads();
+    for (int w = PM_THREADS / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + w];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) out[(size_t)blockIdx.x * 4 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
 struct SumArgs {
     const u64* in[16];
     int n_in;
@@ -568,6 +610,19 @@ int cgb_decode(cgb_ctx* ctx, const uint64_t* d_v, double* d_out, uint64_t n, int
     if (n == 0) return CGB_OK;
     decode_kernel<<<ew_blocks(ctx, n), EW_THREADS, 0, ctx->stream>>>((const u64*)d_v, nullptr, d_out, n, f);
     CGB_CHECK_LAUNCH(ctx, "decode_kernel");
+    return CGB_OK;
+}
+int cgb_prediction_metrics(cgb_ctx* ctx, const uint64_t* d_s0, const uint64_t* d_s1, const int32_t* d_labels, uint32_t n,
+                           uint32_t C, uint32_t train_rows, uint32_t val_rows, int f, double* d_block_out, uint32_t* n_blocks) {
+    CGB_REQUIRE(ctx, n_blocks, "cgb_prediction_metrics: null n_blocks");
+    *n_blocks = (n + PM_THREADS - 1) / PM_THREADS;
+    if (!d_block_out) return CGB_OK;  // size query
+    CGB_REQUIRE(ctx, (d_s0 && d_s1 && d_labels) || n == 0, "cgb_prediction_metrics: null argument");
+    CGB_REQUIRE(ctx, C > 0 && f >= 0 && f < 63, "cgb_prediction_metrics: bad C/f");
+    if (n == 0) return CGB_OK;
+    prediction_metrics_kernel<<<*n_blocks, PM_THREADS, 0, ctx->stream>>>((const u64*)d_s0, (const u64*)d_s1, d_labels, n, C,
+                                                                         train_rows, val_rows, f, d_block_out);
+    CGB_CHECK_LAUNCH(ctx, "prediction_metrics_kernel");
     return CGB_OK;
 }
 int cgb_share_split(cgb_ctx* ctx, const double* d_x, uint64_t n, int f, const uint32_t key[8], uint64_t stream,

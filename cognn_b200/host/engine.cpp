@@ -972,7 +972,10 @@ static void online_iteration(SSGcnEngine::Impl& im, uint64_t it) {
             im.comm->exchange();
             im.for_sides([&](Side& s) {  // getPlainShareVecVec (gcn.h:604): decode on the device, copy to pinned host memory
                 if (s.share != 0) return;
-                s.prob.resize(ctx, s.n, Dout);
+                // loss / accuracy on the device (cgb_prediction_metrics): a few hundred block records come back, not n x C doubles
+                uint32_t nb = 0;
+                ck(ctx, cgb_prediction_metrics(ctx, nullptr, nullptr, nullptr, s.n, Dout, 0, 0, im.f, nullptr, &nb), "metrics size");
+                s.prob.resize(ctx, std::max<uint32_t>(nb, 1), 4);
                 if (s.h_prob_cap < s.prob.n()) {
                     if (g_capturing) throw std::runtime_error("engine: host buffer grew while an iteration was being captured");
                     if (s.h_prob) cgb_host_free(s.h_prob);
@@ -981,8 +984,10 @@ static void online_iteration(SSGcnEngine::Impl& im, uint64_t it) {
                     s.h_prob = (double*)hp;
                     s.h_prob_cap = s.prob.n();
                 }
-                ck(ctx, cgb_open_decode(ctx, s.P.p, s.Ppeer.p, (double*)s.prob.p, s.P.n(), im.f), "open_decode");
-                if (s.prob.n()) ck(ctx, cgb_d2h(ctx, s.h_prob, s.prob.p, s.prob.n() * 8), "d2h");
+                const uint32_t train = (uint32_t)(s.n * im.cfg.train_ratio), val = (uint32_t)(s.n * im.cfg.val_ratio);
+                ck(ctx, cgb_prediction_metrics(ctx, s.P.p, s.Ppeer.p, im.party.at(s.owner).d_labels, s.n, Dout, train, val, im.f,
+                                               (double*)s.prob.p, &nb), "cgb_prediction_metrics");
+                if (s.n) ck(ctx, cgb_d2h(ctx, s.h_prob, s.prob.p, (size_t)nb * 4 * 8), "d2h");
                 im.metrics_pending.push_back(s.owner);
             });
         }
@@ -1035,27 +1040,19 @@ static void online_iteration(SSGcnEngine::Impl& im, uint64_t it) {
 // loss / accuracy the owner prints after the prediction layer (gcn.h:603-632), from the opened probabilities
 static Metrics owner_metrics(SSGcnEngine::Impl& im, uint64_t it, int owner, bool verbose) {
     Side& s = im.own.at(owner);
-    const uint32_t C = im.C, n = s.n;
-    double* prob = s.h_prob;
-    const auto& labels = im.party.at(owner).labels;
+    const uint32_t n = s.n;
     const uint64_t train = (uint64_t)(n * im.cfg.train_ratio), val = (uint64_t)(n * im.cfg.val_ratio);
-    double loss = 0;
-    uint64_t hit_full = 0, hit_train = 0, hit_test = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        uint32_t best = 0;
-        for (uint32_t j = 0; j < C; ++j) {
-            double& pj = prob[(size_t)i * C + j];
-            if (pj == 0) pj = 0.001;  // gcn.h:615
-            if (pj > prob[(size_t)i * C + best]) best = j;
-        }
-        loss -= std::log(std::max(prob[(size_t)i * C + labels[i]], 1e-30));
-        const bool ok = best == (uint32_t)labels[i];
-        hit_full += ok;
-        if (i < train) hit_train += ok;
-        if (i >= train + val) hit_test += ok;
+    // block records {loss, hits full, hits train, hits test} of cgb_prediction_metrics, added in block order
+    const uint32_t nb = (n + 255) / 256;
+    double loss = 0, hit_full = 0, hit_train = 0, hit_test = 0;
+    for (uint32_t b = 0; b < nb; ++b) {
+        loss += s.h_prob[4 * b];
+        hit_full += s.h_prob[4 * b + 1];
+        hit_train += s.h_prob[4 * b + 2];
+        hit_test += s.h_prob[4 * b + 3];
     }
-    Metrics m{it, owner, n ? loss / n : 0.0, n ? (double)hit_full / n : 0.0, train ? (double)hit_train / train : 0.0,
-              n > train + val ? (double)hit_test / (n - train - val) : 0.0};
+    Metrics m{it, owner, n ? loss / n : 0.0, n ? hit_full / n : 0.0, train ? hit_train / train : 0.0,
+              n > train + val ? hit_test / (n - train - val) : 0.0};
     if (verbose) {  // the reference's log lines (gcn.h:620-632)
         printf("cross-entropy-loss = %lf\n", m.loss);
         printf("full set accuracy = %lf\n", m.acc_full);

@@ -302,6 +302,13 @@ int cgb_decode(cgb_ctx* ctx, const uint64_t* d_v, double* d_out, uint64_t n, int
 int cgb_share_split(cgb_ctx* ctx, const double* d_x, uint64_t n, int f, const uint32_t key[8], uint64_t stream,
                     uint64_t word_offset, uint64_t* d_s0, uint64_t* d_s1);
 int cgb_open_decode(cgb_ctx* ctx, const uint64_t* d_s0, const uint64_t* d_s1, double* d_out, uint64_t n, int f);
+/* Loss / accuracy the owner prints after the prediction layer (gcn.h:603-632), from the two shares of the n x C probabilities:
+ * every 256-vertex block writes 4 doubles {sum of -log p[label], hits over all / the first train_rows / the rows from
+ * train_rows + val_rows on} to d_block_out (zeros count as 0.001, gcn.h:615; first maximal class wins); the caller adds the
+ * *n_blocks records in order.  d_block_out == NULL only reports *n_blocks. */
+int cgb_prediction_metrics(cgb_ctx* ctx, const uint64_t* d_s0, const uint64_t* d_s1, const int32_t* d_labels, uint32_t n,
+                           uint32_t C, uint32_t train_rows, uint32_t val_rows, int f, double* d_block_out,
+                           uint32_t* n_blocks);
 
 /* ---- (4) device PRG (ChaCha20 block function, RFC 8439; stream layout in DESIGN.md) ------------------------ */
 int cgb_prg_fill(cgb_ctx* ctx, const uint32_t key[8], uint64_t stream, uint64_t word_offset, uint64_t* d_out,

@@ -411,3 +411,31 @@ def test_prg_fill_multi_and_rowmul_sub_match_oracle(cgb, oracle):
     a, c = rand_u64(rng, rows, D), rand_u64(rng, rows, D)
     b = rand_u64(rng, rows)
     assert np.array_equal(to_np(cgb.rowmul_sub(to_dev(a), to_dev(b), to_dev(c))), a * b[:, None] - c)
+
+
+@pytest.mark.parametrize("n,C", [(1, 3), (255, 7), (256, 7), (1354, 7), (21168, 40)])
+def test_prediction_metrics_match_host_loop(cgb, n, C):
+    """gcn.h:603-632 as the engine's host loop computed it until round 2: zeros -> 0.001, first maximal class, -log p[label]."""
+    import torch
+
+    rng = np.random.default_rng(n + C)
+    f = 16
+    p = rng.random((n, C))
+    p /= p.sum(1, keepdims=True)
+    fixed = np.floor(p * (1 << f)).astype(np.int64)
+    fixed[rng.integers(0, n, size=max(1, n // 10)), rng.integers(0, C, size=max(1, n // 10))] = 0  # exact zeros
+    if n > 5:
+        fixed[3] = fixed[3, 0]  # a tie over the whole row: the first class wins
+    s1 = rand_u64(rng, n, C)
+    s0 = fixed.view(np.uint64) - s1
+    labels = rng.integers(0, C, size=n).astype(np.int32)
+    train, val = int(n * 0.4), int(n * 0.2)
+    pd = fixed.astype(np.float64) / (1 << f)
+    pd[pd == 0] = 0.001
+    arg = pd.argmax(1)  # first maximum
+    ok = arg == labels
+    want = (float(-np.log(np.maximum(pd[np.arange(n), labels], 1e-30)).sum()), float(ok.sum()), float(ok[:train].sum()),
+            float(ok[train + val:].sum()))
+    got = cgb.prediction_metrics(to_dev(s0), to_dev(s1), torch.from_numpy(labels).cuda(), train, val, f)
+    assert got[1:] == want[1:]
+    assert abs(got[0] - want[0]) <= 1e-9 * max(1.0, abs(want[0]))
