@@ -1,5 +1,6 @@
-// comm.cpp -- message planes for the engine: LoopbackComm (all parties in one process, device-to-device copies) and
-// NcclComm (one party per process / GPU: ncclSend / ncclRecv grouped per protocol round over NVLink).  They replace the
+// comm.cpp -- message planes for the engine: LoopbackComm (all parties in one process, one segmented copy launch per round) and
+// NcclComm (one party per process / GPU: ncclSend / ncclRecv grouped per protocol round over NVLink, or -- after reserve() --
+// peer-memory rounds: pushes into the receiver's slot and flags, cgb_peer_round).  They replace the
 // reference's host TCP planes (CommSync over osuCrypto::Channel, include/comm_sync.h:212-277, engine.h:157-201; TaskComm).
 // Message bytes are the raw little-endian row-major u64 buffer (no Boost archive framing).
 #include <cuda_runtime.h>
@@ -103,9 +104,9 @@ public:
 
     // ---- peer-memory plane --------------------------------------------------------------------------------------------
     // Every ordered pair of parties gets a double-buffered slot pair in the receiver's memory, mapped by the sender with CUDA
-    // IPC, plus a data flag (receiver side) and an acknowledge flag (sender side).  A round is then two launches per rank
-    // (cgb_peer_round push, then recv) instead of one NCCL group: no proxy thread, no channel set-up, a few microseconds of
-    // latency, and the round counters live on the device so the launches replay from a CUDA graph.  Handles travel once, over
+    // IPC, plus a data flag (receiver side) and an acknowledge flag (sender side).  A round is then ONE launch per rank
+    // (cgb_peer_round: the pushes first, then the consumption of what arrives) instead of an NCCL group: no proxy thread, no
+    // channel set-up, and the round counters live on the device so the launches replay from a CUDA graph.  Handles travel once, over
     // NCCL.  Pairs whose messages do not fit the slot (or more than 16 messages) keep using ncclSend / ncclRecv, and so does
     // everything when any rank could not map its peers (different nodes, IPC disabled) or when the plane is off (see below).
     void reserve(size_t max_words) override {
