@@ -389,7 +389,7 @@ def secure_gcn_epoch_probe(timeout_s=300):
         env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
         rec = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-        keep = ("shape", "parties", "plane", "N", "E", "cfg", "iterations", "online_s", "online_mode", "offline_dealer_s", "launches",
+        keep = ("shape", "parties", "plane", "N", "E", "cfg", "iterations", "online_s", "online_gpu_s_this_rank", "online_mode", "offline_dealer_s", "launches",
                 "rounds", "graph_replays", "cpu_oracle", "bit_exact_vs_oracle", "note")
         out = {k: rec[k] for k in keep if k in rec}
         out["unit"] = "s per epoch (online phase; offline = trusted-dealer emulation, reported beside it)"
@@ -420,7 +420,7 @@ def secure_gcn_epoch_nccl(rank, P, timeout_s=420):
         if rank != 0:
             return None
         rec = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-        keep = ("shape", "parties", "plane", "N", "E", "inter_party_edges", "cfg", "iterations", "online_s", "online_mode",
+        keep = ("shape", "parties", "plane", "N", "E", "inter_party_edges", "cfg", "iterations", "online_s", "online_gpu_s_this_rank", "online_mode",
                 "offline_dealer_s", "launches", "rounds", "graph_replays", "bit_exact_vs_oracle", "checked", "note")
         out = {"config": which}
         out.update({k: rec[k] for k in keep if k in rec})

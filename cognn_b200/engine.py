@@ -21,7 +21,7 @@ class CgeConfig(C.Structure):
 
 ENGINE_SYMBOLS = ["cge_last_error", "cge_nccl_unique_id", "cge_create_loopback", "cge_create_nccl", "cge_destroy",
                   "cge_add_party", "cge_setup", "cge_run", "cge_download", "cge_message_count", "cge_message_info",
-                  "cge_message_data", "cge_words_sent", "cge_rounds", "cge_launch_count", "cge_seconds_online", "cge_seconds_offline", "cge_seconds_residual_host",
+                  "cge_message_data", "cge_words_sent", "cge_rounds", "cge_launch_count", "cge_seconds_online", "cge_seconds_online_gpu", "cge_seconds_offline", "cge_seconds_residual_host",
                   "cge_metrics_count", "cge_metrics_get", "cge_build_party_graph", "cge_graph_replays", "cge_plane"]
 
 
@@ -41,7 +41,7 @@ def load_host():
     for n in ("cge_message_count", "cge_words_sent", "cge_rounds", "cge_launch_count", "cge_metrics_count", "cge_graph_replays"):
         getattr(h, n).restype = C.c_uint64
         getattr(h, n).argtypes = [C.c_void_p]
-    for n in ("cge_seconds_online", "cge_seconds_offline", "cge_seconds_residual_host"):
+    for n in ("cge_seconds_online", "cge_seconds_online_gpu", "cge_seconds_offline", "cge_seconds_residual_host"):
         getattr(h, n).restype = C.c_double
         getattr(h, n).argtypes = [C.c_void_p]
     h.cge_create_loopback.argtypes = [C.c_int, C.c_void_p, C.c_int, C.POINTER(CgeConfig), C.POINTER(C.c_void_p)]
@@ -182,6 +182,10 @@ class Engine:
     @property
     def seconds_online(self):
         return float(self.h.cge_seconds_online(self.e))
+
+    @property
+    def seconds_online_gpu(self):
+        return float(self.h.cge_seconds_online_gpu(self.e))
 
     @property
     def seconds_residual_host(self):

@@ -155,6 +155,7 @@ const char* cge_plane(cge_engine* h) { return h->comm->plane(); }
 uint64_t cge_launch_count(cge_engine* h) { return h->eng->eager_launches() + h->eng->replayed_launches(); }
 uint64_t cge_graph_replays(cge_engine* h) { return h->eng->graph_replays(); }
 double cge_seconds_online(cge_engine* h) { return h->eng->seconds_online; }
+double cge_seconds_online_gpu(cge_engine* h) { return h->eng->seconds_online_gpu; }
 double cge_seconds_offline(cge_engine* h) { return h->eng->seconds_offline; }
 double cge_seconds_residual_host(cge_engine* h) { return h->eng->seconds_residual_host(); }
 

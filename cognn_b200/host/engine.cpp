@@ -250,6 +250,7 @@ struct SSGcnEngine::Impl {
     cgb_ctx* main_ctx = nullptr;
     bool branches = !(getenv("COGNN_B200_BRANCHES") && atoi(getenv("COGNN_B200_BRANCHES")) == 0);
     cudaEvent_t fork_ev = nullptr;
+    cudaEvent_t ev_on[2] = {nullptr, nullptr};  // around the online phase of an iteration (seconds_online_gpu)
     std::vector<cgb_ctx*> side_ctxs;
     uint64_t total_launches() const {
         uint64_t n = cgb_ctx_launch_count(main_ctx);
@@ -776,6 +777,8 @@ SSGcnEngine::~SSGcnEngine() {
     }
     for (cgb_ctx* c : impl_->side_ctxs) cgb_ctx_destroy(c);
     if (impl_->fork_ev) cudaEventDestroy(impl_->fork_ev);
+    for (cudaEvent_t e : impl_->ev_on)
+        if (e) cudaEventDestroy(e);
     delete impl_;
 }
 
@@ -1136,10 +1139,20 @@ void SSGcnEngine::run(uint64_t n_iters) {
         seconds_offline += std::chrono::duration<double>(t0 - t_deal).count();
 
         const bool replay = use_graph && im.graph[ph].exec;
+        if (!im.ev_on[0]) {
+            ckc(cudaEventCreate(&im.ev_on[0]), "cudaEventCreate");
+            ckc(cudaEventCreate(&im.ev_on[1]), "cudaEventCreate");
+        }
+        ckc(cudaEventRecord(im.ev_on[0], stream), "cudaEventRecord");
         run_phase(im, stream, use_graph, im.graph[ph], true, [&] { online_iteration(im, it); });
+        ckc(cudaEventRecord(im.ev_on[1], stream), "cudaEventRecord");
         if (replay && ph == 1)
             for (auto& kv : im.own) im.metrics_pending.push_back(kv.first);
         ck(ctx, cgb_ctx_sync(ctx), "sync");
+        {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, im.ev_on[0], im.ev_on[1]) == cudaSuccess) seconds_online_gpu += ms * 1e-3;
+        }
         for (int owner : im.metrics_pending) metrics_.push_back(owner_metrics(im, it, owner, verbose));
         im.metrics_pending.clear();
         const double dt = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();

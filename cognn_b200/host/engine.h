@@ -103,6 +103,7 @@ public:
     const std::vector<Metrics>& metrics() const { return metrics_; }
     bool verbose = false;          // print the reference's log lines ("::iteration took", accuracy)
     double seconds_online = 0, seconds_offline = 0;
+    double seconds_online_gpu = 0;  // the same online phases between two CUDA events on the main stream (no host launch / sync latency)
     double seconds_residual_host() const;   // 0: kept for the C ABI (the stand-ins moved to the device)
     // kernels that ran inside replayed CUDA graphs of the online phase (not seen by cgb_ctx_launch_count), and replays
     uint64_t replayed_launches() const;

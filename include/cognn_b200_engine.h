@@ -53,6 +53,7 @@ uint64_t cge_launch_count(cge_engine* h);   /* kernels launched, including those
  * occurrence, replayed afterwards; COGNN_B200_GRAPHS=0 or record_messages keep the eager path).  Number of replays: */
 uint64_t cge_graph_replays(cge_engine* h);
 double cge_seconds_online(cge_engine* h);   /* host wall time of the online phases, stream-synchronised */
+double cge_seconds_online_gpu(cge_engine* h); /* the same phases between two CUDA events on the engine's main stream */
 double cge_seconds_offline(cge_engine* h);  /* dealer emulation (correlation generation), excluded from online */
 double cge_seconds_residual_host(cge_engine* h); /* always 0: the 2PC-residual stand-ins run on the device (cgb_ideal_*) */
 uint64_t cge_metrics_count(cge_engine* h);

@@ -69,8 +69,9 @@ def main():
 
     def measured(n):
         on0, off0, l0, w0, r0, h0 = e.seconds_online, e.seconds_offline, e.launches, e.words_sent, e.rounds, e.seconds_residual_host
+        g0 = e.seconds_online_gpu
         e.run(n)
-        return {"online_s": e.seconds_online - on0, "offline_s": e.seconds_offline - off0,
+        return {"online_s": e.seconds_online - on0, "offline_s": e.seconds_offline - off0, "online_gpu_s": e.seconds_online_gpu - g0,
                 "residual_host_s": e.seconds_residual_host - h0,
                 "launches": e.launches - l0, "words_sent": e.words_sent - w0, "rounds": e.rounds - r0}
 
@@ -90,6 +91,7 @@ def main():
            "plane": e.plane if world > 1 else "loopback(1 GPU)", "N": g["N"], "E": g["E"],
            "inter_party_edges": g["inter_party_edges"], "cfg": {k: g["cfg"][k] for k in ("input_dim", "hidden_dim", "num_labels")},
            "iterations": iters, "online_s": online,
+           "online_gpu_s_this_rank": best["online_gpu_s"],
            "online_mode": "CUDA-graph replay of each iteration's online phase" if graphs else "eager launches",
            "online_s_per_epoch_this_rank": [round(x["online_s"], 6) for x in per_epoch], "graph_replays": e.graph_replays,
            "of_which_host_2pc_residual_standin_s": best["residual_host_s"], "offline_dealer_s": min(x["offline_s"] for x in warm),
